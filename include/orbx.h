@@ -1,0 +1,149 @@
+/*
+ * orbx.h -- C ABI of the B200-native ORB front end (liborbx.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, int status codes, no C++/torch types.
+ * The C++ classes ORBSlam::ORBextractor / ORBSlam::ORBmatcher in orbslam_in_practice_b200/cpp/
+ * keep the reference's signatures and forward to these entry points.  Reference interfaces
+ * replaced (paths relative to the reference tree):
+ *
+ *   orbx_create / orbx_tables        ORBextractor::ORBextractor        include/ORBextractor.h:35-36, src/ORBextractor.cpp:360-420
+ *                                    GetLevels/GetScaleFactor(s)/...   include/ORBextractor.h:47-69
+ *   orbx_extract_host/_device        ORBextractor::operator()          include/ORBextractor.h:43-45, src/ORBextractor.cpp:1001-1065
+ *   orbx_download_level              mvImagePyramid (public member)    include/ORBextractor.h:71, src/ORBextractor.cpp:1071-1096
+ *   orbm_hamming_pairs_host          ORBmatcher::DescriptorDistance    include/ORBmatcher.h:19, src/ORBmatcher.cpp:128-144
+ *   orbm_knn2_* / orbm_ratio_select  best-2 scan + acceptance          src/ORBmatcher.cpp:37-67
+ *   orbm_merge_shards_device         (database sharding; no reference counterpart)
+ *
+ * All functions return 0 on success or a negative ORBX_E_* code; nothing throws across the ABI.
+ * Handles are NOT thread-safe (the reference extractor is stateful too: one call in flight).
+ * There is no CPU fallback: every entry point needs a CUDA device of compute capability 10.0.
+ */
+#ifndef ORBX_H
+#define ORBX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORBX_OK 0
+#define ORBX_E_INVALID (-1)   /* bad argument */
+#define ORBX_E_CUDA (-2)      /* CUDA runtime error (see orbx_last_cuda_error) */
+#define ORBX_E_NOMEM (-3)     /* allocation failed */
+#define ORBX_E_CAPACITY (-4)  /* frame/batch larger than the handle was created for */
+#define ORBX_E_NODEVICE (-5)  /* no usable sm_100 device */
+#define ORBX_E_UNSUPPORTED (-6)
+
+#define ORBX_MAX_LEVELS 16
+#define ORBX_EDGE_THRESHOLD 19 /* pyramid border, src/ORBextractor.cpp:24 */
+
+typedef struct {
+    int32_t nfeatures;
+    float scale_factor;
+    int32_t nlevels;
+    int32_t ini_th_fast;
+    int32_t min_th_fast;
+} orbx_params;
+
+/* Binary layout identical to cv::KeyPoint (28 bytes): the C++ wrapper memcpy's these. */
+typedef struct {
+    float x, y, size, angle, response;
+    int32_t octave, class_id;
+} orbx_keypoint;
+
+/* FAST candidate / octree survivor, coordinates relative to (minBorderX, minBorderY) = (16,16) of
+ * its level, exactly the values held by vToDistributeKeys (src/ORBextractor.cpp:777-782). */
+typedef struct {
+    int16_t x, y;
+    int32_t score;
+} orbx_cand;
+
+typedef struct orbx_extractor orbx_extractor;
+typedef struct orbm_matcher orbm_matcher;
+
+const char *orbx_strerror(int code);
+const char *orbx_last_cuda_error(void);
+int orbx_version(void);
+/* number of visible CUDA devices with compute capability 10.x (0 if none / no driver) */
+int orbx_device_count(void);
+
+/* ---------------- extractor ---------------- */
+int orbx_create(const orbx_params *params, int max_width, int max_height, int max_batch, int device,
+                orbx_extractor **out);
+int orbx_destroy(orbx_extractor *ex);
+int orbx_nlevels(const orbx_extractor *ex);
+/* row stride (in keypoints) of the per-frame output arrays: sum over levels of the octree bound */
+int orbx_capacity(const orbx_extractor *ex);
+/* arrays of nlevels entries (umax: 16); any pointer may be NULL */
+int orbx_tables(const orbx_extractor *ex, float *scale, float *inv_scale, float *sigma2, float *inv_sigma2,
+                int32_t *features_per_level, int32_t *umax);
+
+/* operator() on a batch of same-sized 8-bit grayscale frames held in HOST memory.
+ *   imgs: frame f, row y at imgs + f*frame_stride + y*row_pitch
+ *   kps  [nframes][capacity], desc [nframes][capacity][32], counts [nframes] (host)
+ * Copies in, runs the kernels, copies out and synchronises before returning.  Zero-sized images
+ * return ORBX_OK with counts = 0 (the reference returns silently, src/ORBextractor.cpp:1004). */
+int orbx_extract_host(orbx_extractor *ex, const uint8_t *imgs, size_t row_pitch, size_t frame_stride,
+                      int width, int height, int nframes,
+                      orbx_keypoint *kps, uint8_t *desc, int32_t *counts);
+
+/* Same with DEVICE pointers; asynchronous on `stream` (a cudaStream_t; NULL = the handle's stream). */
+int orbx_extract_device(orbx_extractor *ex, const uint8_t *d_imgs, size_t row_pitch, size_t frame_stride,
+                        int width, int height, int nframes,
+                        orbx_keypoint *d_kps, uint8_t *d_desc, int32_t *d_counts, void *stream);
+
+/* Enable (1) / disable (0) writing the 19-px reflect-101 border of the pyramid levels.  The
+ * extractor itself never reads it; it exists for consumers of mvImagePyramid.  Default: 1. */
+int orbx_set_pyramid_border(orbx_extractor *ex, int enabled);
+
+/* --- stage access of the LAST extract call (synchronous; for mvImagePyramid and parity tests) --- */
+int orbx_level_dims(const orbx_extractor *ex, int level, int *width, int *height);
+/* copies level pixels of `frame` to host.  border = 0 -> width x height; border = 19 -> the
+ * (width+38) x (height+38) bordered image.  blurred != 0 -> the Gaussian-blurred level (border 0). */
+int orbx_download_level(orbx_extractor *ex, int frame, int level, int blurred, int border,
+                        uint8_t *dst, size_t dst_pitch);
+/* device pointer to pixel (0,0) of the level interior of `frame` and its row pitch */
+int orbx_level_device_ptr(orbx_extractor *ex, int frame, int level, const uint8_t **ptr, size_t *pitch);
+/* FAST candidates in reference order (cell row-major, then row-major inside the cell) */
+int orbx_download_candidates(orbx_extractor *ex, int frame, int level, orbx_cand *out, int cap, int *n);
+/* octree survivors in reference list order */
+int orbx_download_kept(orbx_extractor *ex, int frame, int level, orbx_cand *out, int cap, int *n);
+/* upper bound of candidates a level can produce (sizing for orbx_download_candidates) */
+int orbx_max_candidates(const orbx_extractor *ex, int level);
+/* kernels launched by this handle since creation (for bench.py's gpu_launches) */
+long long orbx_launch_count(const orbx_extractor *ex);
+
+/* ---------------- matcher ---------------- */
+int orbm_create(int max_queries, int max_db, int device, orbm_matcher **out);
+int orbm_destroy(orbm_matcher *m);
+long long orbm_launch_count(const orbm_matcher *m);
+
+/* DescriptorDistance for n independent pairs of 32-byte rows (host pointers). */
+int orbm_hamming_pairs_host(orbm_matcher *m, const uint8_t *a, const uint8_t *b, int n, int32_t *dist);
+
+/* Brute-force best-2: for each query scan db rows in ascending index; strict '<' (first minimal
+ * index wins); d2 = second smallest distance (may equal d1).  idx1 = index_base + row.
+ * Empty db -> d1 = d2 = INT32_MAX, idx1 = -1.  Device pointers, async on stream. */
+int orbm_knn2_device(orbm_matcher *m, const uint8_t *d_query, int nq, const uint8_t *d_db, int ndb,
+                     int index_base, int32_t *d_d1, int32_t *d_idx1, int32_t *d_d2, void *stream);
+/* Host-pointer convenience (copies in/out, synchronous). */
+int orbm_knn2_host(orbm_matcher *m, const uint8_t *query, int nq, const uint8_t *db, int ndb,
+                   int index_base, int32_t *d1, int32_t *idx1, int32_t *d2);
+/* match[i] = idx1[i] if d1 <= th_low && (float)d1 < (float)d2 * ratio else -1 (ORBmatcher.cpp:65-67) */
+int orbm_ratio_select_device(orbm_matcher *m, const int32_t *d_d1, const int32_t *d_idx1, const int32_t *d_d2,
+                             int nq, int th_low, float ratio, int32_t *d_match, void *stream);
+/* Merge `nshards` per-shard triples laid out [shard][nq] (shards in ascending index-range order)
+ * into the unsharded result.  Outputs may alias shard 0 of the inputs. */
+int orbm_merge_shards_device(orbm_matcher *m, const int32_t *d_d1, const int32_t *d_idx1, const int32_t *d_d2,
+                             int nshards, int nq, int32_t *d_od1, int32_t *d_oidx1, int32_t *d_od2, void *stream);
+
+/* Integer-pipe microbenchmark used for the kNN roofline: runs a dependent-free POPC loop on every
+ * SM and returns measured 32-bit POPC results per second (device-event timed). */
+int orbm_popc_peak(int device, double *popc_per_second, double *lop3_per_second);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORBX_H */

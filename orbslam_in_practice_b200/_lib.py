@@ -1,0 +1,222 @@
+"""ctypes binding of liborbx.so (include/orbx.h).  Used by tests/, bench.py and smoke().
+
+This is a test/bench harness binding, not the product host layer: the reference is C++, so the
+host-side mirror of its classes lives in orbslam_in_practice_b200/cpp/ (ORBSlam::ORBextractor,
+ORBSlam::ORBmatcher over the same C ABI).  There is no CPU fallback: a missing library or a
+missing sm_100 device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "liborbx.so")
+
+KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                           ("response", "<f4"), ("octave", "<i4"), ("class_id", "<i4")])
+CAND_DTYPE = np.dtype([("x", "<i2"), ("y", "<i2"), ("score", "<i4")])
+
+# every symbol include/orbx.h declares (tests check the library exports all of them)
+ABI_SYMBOLS = [
+    "orbx_strerror", "orbx_last_cuda_error", "orbx_version", "orbx_device_count",
+    "orbx_create", "orbx_destroy", "orbx_nlevels", "orbx_capacity", "orbx_tables",
+    "orbx_extract_host", "orbx_extract_device", "orbx_set_pyramid_border",
+    "orbx_level_dims", "orbx_download_level", "orbx_level_device_ptr",
+    "orbx_download_candidates", "orbx_download_kept", "orbx_max_candidates", "orbx_launch_count",
+    "orbm_create", "orbm_destroy", "orbm_launch_count", "orbm_hamming_pairs_host",
+    "orbm_knn2_device", "orbm_knn2_host", "orbm_ratio_select_device", "orbm_merge_shards_device",
+    "orbm_popc_peak",
+]
+
+
+class OrbxError(RuntimeError):
+    pass
+
+
+class Params(C.Structure):
+    _fields_ = [("nfeatures", C.c_int32), ("scale_factor", C.c_float), ("nlevels", C.c_int32),
+                ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32)]
+
+
+_lib = None
+
+
+def load():
+    """Load liborbx.so; raises if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise OrbxError("liborbx.so is missing: run `python -m orbslam_in_practice_b200.build` "
+                        "(or __graft_entry__.build()); there is no CPU fallback")
+    L = C.CDLL(SO_PATH)
+    vp, i32, f32, sz, ll = C.c_void_p, C.c_int, C.c_float, C.c_size_t, C.c_longlong
+    L.orbx_strerror.restype = C.c_char_p
+    L.orbx_strerror.argtypes = [i32]
+    L.orbx_last_cuda_error.restype = C.c_char_p
+    L.orbx_create.argtypes = [C.POINTER(Params), i32, i32, i32, i32, C.POINTER(vp)]
+    L.orbx_destroy.argtypes = [vp]
+    L.orbx_nlevels.argtypes = [vp]
+    L.orbx_capacity.argtypes = [vp]
+    L.orbx_tables.argtypes = [vp] * 7
+    L.orbx_extract_host.argtypes = [vp, vp, sz, sz, i32, i32, i32, vp, vp, vp]
+    L.orbx_extract_device.argtypes = [vp, vp, sz, sz, i32, i32, i32, vp, vp, vp, vp]
+    L.orbx_set_pyramid_border.argtypes = [vp, i32]
+    L.orbx_level_dims.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
+    L.orbx_download_level.argtypes = [vp, i32, i32, i32, i32, vp, sz]
+    L.orbx_level_device_ptr.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(sz)]
+    L.orbx_download_candidates.argtypes = [vp, i32, i32, vp, i32, C.POINTER(i32)]
+    L.orbx_download_kept.argtypes = [vp, i32, i32, vp, i32, C.POINTER(i32)]
+    L.orbx_max_candidates.argtypes = [vp, i32]
+    L.orbx_launch_count.restype = ll
+    L.orbx_launch_count.argtypes = [vp]
+    L.orbm_create.argtypes = [i32, i32, i32, C.POINTER(vp)]
+    L.orbm_destroy.argtypes = [vp]
+    L.orbm_launch_count.restype = ll
+    L.orbm_launch_count.argtypes = [vp]
+    L.orbm_hamming_pairs_host.argtypes = [vp, vp, vp, i32, vp]
+    L.orbm_knn2_device.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp, vp, vp]
+    L.orbm_knn2_host.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp, vp]
+    L.orbm_ratio_select_device.argtypes = [vp, vp, vp, vp, i32, i32, f32, vp, vp]
+    L.orbm_merge_shards_device.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp]
+    L.orbm_popc_peak.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        L = load()
+        msg = L.orbx_strerror(rc).decode()
+        cu = L.orbx_last_cuda_error().decode()
+        raise OrbxError("liborbx: %s (%d)%s" % (msg, rc, (" [" + cu + "]") if rc == -2 and cu else ""))
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Extractor:
+    """Batched ORBextractor over the C ABI (ORBextractor.h:29-97)."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7,
+                 max_width=640, max_height=480, max_batch=1, device=0):
+        L = load()
+        self.params = Params(nfeatures, scale_factor, nlevels, ini_th, min_th)
+        self.h = C.c_void_p()
+        self.nlevels, self.max_batch, self.device = nlevels, max_batch, device
+        check(L.orbx_create(C.byref(self.params), max_width, max_height, max_batch, device, C.byref(self.h)))
+        self.capacity = L.orbx_capacity(self.h)
+        t = [np.zeros(nlevels, np.float32) for _ in range(4)] + [np.zeros(nlevels, np.int32), np.zeros(16, np.int32)]
+        check(L.orbx_tables(self.h, *[_p(a) for a in t]))
+        (self.scale_factors, self.inv_scale_factors, self.level_sigma2, self.inv_level_sigma2,
+         self.features_per_level, self.umax) = t
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            load().orbx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    __del__ = close
+
+    def set_pyramid_border(self, on):
+        check(load().orbx_set_pyramid_border(self.h, int(on)))
+
+    def extract_host(self, imgs, out=None):
+        """imgs: (F,H,W) or (H,W) u8 host array -> (kps [F,cap], desc [F,cap,32], counts [F])."""
+        imgs = np.asarray(imgs)
+        if imgs.ndim == 2:
+            imgs = imgs[None]
+        assert imgs.dtype == np.uint8 and imgs.ndim == 3 and imgs.strides[2] == 1
+        F, H, W = imgs.shape
+        if out is None:
+            out = (np.zeros((F, self.capacity), KEYPOINT_DTYPE), np.zeros((F, self.capacity, 32), np.uint8),
+                   np.zeros(F, np.int32))
+        kps, desc, counts = out
+        check(load().orbx_extract_host(self.h, _p(imgs), imgs.strides[1], imgs.strides[0] if F > 1 else imgs.strides[1] * H,
+                                       W, H, F, _p(kps), _p(desc), _p(counts)))
+        return kps, desc, counts
+
+    def extract_host_ptr(self, img_ptr, row_pitch, frame_stride, W, H, F, kps_ptr, desc_ptr, counts_ptr):
+        check(load().orbx_extract_host(self.h, img_ptr, row_pitch, frame_stride, W, H, F, kps_ptr, desc_ptr, counts_ptr))
+
+    def extract_device(self, img_ptr, row_pitch, frame_stride, W, H, F, kps_ptr, desc_ptr, counts_ptr, stream=0):
+        check(load().orbx_extract_device(self.h, img_ptr, row_pitch, frame_stride, W, H, F, kps_ptr, desc_ptr,
+                                         counts_ptr, stream))
+
+    def level_dims(self, level):
+        w, h = C.c_int(), C.c_int()
+        check(load().orbx_level_dims(self.h, level, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    def level(self, frame, level, blurred=False, border=0):
+        w, h = self.level_dims(level)
+        out = np.zeros((h + 2 * border, w + 2 * border), np.uint8)
+        check(load().orbx_download_level(self.h, frame, level, int(blurred), border, _p(out), out.strides[0]))
+        return out
+
+    def _cands(self, fn, frame, level, cap):
+        out = np.zeros(max(cap, 1), CAND_DTYPE)
+        n = C.c_int()
+        check(fn(self.h, frame, level, _p(out), cap, C.byref(n)))
+        return out[:n.value].copy()
+
+    def candidates(self, frame, level):
+        return self._cands(load().orbx_download_candidates, frame, level, load().orbx_max_candidates(self.h, level))
+
+    def kept(self, frame, level):
+        return self._cands(load().orbx_download_kept, frame, level, self.capacity)
+
+    @property
+    def launches(self):
+        return load().orbx_launch_count(self.h)
+
+
+class Matcher:
+    """ORBmatcher distance / best-2 search over the C ABI (ORBmatcher.cpp:37-67,128-144)."""
+
+    def __init__(self, max_queries, max_db, device=0):
+        self.h = C.c_void_p()
+        self.max_q, self.max_db = max_queries, max_db
+        check(load().orbm_create(max_queries, max_db, device, C.byref(self.h)))
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            load().orbm_destroy(self.h)
+            self.h = C.c_void_p()
+
+    __del__ = close
+
+    def hamming_pairs(self, a, b):
+        a = np.ascontiguousarray(a, np.uint8).reshape(-1, 32); b = np.ascontiguousarray(b, np.uint8).reshape(-1, 32)
+        assert len(a) == len(b)
+        out = np.zeros(len(a), np.int32)
+        check(load().orbm_hamming_pairs_host(self.h, _p(a), _p(b), len(a), _p(out)))
+        return out
+
+    def knn2_host(self, q, db, index_base=0):
+        q = np.ascontiguousarray(q, np.uint8).reshape(-1, 32); db = np.ascontiguousarray(db, np.uint8).reshape(-1, 32)
+        d1, idx1, d2 = (np.zeros(len(q), np.int32) for _ in range(3))
+        check(load().orbm_knn2_host(self.h, _p(q), len(q), _p(db), len(db), index_base, _p(d1), _p(idx1), _p(d2)))
+        return d1, idx1, d2
+
+    def knn2_device(self, q_ptr, nq, db_ptr, ndb, index_base, d1_ptr, idx1_ptr, d2_ptr, stream=0):
+        check(load().orbm_knn2_device(self.h, q_ptr, nq, db_ptr, ndb, index_base, d1_ptr, idx1_ptr, d2_ptr, stream))
+
+    def ratio_select_device(self, d1_ptr, idx1_ptr, d2_ptr, nq, th_low, ratio, match_ptr, stream=0):
+        check(load().orbm_ratio_select_device(self.h, d1_ptr, idx1_ptr, d2_ptr, nq, th_low, ratio, match_ptr, stream))
+
+    def merge_shards_device(self, d1_ptr, idx1_ptr, d2_ptr, nshards, nq, od1_ptr, oidx1_ptr, od2_ptr, stream=0):
+        check(load().orbm_merge_shards_device(self.h, d1_ptr, idx1_ptr, d2_ptr, nshards, nq, od1_ptr, oidx1_ptr,
+                                              od2_ptr, stream))
+
+    @property
+    def launches(self):
+        return load().orbm_launch_count(self.h)
+
+
+def popc_peak(device=0):
+    a, b = C.c_double(), C.c_double()
+    check(load().orbm_popc_peak(device, C.byref(a), C.byref(b)))
+    return a.value, b.value

@@ -1,0 +1,630 @@
+// abi.cu -- the C ABI of liborbx.so (include/orbx.h): handles, geometry, launch sequencing.
+// Host-side table math follows the reference constructor (ORBextractor.cpp:360-420) and
+// OpenCV's resize coefficient generation; everything per-pixel runs on the device.
+#include "orbx_internal.cuh"
+
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace orbx {
+// knn.cu
+int knn_segments(int nq, int ndb, int sm_count, int *seg_rows_out);
+void launch_knn2(const uint8_t *d_query, int nq, const uint8_t *d_db, int ndb, int index_base, int nseg, int seg_rows,
+                 uint2 *partial, int *d1, int *idx1, int *d2, cudaStream_t s);
+void launch_hamming_pairs(const uint8_t *a, const uint8_t *b, int n, int *dist, cudaStream_t s);
+void launch_ratio_select(const int *d1, const int *idx1, const int *d2, int nq, int th, float ratio, int *match, cudaStream_t s);
+void launch_merge_shards(const int *d1, const int *idx1, const int *d2, int nshards, int nq, int *od1, int *oidx1, int *od2, cudaStream_t s);
+int run_popc_bench(int mode, int sm_count, double *ops_per_second);
+} // namespace orbx
+
+using namespace orbx;
+
+static thread_local char g_cuda_err[256] = "";
+
+static int cuda_fail(cudaError_t e, const char *what)
+{
+    std::snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", what, cudaGetErrorString(e));
+    return ORBX_E_CUDA;
+}
+#define CK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail(e__, #call); } while (0)
+
+struct orbx_extractor {
+    orbx_params params;
+    int device, max_w, max_h, max_batch;
+    int cur_w, cur_h;            // geometry currently built
+    int last_frames;
+    Geo geo;                     // geometry of the current frame size
+    Geo full;                    // geometry of (max_w, max_h): sized every buffer
+    DevBuffers buf;
+    std::vector<void *> allocs;
+    cudaStream_t stream;
+    int oct_smem;
+    long long launches;
+    // reference tables
+    float scale[ORBX_MAX_LEVELS], inv_scale[ORBX_MAX_LEVELS], sigma2[ORBX_MAX_LEVELS], inv_sigma2[ORBX_MAX_LEVELS];
+    int nfeat[ORBX_MAX_LEVELS];
+    int umax[16];
+    int border_on;
+};
+
+extern "C" const char *orbx_strerror(int code)
+{
+    switch (code) {
+    case ORBX_OK: return "ok";
+    case ORBX_E_INVALID: return "invalid argument";
+    case ORBX_E_CUDA: return "CUDA runtime error";
+    case ORBX_E_NOMEM: return "out of memory";
+    case ORBX_E_CAPACITY: return "input exceeds the capacity the handle was created with";
+    case ORBX_E_NODEVICE: return "no sm_100 CUDA device available (this library has no CPU fallback)";
+    case ORBX_E_UNSUPPORTED: return "unsupported configuration";
+    default: return "unknown error";
+    }
+}
+extern "C" const char *orbx_last_cuda_error(void) { return g_cuda_err; }
+extern "C" int orbx_version(void) { return 100; }
+
+extern "C" int orbx_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++ok;
+    }
+    return ok;
+}
+
+static int cv_round(double v) { return (int)lrint(v); }
+static int cv_floor(double v) { int i = (int)v; return i - (i > v); }
+static int cv_ceil(double v) { int i = (int)v; return i + (i < v); }
+static short sat_short(int v) { return (short)(v < -32768 ? -32768 : v > 32767 ? 32767 : v); }
+
+// ORBextractor::ORBextractor, ORBextractor.cpp:360-420
+static void build_reference_tables(orbx_extractor *ex)
+{
+    const int nlevels = ex->params.nlevels, nfeatures = ex->params.nfeatures;
+    const double scaleFactor = ex->params.scale_factor;      // ORBextractor.h:84: double member
+    ex->scale[0] = 1.0f; ex->sigma2[0] = 1.0f;
+    for (int i = 1; i < nlevels; ++i) {
+        ex->scale[i] = (float)(ex->scale[i - 1] * scaleFactor);
+        ex->sigma2[i] = ex->scale[i] * ex->scale[i];
+    }
+    for (int i = 0; i < nlevels; ++i) { ex->inv_scale[i] = 1.0f / ex->scale[i]; ex->inv_sigma2[i] = 1.0f / ex->sigma2[i]; }
+    const float factor = (float)(1.0f / scaleFactor);
+    float nDesired = nfeatures * (1 - factor) / (1 - (float)std::pow((double)factor, (double)nlevels));
+    int sum = 0;
+    for (int l = 0; l < nlevels - 1; ++l) { ex->nfeat[l] = cv_round(nDesired); sum += ex->nfeat[l]; nDesired *= factor; }
+    ex->nfeat[nlevels - 1] = std::max(nfeatures - sum, 0);
+    int v, v0;
+    const int vmax = cv_floor(kHalfPatch * std::sqrt(2.f) / 2 + 1), vmin = cv_ceil(kHalfPatch * std::sqrt(2.f) / 2);
+    const double hp2 = kHalfPatch * kHalfPatch;
+    for (v = 0; v <= vmax; ++v) ex->umax[v] = cv_round(std::sqrt(hp2 - v * v));
+    for (v = kHalfPatch, v0 = 0; v >= vmin; --v) {
+        while (ex->umax[v0] == ex->umax[v0 + 1]) ++v0;
+        ex->umax[v] = v0;
+        ++v0;
+    }
+}
+
+// OpenCV resize INTER_LINEAR coefficient tables
+static void linear_table(int ssize, int dsize, bool clamp, std::vector<int2> &tab)
+{
+    const double scale = 1.0 / ((double)dsize / ssize);
+    for (int d = 0; d < dsize; ++d) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = cv_floor(f);
+        f -= s;
+        if (clamp && s < 0) { s = 0; f = 0.f; }
+        if (clamp && s >= ssize - 1) { s = ssize - 1; f = 0.f; }
+        const short c0 = sat_short((int)lrintf((1.f - f) * 2048.f)), c1 = sat_short((int)lrintf(f * 2048.f));
+        tab.push_back(make_int2(s, (int)((unsigned)(unsigned short)c0 | ((unsigned)(unsigned short)c1 << 16))));
+    }
+}
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// geometry for frames of w x h (buffer offsets assume max_batch frames per level)
+static int build_geometry(const orbx_extractor *ex, int w, int h, Geo &g, std::vector<int2> *tables)
+{
+    std::memset(&g, 0, sizeof(g));
+    g.nlevels = ex->params.nlevels; g.ini_th = ex->params.ini_th_fast; g.min_th = ex->params.min_th_fast;
+    g.border_on = ex->border_on;
+    for (int i = 0; i < 16; ++i) g.umax[i] = ex->umax[i];
+    size_t pyr_off = 0, blur_off = 0, slot_off = 0, key_off = 0;
+    int cell_off = 0, kept_off = 0;
+    const size_t F = (size_t)ex->max_batch;
+    for (int l = 0; l < g.nlevels; ++l) {
+        LevelGeom &L = g.lv[l];
+        const float s = ex->inv_scale[l];
+        L.w = cv_round((float)w * s); L.h = cv_round((float)h * s);           // :1075-1076
+        if (L.w < 1 || L.h < 1) return ORBX_E_UNSUPPORTED;
+        L.pitch = (int)align_up((size_t)kPadX + L.w + kBorder, 64);
+        L.blur_pitch = (int)align_up((size_t)L.w, 64);
+        L.base = pyr_off; L.frame_stride = (size_t)L.pitch * (L.h + 2 * kPadY);
+        pyr_off += L.frame_stride * F;
+        L.blur_base = blur_off; L.blur_frame_stride = (size_t)L.blur_pitch * L.h;
+        blur_off += L.blur_frame_stride * F;
+        // cell grid :729-743
+        L.maxBorderX = L.w - kBorder + 3; L.maxBorderY = L.h - kBorder + 3;
+        const float width = (float)(L.maxBorderX - kMinBorder), height = (float)(L.maxBorderY - kMinBorder);
+        const int nCols = (int)(width / 30.f), nRows = (int)(height / 30.f);
+        if (width <= 0 || height <= 0 || nCols < 1 || nRows < 1) {
+            L.nCols = L.nRows = 0; L.wCell = L.hCell = 1; L.cell_cap = 1;      // level too small: no cells
+        } else {
+            L.nCols = nCols; L.nRows = nRows;
+            L.wCell = (int)std::ceil(width / nCols); L.hCell = (int)std::ceil(height / nRows);
+            if (L.wCell > 64 || L.hCell > 64) return ORBX_E_UNSUPPORTED;
+            L.cell_cap = ((L.wCell + 1) / 2) * ((L.hCell + 1) / 2);
+        }
+        L.cell_base = cell_off; cell_off += L.nCols * L.nRows;
+        L.slot_base = slot_off; L.max_cand = L.nCols * L.nRows * L.cell_cap;
+        slot_off += (size_t)L.max_cand;
+        L.key_base = key_off; key_off += (size_t)L.max_cand;
+        // octree :493-495
+        L.N = ex->nfeat[l];
+        L.regionW = L.maxBorderX - kMinBorder; L.regionH = L.maxBorderY - kMinBorder;
+        L.nIni = (L.regionW > 0 && L.regionH > 0) ? (int)std::round((float)L.regionW / (float)L.regionH) : 0;
+        L.hX = L.nIni > 0 ? (float)L.regionW / L.nIni : 1.f;
+        if (L.regionW > 4095 || L.regionH > 4095) return ORBX_E_UNSUPPORTED;   // 12-bit packed coordinates
+        L.kept_cap = std::max(L.N + 3, 4 * L.nIni) + 1;
+        L.node_cap = L.kept_cap + 1;
+        if (L.node_cap > 65535) return ORBX_E_UNSUPPORTED;
+        L.kept_base = kept_off; kept_off += L.kept_cap;
+        L.scale = ex->scale[l];
+        L.patch_size = (int)(31 * ex->scale[l]);                                // :794
+        if (l > 0 && tables) {
+            L.tabx = (int)tables->size(); linear_table(g.lv[l - 1].w, L.w, true, *tables);
+            L.taby = (int)tables->size(); linear_table(g.lv[l - 1].h, L.h, false, *tables);
+        }
+    }
+    g.total_cells = cell_off;
+    g.capacity = kept_off; g.kept_total = kept_off;
+    g.slots_per_frame = slot_off; g.keys_per_frame = key_off;
+    g.pyr_frame_total = pyr_off; g.blur_frame_total = blur_off;
+    return ORBX_OK;
+}
+
+template <typename T> static int dev_alloc(orbx_extractor *ex, T **p, size_t count)
+{
+    void *q = nullptr;
+    cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
+    if (e != cudaSuccess) { cuda_fail(e, "cudaMalloc"); return ORBX_E_NOMEM; }
+    ex->allocs.push_back(q);
+    *p = (T *)q;
+    return ORBX_OK;
+}
+
+static int upload_geometry(orbx_extractor *ex, int w, int h)
+{
+    std::vector<int2> tables;
+    Geo ng;
+    int rc = build_geometry(ex, w, h, ng, &tables);
+    if (rc) return rc;
+    // every buffer was sized by the creation geometry; a smaller frame with a wider aspect ratio can
+    // still need more octree roots / keypoint slots than that
+    if (ng.capacity > ex->full.capacity || ng.slots_per_frame > ex->full.slots_per_frame || ng.total_cells > ex->full.total_cells ||
+        ng.keys_per_frame > ex->full.keys_per_frame || ng.pyr_frame_total > ex->full.pyr_frame_total ||
+        ng.blur_frame_total > ex->full.blur_frame_total)
+        return ORBX_E_CAPACITY;
+    ex->geo = ng;
+    ex->geo.capacity = ex->full.capacity;   // output row stride stays the creation capacity
+    if (!tables.empty()) CK(cudaMemcpyAsync(ex->buf.tables, tables.data(), tables.size() * sizeof(int2), cudaMemcpyHostToDevice, ex->stream));
+    CK(cudaStreamSynchronize(ex->stream));   // `tables` is pageable host memory about to go out of scope
+    ex->cur_w = w; ex->cur_h = h;
+    ex->oct_smem = octree_smem_bytes(ex->geo);
+    if (octree_configure(ex->oct_smem)) return cuda_fail(cudaGetLastError(), "octree smem");
+    return ORBX_OK;
+}
+
+extern "C" int orbx_create(const orbx_params *p, int max_width, int max_height, int max_batch, int device, orbx_extractor **out)
+{
+    if (!p || !out || max_width < 1 || max_height < 1 || max_batch < 1) return ORBX_E_INVALID;
+    if (p->nlevels < 1 || p->nlevels > ORBX_MAX_LEVELS || p->nfeatures < 0 || !(p->scale_factor > 1.0f)) return ORBX_E_INVALID;
+    if (p->ini_th_fast < 1 || p->ini_th_fast > 255 || p->min_th_fast < 1 || p->min_th_fast > 255) return ORBX_E_INVALID;
+    if (max_batch > 65535) return ORBX_E_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { cudaGetLastError(); return ORBX_E_NODEVICE; }
+    int major = 0;
+    CK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major != 10) return ORBX_E_NODEVICE;
+    CK(cudaSetDevice(device));
+    orbx_extractor *ex = new (std::nothrow) orbx_extractor();
+    if (!ex) return ORBX_E_NOMEM;
+    ex->params = *p; ex->device = device; ex->max_w = max_width; ex->max_h = max_height; ex->max_batch = max_batch;
+    ex->launches = 0; ex->last_frames = 0; ex->border_on = 1;
+    std::memset(&ex->buf, 0, sizeof(ex->buf));
+    build_reference_tables(ex);
+    int rc = build_geometry(ex, max_width, max_height, ex->full, nullptr);
+    if (rc) { delete ex; return rc; }
+    ex->geo = ex->full;
+    if (cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ex; return cuda_fail(cudaGetLastError(), "stream"); }
+    const Geo &g = ex->full;
+    const size_t F = (size_t)max_batch;
+    DevBuffers &b = ex->buf;
+    size_t ntab = 0;
+    for (int l = 1; l < g.nlevels; ++l) ntab += (size_t)g.lv[l].w + g.lv[l].h;
+#define TRY(x) do { rc = (x); if (rc) { orbx_destroy(ex); return rc; } } while (0)
+    TRY(dev_alloc(ex, &b.pyr, g.pyr_frame_total));
+    TRY(dev_alloc(ex, &b.blur, g.blur_frame_total));
+    TRY(dev_alloc(ex, &b.tables, ntab + 16));
+    TRY(dev_alloc(ex, &b.cell_count, F * g.total_cells));
+    TRY(dev_alloc(ex, &b.cell_slots, F * g.slots_per_frame));
+    TRY(dev_alloc(ex, &b.keysA, F * g.keys_per_frame));
+    TRY(dev_alloc(ex, &b.keysB, F * g.keys_per_frame));
+    TRY(dev_alloc(ex, &b.nodeA, F * g.keys_per_frame));
+    TRY(dev_alloc(ex, &b.nodeB, F * g.keys_per_frame));
+    TRY(dev_alloc(ex, &b.scanE, F * (g.keys_per_frame + g.nlevels)));
+    TRY(dev_alloc(ex, &b.ncand, F * g.nlevels));
+    TRY(dev_alloc(ex, &b.kept, F * g.kept_total));
+    TRY(dev_alloc(ex, &b.nkept, F * g.nlevels));
+    TRY(dev_alloc(ex, &b.staging, F * (size_t)max_width * max_height));
+    TRY(dev_alloc(ex, &b.out_kps, F * g.capacity));
+    TRY(dev_alloc(ex, &b.out_desc, F * g.capacity * 32));
+    TRY(dev_alloc(ex, &b.out_counts, F));
+#undef TRY
+    rc = upload_geometry(ex, max_width, max_height);
+    if (rc) { orbx_destroy(ex); return rc; }
+    *out = ex;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_destroy(orbx_extractor *ex)
+{
+    if (!ex) return ORBX_OK;
+    cudaSetDevice(ex->device);
+    if (ex->stream) { cudaStreamSynchronize(ex->stream); cudaStreamDestroy(ex->stream); }
+    for (void *p : ex->allocs) cudaFree(p);
+    delete ex;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_nlevels(const orbx_extractor *ex) { return ex ? ex->params.nlevels : ORBX_E_INVALID; }
+
+extern "C" int orbx_capacity(const orbx_extractor *ex)
+{
+    if (!ex) return ORBX_E_INVALID;
+    // the capacity depends on nIni (aspect ratio); report the one of the creation geometry, which
+    // also sized the output buffers.  Geometry rebuilds for smaller frames never exceed it unless
+    // the aspect ratio grows, which orbx_extract_* rejects with ORBX_E_CAPACITY.
+    return ex->full.capacity;
+}
+
+extern "C" int orbx_tables(const orbx_extractor *ex, float *scale, float *inv_scale, float *sigma2, float *inv_sigma2,
+                           int32_t *features_per_level, int32_t *umax)
+{
+    if (!ex) return ORBX_E_INVALID;
+    for (int i = 0; i < ex->params.nlevels; ++i) {
+        if (scale) scale[i] = ex->scale[i];
+        if (inv_scale) inv_scale[i] = ex->inv_scale[i];
+        if (sigma2) sigma2[i] = ex->sigma2[i];
+        if (inv_sigma2) inv_sigma2[i] = ex->inv_sigma2[i];
+        if (features_per_level) features_per_level[i] = ex->nfeat[i];
+    }
+    if (umax) for (int i = 0; i < 16; ++i) umax[i] = ex->umax[i];
+    return ORBX_OK;
+}
+
+extern "C" int orbx_set_pyramid_border(orbx_extractor *ex, int enabled)
+{
+    if (!ex) return ORBX_E_INVALID;
+    ex->border_on = enabled ? 1 : 0;
+    ex->geo.border_on = ex->border_on; ex->full.border_on = ex->border_on;
+    return ORBX_OK;
+}
+
+static int run_pipeline(orbx_extractor *ex, const uint8_t *d_imgs, size_t pitch, size_t fstride, int w, int h, int nframes,
+                        orbx_keypoint *d_kps, uint8_t *d_desc, int *d_counts, cudaStream_t s)
+{
+    if (w != ex->cur_w || h != ex->cur_h) {
+        CK(cudaStreamSynchronize(ex->stream));
+        int rc = upload_geometry(ex, w, h);
+        if (rc) return rc;
+    }
+    const Geo &g = ex->geo;
+    launch_level0(g, ex->buf, d_imgs, pitch, fstride, nframes, s);
+    for (int l = 1; l < g.nlevels; ++l) launch_resize(g, ex->buf, l, nframes, s);
+    if (g.total_cells > 0) launch_fast(g, ex->buf, nframes, s);
+    launch_octree(g, ex->buf, nframes, ex->oct_smem, s);
+    launch_blur(g, ex->buf, nframes, s);
+    launch_describe(g, ex->buf, nframes, d_kps, d_desc, d_counts, s);
+    ex->launches += 1 + (g.nlevels - 1) + (g.total_cells > 0) + 1 + g.nlevels + 1;
+    ex->last_frames = nframes;
+    CK(cudaGetLastError());
+    return ORBX_OK;
+}
+
+extern "C" int orbx_extract_device(orbx_extractor *ex, const uint8_t *d_imgs, size_t row_pitch, size_t frame_stride,
+                                   int width, int height, int nframes,
+                                   orbx_keypoint *d_kps, uint8_t *d_desc, int32_t *d_counts, void *stream)
+{
+    if (!ex || nframes < 0 || !d_kps || !d_desc || !d_counts) return ORBX_E_INVALID;
+    if (nframes == 0) return ORBX_OK;
+    CK(cudaSetDevice(ex->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : ex->stream;
+    if (width <= 0 || height <= 0 || !d_imgs) {               // empty image: :1004-1005
+        CK(cudaMemsetAsync(d_counts, 0, sizeof(int) * (size_t)nframes, s));
+        return ORBX_OK;
+    }
+    if (width > ex->max_w || height > ex->max_h || nframes > ex->max_batch) return ORBX_E_CAPACITY;
+    if (row_pitch < (size_t)width) return ORBX_E_INVALID;
+    return run_pipeline(ex, d_imgs, row_pitch, frame_stride, width, height, nframes, d_kps, d_desc, d_counts, s);
+}
+
+extern "C" int orbx_extract_host(orbx_extractor *ex, const uint8_t *imgs, size_t row_pitch, size_t frame_stride,
+                                 int width, int height, int nframes,
+                                 orbx_keypoint *kps, uint8_t *desc, int32_t *counts)
+{
+    if (!ex || nframes < 0 || !counts) return ORBX_E_INVALID;
+    if (nframes == 0) return ORBX_OK;
+    if (width <= 0 || height <= 0 || !imgs) { std::memset(counts, 0, sizeof(int) * (size_t)nframes); return ORBX_OK; }
+    if (!kps || !desc) return ORBX_E_INVALID;
+    if (width > ex->max_w || height > ex->max_h || nframes > ex->max_batch) return ORBX_E_CAPACITY;
+    if (row_pitch < (size_t)width) return ORBX_E_INVALID;
+    CK(cudaSetDevice(ex->device));
+    cudaStream_t s = ex->stream;
+    const size_t cap = (size_t)ex->full.capacity;
+    // one 2-D copy for the whole batch when frames are evenly strided, straight from the caller's
+    // buffer (pinned or pageable); tight rows on the device side
+    if (frame_stride == row_pitch * (size_t)height || nframes == 1) {
+        CK(cudaMemcpy2DAsync(ex->buf.staging, (size_t)width, imgs, row_pitch, (size_t)width, (size_t)height * nframes,
+                             cudaMemcpyHostToDevice, s));
+    } else {
+        for (int f = 0; f < nframes; ++f)
+            CK(cudaMemcpy2DAsync(ex->buf.staging + (size_t)f * width * height, (size_t)width, imgs + (size_t)f * frame_stride, row_pitch,
+                                 (size_t)width, (size_t)height, cudaMemcpyHostToDevice, s));
+    }
+    int rc = run_pipeline(ex, ex->buf.staging, (size_t)width, (size_t)width * height, width, height, nframes,
+                          ex->buf.out_kps, ex->buf.out_desc, ex->buf.out_counts, s);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(kps, ex->buf.out_kps, (size_t)nframes * cap * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(desc, ex->buf.out_desc, (size_t)nframes * cap * 32, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(counts, ex->buf.out_counts, (size_t)nframes * sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return ORBX_OK;
+}
+
+extern "C" int orbx_level_dims(const orbx_extractor *ex, int level, int *width, int *height)
+{
+    if (!ex || level < 0 || level >= ex->params.nlevels || !width || !height) return ORBX_E_INVALID;
+    *width = ex->geo.lv[level].w; *height = ex->geo.lv[level].h;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_download_level(orbx_extractor *ex, int frame, int level, int blurred, int border, uint8_t *dst, size_t dst_pitch)
+{
+    if (!ex || !dst || level < 0 || level >= ex->params.nlevels || frame < 0 || frame >= ex->last_frames) return ORBX_E_INVALID;
+    if (border != 0 && (border != kBorder || blurred || !ex->border_on)) return ORBX_E_INVALID;
+    CK(cudaSetDevice(ex->device));
+    const LevelGeom &L = ex->geo.lv[level];
+    const size_t w = (size_t)L.w + 2 * border, h = (size_t)L.h + 2 * border;
+    if (dst_pitch < w) return ORBX_E_INVALID;
+    CK(cudaStreamSynchronize(ex->stream));
+    if (blurred) {
+        CK(cudaMemcpy2D(dst, dst_pitch, ex->buf.blur + L.blur_base + (size_t)frame * L.blur_frame_stride, L.blur_pitch, w, h, cudaMemcpyDeviceToHost));
+    } else {
+        const uint8_t *src = ex->buf.pyr + L.base + (size_t)frame * L.frame_stride + (size_t)(kPadY - border) * L.pitch + kPadX - border;
+        CK(cudaMemcpy2D(dst, dst_pitch, src, L.pitch, w, h, cudaMemcpyDeviceToHost));
+    }
+    return ORBX_OK;
+}
+
+extern "C" int orbx_level_device_ptr(orbx_extractor *ex, int frame, int level, const uint8_t **ptr, size_t *pitch)
+{
+    if (!ex || !ptr || !pitch || level < 0 || level >= ex->params.nlevels || frame < 0 || frame >= ex->max_batch) return ORBX_E_INVALID;
+    const LevelGeom &L = ex->geo.lv[level];
+    *ptr = ex->buf.pyr + L.base + (size_t)frame * L.frame_stride + (size_t)kPadY * L.pitch + kPadX;
+    *pitch = (size_t)L.pitch;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_max_candidates(const orbx_extractor *ex, int level)
+{
+    if (!ex || level < 0 || level >= ex->params.nlevels) return ORBX_E_INVALID;
+    return ex->geo.lv[level].max_cand;
+}
+
+static int download_keys(orbx_extractor *ex, const uint32_t *d_src, const int *d_count, int count_cap, orbx_cand *out, int cap, int *n)
+{
+    int cnt = 0;
+    CK(cudaStreamSynchronize(ex->stream));
+    CK(cudaMemcpy(&cnt, d_count, sizeof(int), cudaMemcpyDeviceToHost));
+    if (cnt > count_cap) cnt = count_cap;
+    *n = cnt;
+    if (cnt > cap) return ORBX_E_CAPACITY;
+    std::vector<uint32_t> tmp((size_t)cnt);
+    if (cnt) CK(cudaMemcpy(tmp.data(), d_src, sizeof(uint32_t) * (size_t)cnt, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < cnt; ++i) { out[i].x = (int16_t)cand_x(tmp[i]); out[i].y = (int16_t)cand_y(tmp[i]); out[i].score = cand_score(tmp[i]); }
+    return ORBX_OK;
+}
+
+extern "C" int orbx_download_candidates(orbx_extractor *ex, int frame, int level, orbx_cand *out, int cap, int *n)
+{
+    if (!ex || !out || !n || level < 0 || level >= ex->params.nlevels || frame < 0 || frame >= ex->last_frames) return ORBX_E_INVALID;
+    CK(cudaSetDevice(ex->device));
+    const Geo &g = ex->geo; const LevelGeom &L = g.lv[level];
+    // after the octree kernel the ordered candidate list is no longer contiguous (keys are permuted
+    // inside node ranges); rebuild it from the per-cell slots, which are left untouched
+    CK(cudaStreamSynchronize(ex->stream));
+    const int nCells = L.nCols * L.nRows;
+    std::vector<int> counts((size_t)nCells);
+    if (nCells) CK(cudaMemcpy(counts.data(), ex->buf.cell_count + (size_t)frame * g.total_cells + L.cell_base, sizeof(int) * (size_t)nCells, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> slots((size_t)L.max_cand);
+    if (L.max_cand) CK(cudaMemcpy(slots.data(), ex->buf.cell_slots + (size_t)frame * g.slots_per_frame + L.slot_base, sizeof(uint32_t) * (size_t)L.max_cand, cudaMemcpyDeviceToHost));
+    int total = 0;
+    for (int c = 0; c < nCells; ++c) total += counts[c];
+    *n = total;
+    if (total > cap) return ORBX_E_CAPACITY;
+    int k = 0;
+    for (int c = 0; c < nCells; ++c)
+        for (int i = 0; i < counts[c]; ++i) {
+            const uint32_t key = slots[(size_t)c * L.cell_cap + i];
+            out[k].x = (int16_t)cand_x(key); out[k].y = (int16_t)cand_y(key); out[k].score = cand_score(key); ++k;
+        }
+    return ORBX_OK;
+}
+
+extern "C" int orbx_download_kept(orbx_extractor *ex, int frame, int level, orbx_cand *out, int cap, int *n)
+{
+    if (!ex || !out || !n || level < 0 || level >= ex->params.nlevels || frame < 0 || frame >= ex->last_frames) return ORBX_E_INVALID;
+    CK(cudaSetDevice(ex->device));
+    const Geo &g = ex->geo; const LevelGeom &L = g.lv[level];
+    return download_keys(ex, ex->buf.kept + (size_t)frame * g.kept_total + L.kept_base, ex->buf.nkept + (size_t)frame * g.nlevels + level, L.kept_cap, out, cap, n);
+}
+
+extern "C" long long orbx_launch_count(const orbx_extractor *ex) { return ex ? ex->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// matcher
+// ------------------------------------------------------------------------------------------------
+struct orbm_matcher {
+    int device, max_q, max_db, sm_count;
+    cudaStream_t stream;
+    uint2 *partial; size_t partial_elems;
+    uint8_t *d_q, *d_db; int *d_out;   // device staging for the host-pointer entry points
+    long long launches;
+};
+
+extern "C" int orbm_create(int max_queries, int max_db, int device, orbm_matcher **out)
+{
+    if (!out || max_queries < 1 || max_db < 0) return ORBX_E_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { cudaGetLastError(); return ORBX_E_NODEVICE; }
+    int major = 0;
+    CK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    if (major != 10) return ORBX_E_NODEVICE;
+    CK(cudaSetDevice(device));
+    orbm_matcher *m = new (std::nothrow) orbm_matcher();
+    if (!m) return ORBX_E_NOMEM;
+    std::memset(m, 0, sizeof(*m));
+    m->device = device; m->max_q = max_queries; m->max_db = max_db;
+    CK(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device));
+    CK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    int seg_rows = 0;
+    const int nseg = knn_segments(max_queries, std::max(max_db, 1), m->sm_count, &seg_rows);
+    m->partial_elems = (size_t)(nseg + 1) * max_queries;
+    if (cudaMalloc(&m->partial, m->partial_elems * sizeof(uint2)) != cudaSuccess) { cuda_fail(cudaGetLastError(), "cudaMalloc"); orbm_destroy(m); return ORBX_E_NOMEM; }
+    *out = m;
+    return ORBX_OK;
+}
+
+extern "C" int orbm_destroy(orbm_matcher *m)
+{
+    if (!m) return ORBX_OK;
+    cudaSetDevice(m->device);
+    if (m->stream) { cudaStreamSynchronize(m->stream); cudaStreamDestroy(m->stream); }
+    cudaFree(m->partial); cudaFree(m->d_q); cudaFree(m->d_db); cudaFree(m->d_out);
+    delete m;
+    return ORBX_OK;
+}
+
+extern "C" long long orbm_launch_count(const orbm_matcher *m) { return m ? m->launches : 0; }
+
+extern "C" int orbm_knn2_device(orbm_matcher *m, const uint8_t *d_query, int nq, const uint8_t *d_db, int ndb,
+                                int index_base, int32_t *d_d1, int32_t *d_idx1, int32_t *d_d2, void *stream)
+{
+    if (!m || nq < 0 || ndb < 0 || (nq && (!d_query || !d_d1 || !d_idx1 || !d_d2)) || (ndb && !d_db)) return ORBX_E_INVALID;
+    if (nq > m->max_q || ndb > m->max_db) return ORBX_E_CAPACITY;
+    if (((uintptr_t)d_query | (uintptr_t)d_db) & 15) return ORBX_E_INVALID;   // 16-byte vector loads
+    if (nq == 0) return ORBX_OK;
+    CK(cudaSetDevice(m->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : m->stream;
+    int seg_rows = 0;
+    const int nseg = ndb > 0 ? knn_segments(nq, ndb, m->sm_count, &seg_rows) : 0;
+    if ((size_t)nseg * nq > m->partial_elems) return ORBX_E_CAPACITY;
+    launch_knn2(d_query, nq, d_db, ndb, index_base, nseg, seg_rows, m->partial, d_d1, d_idx1, d_d2, s);
+    m->launches += ndb > 0 ? 2 : 1;
+    CK(cudaGetLastError());
+    return ORBX_OK;
+}
+
+static int ensure_staging(orbm_matcher *m)
+{
+    if (m->d_out) return ORBX_OK;
+    CK(cudaMalloc(&m->d_q, (size_t)m->max_q * 32));
+    CK(cudaMalloc(&m->d_db, (size_t)std::max(std::max(m->max_db, m->max_q), 1) * 32));
+    CK(cudaMalloc(&m->d_out, (size_t)m->max_q * 3 * sizeof(int)));
+    return ORBX_OK;
+}
+
+extern "C" int orbm_knn2_host(orbm_matcher *m, const uint8_t *query, int nq, const uint8_t *db, int ndb,
+                              int index_base, int32_t *d1, int32_t *idx1, int32_t *d2)
+{
+    if (!m || nq < 0 || ndb < 0 || (nq && (!query || !d1 || !idx1 || !d2)) || (ndb && !db)) return ORBX_E_INVALID;
+    if (nq > m->max_q || ndb > m->max_db) return ORBX_E_CAPACITY;
+    if (nq == 0) return ORBX_OK;
+    CK(cudaSetDevice(m->device));
+    int rc = ensure_staging(m);
+    if (rc) return rc;
+    cudaStream_t s = m->stream;
+    CK(cudaMemcpyAsync(m->d_q, query, (size_t)nq * 32, cudaMemcpyHostToDevice, s));
+    if (ndb) CK(cudaMemcpyAsync(m->d_db, db, (size_t)ndb * 32, cudaMemcpyHostToDevice, s));
+    int *o = m->d_out;
+    rc = orbm_knn2_device(m, m->d_q, nq, m->d_db, ndb, index_base, o, o + m->max_q, o + 2 * (size_t)m->max_q, s);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(d1, o, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(idx1, o + m->max_q, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(d2, o + 2 * (size_t)m->max_q, (size_t)nq * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return ORBX_OK;
+}
+
+extern "C" int orbm_hamming_pairs_host(orbm_matcher *m, const uint8_t *a, const uint8_t *b, int n, int32_t *dist)
+{
+    if (!m || n < 0 || (n && (!a || !b || !dist))) return ORBX_E_INVALID;
+    if (n > m->max_q) return ORBX_E_CAPACITY;
+    if (n == 0) return ORBX_OK;
+    CK(cudaSetDevice(m->device));
+    int rc = ensure_staging(m);
+    if (rc) return rc;
+    cudaStream_t s = m->stream;
+    CK(cudaMemcpyAsync(m->d_q, a, (size_t)n * 32, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(m->d_db, b, (size_t)n * 32, cudaMemcpyHostToDevice, s));
+    launch_hamming_pairs(m->d_q, m->d_db, n, m->d_out, s);
+    m->launches += 1;
+    CK(cudaMemcpyAsync(dist, m->d_out, (size_t)n * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return ORBX_OK;
+}
+
+extern "C" int orbm_ratio_select_device(orbm_matcher *m, const int32_t *d_d1, const int32_t *d_idx1, const int32_t *d_d2,
+                                        int nq, int th_low, float ratio, int32_t *d_match, void *stream)
+{
+    if (!m || nq < 0 || (nq && (!d_d1 || !d_idx1 || !d_d2 || !d_match))) return ORBX_E_INVALID;
+    CK(cudaSetDevice(m->device));
+    launch_ratio_select(d_d1, d_idx1, d_d2, nq, th_low, ratio, d_match, stream ? (cudaStream_t)stream : m->stream);
+    m->launches += nq > 0;
+    CK(cudaGetLastError());
+    return ORBX_OK;
+}
+
+extern "C" int orbm_merge_shards_device(orbm_matcher *m, const int32_t *d_d1, const int32_t *d_idx1, const int32_t *d_d2,
+                                        int nshards, int nq, int32_t *d_od1, int32_t *d_oidx1, int32_t *d_od2, void *stream)
+{
+    if (!m || nq < 0 || nshards < 1 || (nq && (!d_d1 || !d_idx1 || !d_d2 || !d_od1 || !d_oidx1 || !d_od2))) return ORBX_E_INVALID;
+    CK(cudaSetDevice(m->device));
+    launch_merge_shards(d_d1, d_idx1, d_d2, nshards, nq, d_od1, d_oidx1, d_od2, stream ? (cudaStream_t)stream : m->stream);
+    m->launches += nq > 0;
+    CK(cudaGetLastError());
+    return ORBX_OK;
+}
+
+extern "C" int orbm_popc_peak(int device, double *popc_per_second, double *lop3_per_second)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { cudaGetLastError(); return ORBX_E_NODEVICE; }
+    CK(cudaSetDevice(device));
+    int sm = 0;
+    CK(cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device));
+    double a = 0, b = 0;
+    if (run_popc_bench(0, sm, &a)) return cuda_fail(cudaGetLastError(), "popc bench");
+    if (run_popc_bench(1, sm, &b)) return cuda_fail(cudaGetLastError(), "popc+lop3 bench");
+    if (popc_per_second) *popc_per_second = a;
+    if (lop3_per_second) *lop3_per_second = b;
+    return ORBX_OK;
+}

@@ -1,0 +1,261 @@
+// knn.cu -- ORBmatcher::DescriptorDistance (ORBmatcher.cpp:128-144) and the brute-force best-2
+// candidate scan of ORBmatcher.cpp:37-62, plus acceptance (:65-67) and the shard merge.
+//
+// k_knn2: each thread keeps QPT queries (8 x u32 each) in registers; the block streams a database
+// segment through shared memory in 4 KB tiles (cp.async double buffer, 16-byte rows read back as
+// broadcast LDS.128).  Per pair: 8 x (LOP3 xor + POPC) + adds, then a branch-free best-2 update on
+// a packed (distance << 22 | row) key: min of keys == smallest distance, lowest index first, which
+// is exactly the reference's strict '<' scan order.  The database is split into segments over
+// blockIdx.y to fill the 148 SMs; k_knn2_merge folds the per-segment (k1, k2) pairs.
+// Integer-pipe bound (POPC), not HBM bound: compulsory traffic is 32 B per row.
+#include "orbx_internal.cuh"
+
+#include <climits>
+
+namespace orbx {
+
+constexpr int kKnnThreads = 256;
+constexpr int kQPT = 4;                       // queries per thread
+constexpr int kQPB = kKnnThreads * kQPT;      // queries per block
+constexpr int kTileRows = 128;                // database rows per shared-memory tile (4 KB)
+constexpr int kIdxBits = 22;                  // rows per segment < 2^22
+constexpr uint32_t kNoKey = 0xffffffffu;
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__global__ void __launch_bounds__(kKnnThreads)
+k_knn2(const uint4 *__restrict__ query, int nq, const uint4 *__restrict__ db, int ndb, int seg_rows,
+       uint2 *__restrict__ partial)
+{
+    __shared__ __align__(16) uint4 tile[2][kTileRows * 2];
+
+    const int tid = threadIdx.x;
+    const int seg = blockIdx.y;
+    const int row0 = seg * seg_rows;
+    const int rows = min(seg_rows, ndb - row0);
+    const int q0 = blockIdx.x * kQPB;
+
+    uint32_t q[kQPT][8];
+    uint32_t k1[kQPT], k2[kQPT];
+#pragma unroll
+    for (int i = 0; i < kQPT; ++i) {
+        const int qi = min(q0 + i * kKnnThreads + tid, nq - 1);
+        const uint4 a = __ldg(query + 2 * (size_t)qi), b = __ldg(query + 2 * (size_t)qi + 1);
+        q[i][0] = a.x; q[i][1] = a.y; q[i][2] = a.z; q[i][3] = a.w;
+        q[i][4] = b.x; q[i][5] = b.y; q[i][6] = b.z; q[i][7] = b.w;
+        k1[i] = kNoKey; k2[i] = kNoKey;
+    }
+
+    const int ntiles = (rows + kTileRows - 1) / kTileRows;
+    const uint4 *seg_db = db + 2 * (size_t)row0;
+    // prologue: tile 0
+    {
+        const int r = tid;                        // one uint4 per thread: 256 x 16 B = 4 KB
+        if (r < min(rows, kTileRows) * 2) cp_async16(&tile[0][r], seg_db + r);
+        cp_async_commit();
+    }
+    for (int t = 0; t < ntiles; ++t) {
+        const int cur = t & 1;
+        if (t + 1 < ntiles) {
+            const int nrow = min(rows - (t + 1) * kTileRows, kTileRows);
+            if (tid < nrow * 2) cp_async16(&tile[cur ^ 1][tid], seg_db + 2 * (size_t)(t + 1) * kTileRows + tid);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const int trows = min(rows - t * kTileRows, kTileRows);
+        const uint32_t rbase = (uint32_t)(t * kTileRows);
+#pragma unroll 2
+        for (int r = 0; r < trows; ++r) {
+            const uint4 d0 = tile[cur][2 * r], d1 = tile[cur][2 * r + 1];
+#pragma unroll
+            for (int i = 0; i < kQPT; ++i) {
+                const int dist = __popc(q[i][0] ^ d0.x) + __popc(q[i][1] ^ d0.y) + __popc(q[i][2] ^ d0.z) + __popc(q[i][3] ^ d0.w) +
+                                 __popc(q[i][4] ^ d1.x) + __popc(q[i][5] ^ d1.y) + __popc(q[i][6] ^ d1.z) + __popc(q[i][7] ^ d1.w);
+                const uint32_t key = ((uint32_t)dist << kIdxBits) | (rbase + (uint32_t)r);
+                const uint32_t hi = max(k1[i], key);
+                k1[i] = min(k1[i], key);
+                k2[i] = min(k2[i], hi);
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < kQPT; ++i) {
+        const int qi = q0 + i * kKnnThreads + tid;
+        if (qi < nq) partial[(size_t)seg * nq + qi] = make_uint2(k1[i], k2[i]);
+    }
+}
+
+// fold the per-segment pairs: segments are ascending index ranges, so (distance, segment, row)
+// lexicographic order == (distance, global index) order.
+__global__ void __launch_bounds__(256)
+k_knn2_merge(const uint2 *__restrict__ partial, int nq, int nseg, int seg_rows, int index_base,
+             int *__restrict__ d1, int *__restrict__ idx1, int *__restrict__ d2)
+{
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= nq) return;
+    unsigned long long b1 = ~0ull, b2 = ~0ull;
+    for (int s = 0; s < nseg; ++s) {
+        const uint2 p = partial[(size_t)s * nq + qi];
+        const uint32_t ks[2] = { p.x, p.y };
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if (ks[j] == kNoKey) continue;
+            const unsigned long long dist = ks[j] >> kIdxBits, row = (ks[j] & ((1u << kIdxBits) - 1u)) + (unsigned long long)s * seg_rows;
+            const unsigned long long key = (dist << 40) | row;
+            const unsigned long long hi = key > b1 ? key : b1;
+            b1 = key < b1 ? key : b1;
+            b2 = hi < b2 ? hi : b2;
+        }
+    }
+    d1[qi] = b1 == ~0ull ? INT_MAX : (int)(b1 >> 40);
+    idx1[qi] = b1 == ~0ull ? -1 : (int)(b1 & ((1ull << 40) - 1)) + index_base;
+    d2[qi] = b2 == ~0ull ? INT_MAX : (int)(b2 >> 40);
+}
+
+__global__ void k_knn2_empty(int nq, int *d1, int *idx1, int *d2)
+{
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi < nq) { d1[qi] = INT_MAX; idx1[qi] = -1; d2[qi] = INT_MAX; }
+}
+
+__global__ void k_hamming_pairs(const uint4 *__restrict__ a, const uint4 *__restrict__ b, int n, int *__restrict__ dist)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 a0 = a[2 * (size_t)i], a1 = a[2 * (size_t)i + 1], b0 = b[2 * (size_t)i], b1 = b[2 * (size_t)i + 1];
+    dist[i] = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+              __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+__global__ void k_ratio_select(const int *__restrict__ d1, const int *__restrict__ idx1, const int *__restrict__ d2,
+                               int nq, int th_low, float ratio, int *__restrict__ match)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    int m = -1;
+    // ORBmatcher.cpp:65-67: int <= int, then float compare of bestDist against (float)bestDist2 * ratio
+    if (idx1[i] >= 0 && d1[i] <= th_low && (float)d1[i] < __fmul_rn((float)d2[i], ratio)) m = idx1[i];
+    match[i] = m;
+}
+
+// shard merge: re-run the :52-61 update over (d1, d2) of each shard in ascending shard order
+__global__ void k_merge_shards(const int *__restrict__ d1, const int *__restrict__ idx1, const int *__restrict__ d2,
+                               int nshards, int nq, int *__restrict__ od1, int *__restrict__ oidx1, int *__restrict__ od2)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    int best = INT_MAX, best2 = INT_MAX, bidx = -1;
+    for (int s = 0; s < nshards; ++s) {
+        const size_t k = (size_t)s * nq + i;
+        const int id = idx1[k];
+        if (id < 0) continue;
+        const int a = d1[k], b = d2[k];
+        if (a < best) { best2 = best; best = a; bidx = id; } else if (a < best2) best2 = a;
+        if (b < best2) best2 = b;     // b >= a, so it can never become 'best'
+    }
+    od1[i] = best; oidx1[i] = bidx; od2[i] = best2;
+}
+
+// ---- integer-pipe microbenchmarks (roofline denominators for k_knn2) ----
+template <int MODE>
+__global__ void __launch_bounds__(256)
+k_popc_bench(uint32_t *out, int iters, uint32_t seed)
+{
+    uint32_t a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = seed * (threadIdx.x + 1) + i * 0x9e3779b9u + blockIdx.x;
+    uint32_t k = seed;
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (MODE == 0) a[i] = __popc(a[i]) + 0x01010101u * 0;          // POPC only (dependent per chain, 16 chains)
+            if (MODE == 1) a[i] = __popc(a[i] ^ k);                         // LOP3 + POPC
+            if (MODE == 2) a[i] = (a[i] ^ k) + (a[i] >> 1);                 // ALU only (LOP3/SHF/IADD)
+        }
+        k = k * 1664525u + 1013904223u;
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+// ---- host launchers (called from abi.cu) ----
+int knn_segments(int nq, int ndb, int sm_count, int *seg_rows_out)
+{
+    const int gx = (nq + kQPB - 1) / kQPB;
+    int target = (sm_count * 4 * 4 + gx - 1) / gx;            // ~4 waves of 4 blocks/SM
+    int max_by_rows = (ndb + kTileRows - 1) / kTileRows;      // at least one tile per segment
+    int nseg = target < 1 ? 1 : target;
+    if (nseg > max_by_rows) nseg = max_by_rows;
+    const int min_seg = (int)(((long long)ndb + (1 << kIdxBits) - 2) / ((1 << kIdxBits) - 1));
+    if (nseg < min_seg) nseg = min_seg;
+    if (nseg < 1) nseg = 1;
+    if (nseg > 65535) nseg = 65535;
+    int seg_rows = (ndb + nseg - 1) / nseg;
+    seg_rows = (seg_rows + kTileRows - 1) / kTileRows * kTileRows;
+    nseg = (ndb + seg_rows - 1) / seg_rows;
+    *seg_rows_out = seg_rows;
+    return nseg;
+}
+
+void launch_knn2(const uint8_t *d_query, int nq, const uint8_t *d_db, int ndb, int index_base, int nseg, int seg_rows,
+                 uint2 *partial, int *d1, int *idx1, int *d2, cudaStream_t s)
+{
+    if (nq <= 0) return;
+    if (ndb <= 0) { k_knn2_empty<<<(nq + 255) / 256, 256, 0, s>>>(nq, d1, idx1, d2); return; }
+    dim3 grd((nq + kQPB - 1) / kQPB, nseg);
+    k_knn2<<<grd, kKnnThreads, 0, s>>>((const uint4 *)d_query, nq, (const uint4 *)d_db, ndb, seg_rows, partial);
+    k_knn2_merge<<<(nq + 255) / 256, 256, 0, s>>>(partial, nq, nseg, seg_rows, index_base, d1, idx1, d2);
+}
+
+void launch_hamming_pairs(const uint8_t *a, const uint8_t *b, int n, int *dist, cudaStream_t s)
+{
+    if (n > 0) k_hamming_pairs<<<(n + 255) / 256, 256, 0, s>>>((const uint4 *)a, (const uint4 *)b, n, dist);
+}
+void launch_ratio_select(const int *d1, const int *idx1, const int *d2, int nq, int th, float ratio, int *match, cudaStream_t s)
+{
+    if (nq > 0) k_ratio_select<<<(nq + 255) / 256, 256, 0, s>>>(d1, idx1, d2, nq, th, ratio, match);
+}
+void launch_merge_shards(const int *d1, const int *idx1, const int *d2, int nshards, int nq, int *od1, int *oidx1, int *od2, cudaStream_t s)
+{
+    if (nq > 0) k_merge_shards<<<(nq + 255) / 256, 256, 0, s>>>(d1, idx1, d2, nshards, nq, od1, oidx1, od2);
+}
+
+int run_popc_bench(int mode, int sm_count, double *ops_per_second)
+{
+    const int blocks = sm_count * 8, iters = 4096;
+    uint32_t *out = nullptr;
+    if (cudaMalloc(&out, (size_t)blocks * 256 * 4) != cudaSuccess) return -1;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0);
+        if (mode == 0) k_popc_bench<0><<<blocks, 256>>>(out, iters, 12345u + rep);
+        else if (mode == 1) k_popc_bench<1><<<blocks, 256>>>(out, iters, 12345u + rep);
+        else k_popc_bench<2><<<blocks, 256>>>(out, iters, 12345u + rep);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(out);
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    *ops_per_second = (double)blocks * 256.0 * iters * 16.0 / (best * 1e-3);
+    return 0;
+}
+
+} // namespace orbx

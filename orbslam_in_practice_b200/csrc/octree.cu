@@ -1,0 +1,399 @@
+// octree.cu -- DistributeOctTree (ORBextractor.cpp:489-718) as a deterministic block-parallel
+// algorithm: one thread block per (level, frame) problem.
+//
+// Parallel restatement.  Keys (packed candidates) live in a ping-pong array
+// where every node owns a contiguous range whose internal order is the candidate order, so a
+// DivideNode is a *stable 4-way partition inside the parent's range*.  The std::list is a node
+// table in list order.  One pass =
+//   A  block-wide exclusive scan over all keys of the one-hot quadrant vector (stable ranks)
+//   B  per node: child sizes from the scan at the range ends
+//   C  choose the nodes to split and their processing rank
+//        phase 1 (:558-617): every >1-key node, in list order
+//        phase 2 (:629-691): >1-key nodes sorted by (size desc, later-created first = smaller
+//                            list index first); cut at the first prefix with size >= N (:684)
+//   D  scans over the processing order -> creation index of every child; push_front means the
+//      new list is [children, latest created first] ++ [untouched nodes in old order]
+//   E  write the new node table;  F  move the keys.
+// The result (set AND order) equals the sequential reference under the defined tie-break
+// "equal sizes: later-created node first" (= the reference under a monotonic allocator).
+#include "orbx_internal.cuh"
+
+namespace orbx {
+
+constexpr int kOctThreads = 256;
+constexpr int kOctWarps = kOctThreads / 32;
+
+struct __align__(16) Node {
+    short x0, y0, x1, y1;
+    int begin, count;
+};
+
+struct OctShared {
+    int warp_i[kOctWarps + 1];
+    uint4 warp_v[kOctWarps + 1];
+    int size, n, nsplit, C, U, nToExpand, J, pending;
+};
+
+__device__ __forceinline__ int warp_incl_scan(int v)
+{
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+    return v;
+}
+
+// exclusive scan of one int per thread over the block; returns exclusive prefix, total via ref
+__device__ __forceinline__ int block_excl_scan(int v, OctShared &S, int &total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int inc = warp_incl_scan(v);
+    if (lane == 31) S.warp_i[warp] = inc;
+    __syncthreads();
+    int off = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kOctWarps; ++w) { const int t = S.warp_i[w]; if (w < warp) off += t; tot += t; }
+    __syncthreads();
+    total = tot;
+    return off + inc - v;
+}
+
+__device__ __forceinline__ uint4 add4(uint4 a, uint4 b) { return make_uint4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+__device__ __forceinline__ uint4 block_excl_scan4(uint4 v, OctShared &S, uint4 &total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint4 inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint4 t;
+        t.x = __shfl_up_sync(0xffffffffu, inc.x, o); t.y = __shfl_up_sync(0xffffffffu, inc.y, o);
+        t.z = __shfl_up_sync(0xffffffffu, inc.z, o); t.w = __shfl_up_sync(0xffffffffu, inc.w, o);
+        if (lane >= o) inc = add4(inc, t);
+    }
+    if (lane == 31) S.warp_v[warp] = inc;
+    __syncthreads();
+    uint4 off = make_uint4(0, 0, 0, 0), tot = off;
+#pragma unroll
+    for (int w = 0; w < kOctWarps; ++w) { const uint4 t = S.warp_v[w]; if (w < warp) off = add4(off, t); tot = add4(tot, t); }
+    __syncthreads();
+    total = tot;
+    return make_uint4(off.x + inc.x - v.x, off.y + inc.y - v.y, off.z + inc.z - v.z, off.w + inc.w - v.w);
+}
+
+__device__ __forceinline__ int quadrant(uint32_t key, const Node &nd)
+{
+    // DivideNode :433-434, :462-476
+    const int sx = nd.x0 + ((nd.x1 - nd.x0 + 1) >> 1), sy = nd.y0 + ((nd.y1 - nd.y0 + 1) >> 1);
+    const bool left = cand_x(key) < sx, up = cand_y(key) < sy;
+    return left ? (up ? 0 : 2) : (up ? 1 : 3);
+}
+
+__device__ __forceinline__ uint32_t comp(const uint4 &v, int q) { return q == 0 ? v.x : q == 1 ? v.y : q == 2 ? v.z : v.w; }
+
+__global__ void __launch_bounds__(kOctThreads)
+k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, const uint32_t *__restrict__ cell_slots,
+         uint32_t *keysA_all, uint32_t *keysB_all, uint16_t *nodeA_all, uint16_t *nodeB_all, uint4 *scanE_all,
+         int *__restrict__ ncand_out, uint32_t *__restrict__ kept_out, int *__restrict__ nkept_out)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ OctShared S;
+
+    const int level = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+    const LevelGeom &L = g.lv[level];
+    const int NC = L.node_cap;
+    // dynamic shared memory carve-up (sized by the largest level's node_cap)
+    Node *nodes = reinterpret_cast<Node *>(smem_raw);
+    Node *nodesN = nodes + NC;
+    int *childCnt = reinterpret_cast<int *>(nodesN + NC);   // [4*NC]
+    int *newIdx = childCnt + 4 * NC;                        // [4*NC]
+    int *rank = newIdx + 4 * NC;                            // [NC]
+    int *arr = rank + NC;                                   // [NC] processing-order scratch
+    int *ubase = arr + NC;                                  // [NC]
+    unsigned char *nonEmpty = reinterpret_cast<unsigned char *>(ubase + NC); // [NC]
+    unsigned char *split = nonEmpty + NC;                   // [NC]
+
+    uint32_t *kA = keysA_all + (size_t)f * g.keys_per_frame + L.key_base;
+    uint32_t *kB = keysB_all + (size_t)f * g.keys_per_frame + L.key_base;
+    uint16_t *nA = nodeA_all + (size_t)f * g.keys_per_frame + L.key_base;
+    uint16_t *nB = nodeB_all + (size_t)f * g.keys_per_frame + L.key_base;
+    uint4 *E = scanE_all + (size_t)f * (g.keys_per_frame + g.nlevels) + L.key_base + level;
+    int *celloff = reinterpret_cast<int *>(E);              // reused before the first scan
+
+    const int N = L.N;
+    const int nCells = L.nCols * L.nRows;
+    const int *ccount = cell_count + (size_t)f * g.total_cells + L.cell_base;
+    const uint32_t *cslots = cell_slots + (size_t)f * g.slots_per_frame + L.slot_base;
+
+    // ---- gather candidates in reference order (cell row-major, in-cell row-major) into kB ----
+    {
+        int carry = 0;
+        for (int base = 0; base < nCells; base += kOctThreads) {
+            const int c = base + tid;
+            const int v = c < nCells ? ccount[c] : 0;
+            int tot;
+            const int ex = block_excl_scan(v, S, tot);
+            if (c < nCells) celloff[c] = carry + ex;
+            carry += tot;
+        }
+        if (tid == 0) { S.n = carry; ncand_out[f * g.nlevels + level] = carry; }
+        __syncthreads();
+        const int lane = tid & 31, warp = tid >> 5;
+        for (int c = warp; c < nCells; c += kOctWarps) {
+            const int cnt = ccount[c], off = celloff[c];
+            for (int i = lane; i < cnt; i += 32) kB[off + i] = cslots[(size_t)c * L.cell_cap + i];
+        }
+        __syncthreads();
+    }
+    const int n = S.n;
+
+    // ---- roots (:493-535): stable partition of kB by root index into kA ----
+    const int nIni = L.nIni;
+    if (nIni <= 0 || n == 0) { if (tid == 0) nkept_out[f * g.nlevels + level] = 0; return; }
+    {
+        const float hX = L.hX;
+        int placed = 0, nroots = 0;
+        for (int r = 0; r < nIni; ++r) {
+            int carry = 0;
+            for (int base = 0; base < n; base += kOctThreads) {
+                const int p = base + tid;
+                uint32_t key = 0; int flag = 0;
+                if (p < n) {
+                    key = kB[p];
+                    int ri = (int)((float)cand_x(key) / hX);      // :519
+                    ri = min(ri, nIni - 1);
+                    flag = (ri == r);
+                }
+                int tot;
+                const int ex = block_excl_scan(flag, S, tot);
+                if (flag) { kA[placed + carry + ex] = key; nA[placed + carry + ex] = (uint16_t)nroots; }
+                carry += tot;
+            }
+            if (carry > 0) {
+                if (tid == 0) {
+                    Node nd;
+                    nd.x0 = (short)(int)(hX * (float)r); nd.x1 = (short)(int)(hX * (float)(r + 1));  // :505-506
+                    nd.y0 = 0; nd.y1 = (short)L.regionH;
+                    nd.begin = placed; nd.count = carry;
+                    nodes[nroots] = nd;
+                }
+                ++nroots;
+                placed += carry;
+            }
+        }
+        if (tid == 0) S.size = nroots;
+        __syncthreads();
+    }
+
+    bool phase2 = false;
+#pragma unroll 1
+    for (;;) {
+        const int size = S.size;
+        const int prevSize = size;
+
+        // ---- A: stable ranks of every key inside its future child ----
+        {
+            uint4 carry = make_uint4(0, 0, 0, 0);
+            for (int base = 0; base < n; base += kOctThreads) {
+                const int p = base + tid;
+                uint4 c = make_uint4(0, 0, 0, 0);
+                if (p < n) {
+                    const Node nd = nodes[nA[p]];
+                    if (nd.count > 1) {
+                        const int q = quadrant(kA[p], nd);
+                        c.x = q == 0; c.y = q == 1; c.z = q == 2; c.w = q == 3;
+                    }
+                }
+                uint4 tot;
+                const uint4 ex = block_excl_scan4(c, S, tot);
+                if (p < n) E[p] = add4(carry, ex);
+                carry = add4(carry, tot);
+            }
+            if (tid == 0) { E[n] = carry; S.nToExpand = 0; S.J = 0x7fffffff; S.pending = 0; }
+            __syncthreads();
+        }
+        // ---- B: child sizes ----
+        for (int gi = tid; gi < size; gi += kOctThreads) {
+            const Node nd = nodes[gi];
+            int ne = 0;
+            if (nd.count > 1) {
+                const uint4 e0 = E[nd.begin], e1 = E[nd.begin + nd.count];
+                const int c0 = e1.x - e0.x, c1 = e1.y - e0.y, c2 = e1.z - e0.z, c3 = e1.w - e0.w;
+                childCnt[4 * gi] = c0; childCnt[4 * gi + 1] = c1; childCnt[4 * gi + 2] = c2; childCnt[4 * gi + 3] = c3;
+                ne = (c0 > 0) + (c1 > 0) + (c2 > 0) + (c3 > 0);
+            }
+            nonEmpty[gi] = (unsigned char)ne;
+        }
+        __syncthreads();
+        // ---- C: which nodes split, and in which processing order ----
+        if (!phase2) {
+            int carry = 0;
+            for (int base = 0; base < size; base += kOctThreads) {
+                const int gi = base + tid;
+                const int fl = gi < size ? (nodes[gi].count > 1) : 0;
+                int tot;
+                const int ex = block_excl_scan(fl, S, tot);
+                if (gi < size) { split[gi] = (unsigned char)fl; rank[gi] = carry + ex; }
+                carry += tot;
+            }
+            if (tid == 0) S.nsplit = carry;
+            __syncthreads();
+        } else {
+            // sort key (:638 ascending, walked from the back): more keys first; ties -> later created
+            // first.  Pending nodes were all created in the previous pass, where creation order is
+            // the reverse of list order, so "later created" == smaller list index.
+            for (int gi = tid; gi < size; gi += kOctThreads) {
+                const int cg = nodes[gi].count;
+                int r = -1;
+                if (cg > 1) {
+                    r = 0;
+                    for (int j = 0; j < size; ++j) {
+                        const int cj = nodes[j].count;
+                        r += (cj > 1) && (cj > cg || (cj == cg && j < gi));
+                    }
+                    atomicAdd(&S.pending, 1);
+                }
+                rank[gi] = r;
+                if (r >= 0) arr[r] = (int)nonEmpty[gi] - 1;   // gain of splitting this node
+            }
+            __syncthreads();
+            const int P = S.pending;
+            int carry = 0;
+            for (int base = 0; base < P; base += kOctThreads) {
+                const int r = base + tid;
+                const int v = r < P ? arr[r] : 0;
+                int tot;
+                const int ex = block_excl_scan(v, S, tot);
+                if (r < P && size + carry + ex + v >= N) atomicMin(&S.J, r);   // :684 break
+                carry += tot;
+            }
+            __syncthreads();
+            const int J = min(S.J, P - 1);
+            for (int gi = tid; gi < size; gi += kOctThreads) split[gi] = (unsigned char)(rank[gi] >= 0 && rank[gi] <= J);
+            if (tid == 0) S.nsplit = J + 1;
+            __syncthreads();
+        }
+        const int nsplit = S.nsplit;
+        // ---- D: creation index of every child, list slot of every untouched node ----
+        for (int gi = tid; gi < size; gi += kOctThreads) if (split[gi]) arr[rank[gi]] = nonEmpty[gi];
+        __syncthreads();
+        {
+            int carry = 0;
+            for (int base = 0; base < nsplit; base += kOctThreads) {
+                const int r = base + tid;
+                const int v = r < nsplit ? arr[r] : 0;
+                int tot;
+                const int ex = block_excl_scan(v, S, tot);
+                if (r < nsplit) arr[r] = carry + ex;
+                carry += tot;
+            }
+            if (tid == 0) S.C = carry;
+            int ucarry = 0;
+            for (int base = 0; base < size; base += kOctThreads) {
+                const int gi = base + tid;
+                const int fl = gi < size ? !split[gi] : 0;
+                int tot;
+                const int ex = block_excl_scan(fl, S, tot);
+                if (gi < size) ubase[gi] = ucarry + ex;
+                ucarry += tot;
+            }
+            if (tid == 0) S.U = ucarry;
+            __syncthreads();
+        }
+        const int C = S.C, U = S.U;
+        // ---- E: new node table ----
+        {
+            int expand = 0;
+            for (int gi = tid; gi < size; gi += kOctThreads) {
+                const Node nd = nodes[gi];
+                if (split[gi]) {
+                    const int sx = nd.x0 + ((nd.x1 - nd.x0 + 1) >> 1), sy = nd.y0 + ((nd.y1 - nd.y0 + 1) >> 1);
+                    int ci = arr[rank[gi]], off = 0;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int cnt = childCnt[4 * gi + q];
+                        int pos = -1;
+                        if (cnt > 0) {
+                            pos = C - 1 - ci; ++ci;                 // push_front: latest created first
+                            Node ch;
+                            ch.x0 = (q & 1) ? (short)sx : nd.x0; ch.x1 = (q & 1) ? nd.x1 : (short)sx;
+                            ch.y0 = (q & 2) ? (short)sy : nd.y0; ch.y1 = (q & 2) ? nd.y1 : (short)sy;
+                            ch.begin = nd.begin + off; ch.count = cnt;
+                            nodesN[pos] = ch;
+                            off += cnt;
+                            expand += cnt > 1;
+                        }
+                        newIdx[4 * gi + q] = pos;
+                    }
+                } else {
+                    const int pos = C + ubase[gi];
+                    nodesN[pos] = nd;
+                    newIdx[4 * gi] = pos;
+                }
+            }
+            if (expand) atomicAdd(&S.nToExpand, expand);
+            __syncthreads();
+        }
+        // ---- F: move keys ----
+        for (int p = tid; p < n; p += kOctThreads) {
+            const int gi = nA[p];
+            const uint32_t key = kA[p];
+            if (split[gi]) {
+                const Node nd = nodes[gi];
+                const int q = quadrant(key, nd);
+                int off = 0;
+#pragma unroll
+                for (int qq = 0; qq < 3; ++qq) if (qq < q) off += childCnt[4 * gi + qq];
+                const int np = nd.begin + off + (int)(comp(E[p], q) - comp(E[nd.begin], q));
+                kB[np] = key; nB[np] = (uint16_t)newIdx[4 * gi + q];
+            } else {
+                kB[p] = key; nB[p] = (uint16_t)newIdx[4 * gi];
+            }
+        }
+        __syncthreads();
+        { uint32_t *t = kA; kA = kB; kB = t; uint16_t *u = nA; nA = nB; nB = u; Node *v = nodes; nodes = nodesN; nodesN = v; }
+        const int newSize = C + U;
+        const int nToExpand = S.nToExpand;
+        __syncthreads();
+        if (tid == 0) S.size = newSize;
+        __syncthreads();
+        if (newSize >= N || newSize == prevSize) break;                 // :621-624 / :688
+        if (!phase2 && newSize + nToExpand * 3 > N) phase2 = true;      // :626
+    }
+
+    // ---- :697-715 keep the best key of every node (first maximum wins), list order ----
+    const int size = S.size;
+    uint32_t *kept = kept_out + (size_t)f * g.kept_total + L.kept_base;
+    for (int gi = tid; gi < size && gi < L.kept_cap; gi += kOctThreads) {
+        const Node nd = nodes[gi];
+        uint32_t best = kA[nd.begin];
+        for (int k = 1; k < nd.count; ++k) {
+            const uint32_t key = kA[nd.begin + k];
+            if (cand_score(key) > cand_score(best)) best = key;
+        }
+        kept[gi] = best;
+    }
+    if (tid == 0) nkept_out[f * g.nlevels + level] = min(size, L.kept_cap);
+}
+
+int octree_smem_bytes(const Geo &g)
+{
+    int nc = 0;
+    for (int l = 0; l < g.nlevels; ++l) nc = nc > g.lv[l].node_cap ? nc : g.lv[l].node_cap;
+    // 2 node tables + childCnt + newIdx (4 ints each) + rank + arr + ubase + 2 byte flags
+    return nc * (2 * (int)sizeof(Node) + 4 * 4 * 2 + 3 * 4 + 2) + 64;
+}
+
+int octree_configure(int smem_bytes)
+{
+    cudaError_t e = cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    return e == cudaSuccess ? 0 : -1;
+}
+
+void launch_octree(const Geo &g, const DevBuffers &b, int nframes, int smem_bytes, cudaStream_t s)
+{
+    dim3 grd(g.nlevels, nframes);
+    k_octree<<<grd, kOctThreads, smem_bytes, s>>>(g, b.cell_count, b.cell_slots, b.keysA, b.keysB, b.nodeA, b.nodeB,
+                                                  b.scanE, b.ncand, b.kept, b.nkept);
+}
+
+} // namespace orbx

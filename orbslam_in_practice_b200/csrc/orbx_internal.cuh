@@ -1,0 +1,87 @@
+// orbx_internal.cuh -- shared definitions of the sm_100a ORB front end (not part of the ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/orbx.h"
+
+namespace orbx {
+
+constexpr int kPadX = 32;            // left pad of every pyramid row (>= 19, keeps the interior 32 B aligned)
+constexpr int kPadY = ORBX_EDGE_THRESHOLD;
+constexpr int kBorder = ORBX_EDGE_THRESHOLD;
+constexpr int kHalfPatch = 15;       // HALF_PATCH_SIZE, ORBextractor.cpp:23
+constexpr int kMinBorder = 16;       // EDGE_THRESHOLD - 3, ORBextractor.cpp:729
+
+// packed FAST candidate: x (12 bit) | y (12 bit) << 12 | score (8 bit) << 24, coordinates
+// relative to (16,16) of the level (the values of vToDistributeKeys).
+__host__ __device__ inline uint32_t pack_cand(int x, int y, int score) { return (uint32_t)x | ((uint32_t)y << 12) | ((uint32_t)score << 24); }
+__host__ __device__ inline int cand_x(uint32_t k) { return (int)(k & 0xfffu); }
+__host__ __device__ inline int cand_y(uint32_t k) { return (int)((k >> 12) & 0xfffu); }
+__host__ __device__ inline int cand_score(uint32_t k) { return (int)(k >> 24); }
+
+struct LevelGeom {
+    int w, h;                 // level size (cvRound((float)dim * invScale), ORBextractor.cpp:1075-1076)
+    int pitch;                // bytes per row of the bordered level buffer
+    int blur_pitch;
+    unsigned long long base;          // byte offset of frame 0's buffer for this level inside pyr
+    unsigned long long frame_stride;  // bytes between consecutive frames of this level
+    unsigned long long blur_base, blur_frame_stride;
+    // per-cell FAST grid, ORBextractor.cpp:729-743
+    int nCols, nRows, wCell, hCell, maxBorderX, maxBorderY;
+    int cell_base;            // first cell index of this level inside a frame's cell arrays
+    int cell_cap;             // candidate slots per cell: ceil(wCell/2)*ceil(hCell/2) (NMS bound)
+    unsigned long long slot_base;     // u32 offset of this level's slots inside a frame's slot region
+    // octree, ORBextractor.cpp:489-513
+    int N, nIni, regionW, regionH;
+    float hX;
+    int max_cand;             // nCells * cell_cap
+    unsigned long long key_base;      // u32 offset of this level's key scratch inside a frame's region
+    int kept_cap, kept_base;  // survivors bound and offset inside a frame's kept array
+    int node_cap;             // octree node table capacity
+    float scale;              // mvScaleFactor[level]
+    int patch_size;           // (int)(31 * scale), ORBextractor.cpp:794
+    // resize tables (levels >= 1): entries {src offset, c0 | c1 << 16}
+    int tabx, taby;           // offsets into the int2 table array
+};
+
+struct Geo {
+    int nlevels, ini_th, min_th, border_on;
+    int total_cells;          // cells per frame, all levels
+    int capacity;             // output keypoint slots per frame
+    int kept_total;           // kept slots per frame (= capacity)
+    unsigned long long pyr_frame_total, blur_frame_total; // unused when per-level strides are used
+    unsigned long long slots_per_frame, keys_per_frame;
+    LevelGeom lv[ORBX_MAX_LEVELS];
+    int umax[16];
+};
+
+struct DevBuffers {
+    uint8_t *pyr;        // bordered pyramid levels, level-major then frame
+    uint8_t *blur;       // blurred levels
+    int2 *tables;        // resize tables
+    int *cell_count;     // [F][total_cells]
+    uint32_t *cell_slots;// [F][slots_per_frame]
+    uint32_t *keysA, *keysB;   // [F][keys_per_frame]
+    uint16_t *nodeA, *nodeB;   // [F][keys_per_frame]
+    uint4 *scanE;        // [F][keys_per_frame + nlevels]
+    int *ncand;          // [F][nlevels]
+    uint32_t *kept;      // [F][kept_total]
+    int *nkept;          // [F][nlevels]
+    uint8_t *staging;    // device staging for host inputs [max_batch][max_h][max_w]
+    orbx_keypoint *out_kps; uint8_t *out_desc; int *out_counts; // device outputs for the host path
+};
+
+// kernels (defined in the .cu files)
+void launch_level0(const Geo &g, const DevBuffers &b, const uint8_t *d_imgs, size_t pitch, size_t fstride, int nframes, cudaStream_t s);
+void launch_resize(const Geo &g, const DevBuffers &b, int level, int nframes, cudaStream_t s);
+void launch_fast(const Geo &g, const DevBuffers &b, int nframes, cudaStream_t s);
+void launch_octree(const Geo &g, const DevBuffers &b, int nframes, int smem_bytes, cudaStream_t s);
+void launch_blur(const Geo &g, const DevBuffers &b, int nframes, cudaStream_t s);
+void launch_describe(const Geo &g, const DevBuffers &b, int nframes, orbx_keypoint *d_kps, uint8_t *d_desc, int *d_counts, cudaStream_t s);
+int octree_smem_bytes(const Geo &g);
+int octree_configure(int smem_bytes);
+
+} // namespace orbx

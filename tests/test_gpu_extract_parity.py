@@ -1,0 +1,115 @@
+"""GPU parity: CUDA extractor (through the C ABI) vs the CPU oracle, stage by stage.
+
+Bars (BASELINE.json north_star): pyramid pixels, FAST scores/candidates, kept keypoint sets:
+bit-exact; angles within 1e-3 rad; >= 99.9 % descriptor bits identical.
+"""
+import numpy as np
+import pytest
+
+from orbslam_in_practice_b200.synth import synth_frame, synth_batch, adversarial_frame
+
+pytestmark = pytest.mark.gpu
+
+ANGLE_TOL_DEG = 1e-3 * 180.0 / np.pi   # 1e-3 rad
+
+
+def _compare_frame(O, ex, oex, img, frame, kps, desc, counts, check_stages=True):
+    ko, do = oex(img)
+    n = int(counts[frame])
+    assert n == len(ko), "keypoint count differs: gpu %d oracle %d" % (n, len(ko))
+    kg, dg = kps[frame, :n], desc[frame, :n]
+    if check_stages:
+        for l in range(ex.nlevels):
+            assert np.array_equal(ex.level(frame, l), oex.level(l)), "pyramid level %d pixels differ" % l
+            cg, co = ex.candidates(frame, l), oex.candidates(l)
+            assert len(cg) == len(co) and np.array_equal(cg, co), "FAST candidates differ at level %d" % l
+            kg_l, ko_l = ex.kept(frame, l), oex.kept(l)
+            assert len(kg_l) == len(ko_l) and np.array_equal(kg_l, ko_l), "octree survivors differ at level %d" % l
+            ob = oex.blurred(l)
+            if ob is not None:
+                assert np.array_equal(ex.level(frame, l, blurred=True), ob), "blurred level %d differs" % l
+    for fld in ("x", "y", "size", "response", "octave", "class_id"):
+        assert np.array_equal(kg[fld], ko[fld]), "keypoint field %s differs" % fld
+    if n:
+        d = np.abs(kg["angle"] - ko["angle"]); d = np.minimum(d, 360.0 - d)
+        assert d.max() <= ANGLE_TOL_DEG, "angle error %g deg" % d.max()
+        bits = np.unpackbits(dg ^ do).sum()
+        assert bits <= 1e-3 * dg.size * 8, "descriptor bits differing: %d of %d" % (bits, dg.size * 8)
+    return n
+
+
+def test_single_vga_frame_all_stages(orbx, oracle):
+    img = synth_frame(0)
+    ex = orbx.Extractor(max_width=640, max_height=480, max_batch=1)
+    oex = oracle.OracleExtractor()
+    kps, desc, counts = ex.extract_host(img)
+    n = _compare_frame(oracle, ex, oex, img, 0, kps, desc, counts)
+    assert n > 900
+    assert np.array_equal(ex.features_per_level, oex.features_per_level)
+    assert np.array_equal(ex.scale_factors, oex.scale_factors)
+    assert np.array_equal(ex.umax, oex.umax)
+
+
+def test_pyramid_border_is_reflect101(orbx, oracle):
+    img = synth_frame(5)
+    ex = orbx.Extractor(max_width=640, max_height=480, max_batch=1)
+    ex.extract_host(img)
+    oex = oracle.OracleExtractor(); oex(img)
+    for l in range(8):
+        assert np.array_equal(ex.level(0, l, border=19), oracle.reflect101_border(oex.level(l), 19))
+
+
+def test_batch_of_frames(orbx, oracle):
+    seeds = list(range(8))
+    imgs = synth_batch(seeds)
+    ex = orbx.Extractor(max_width=640, max_height=480, max_batch=8)
+    oex = oracle.OracleExtractor()
+    kps, desc, counts = ex.extract_host(imgs)
+    for f in range(len(seeds)):
+        _compare_frame(oracle, ex, oex, imgs[f], f, kps, desc, counts, check_stages=(f in (0, 7)))
+
+
+@pytest.mark.parametrize("kind", ["constant", "noise", "checker"])
+def test_adversarial_frames(orbx, oracle, kind):
+    img = adversarial_frame(kind, 320, 240) if kind == "noise" else adversarial_frame(kind)
+    H, W = img.shape
+    ex = orbx.Extractor(max_width=W, max_height=H, max_batch=1)
+    oex = oracle.OracleExtractor()
+    kps, desc, counts = ex.extract_host(img)
+    n = _compare_frame(oracle, ex, oex, img, 0, kps, desc, counts)
+    if kind == "constant":
+        assert n == 0
+
+
+def test_kitti_sized_stereo_pair(orbx, oracle):
+    imgs = synth_batch([0, 1], 1241, 376)
+    ex = orbx.Extractor(nfeatures=2000, max_width=1241, max_height=376, max_batch=2)
+    oex = oracle.OracleExtractor(nfeatures=2000)
+    kps, desc, counts = ex.extract_host(imgs)
+    for f in range(2):
+        _compare_frame(oracle, ex, oex, imgs[f], f, kps, desc, counts)
+
+
+def test_other_parameters_and_smaller_frame_on_same_handle(orbx, oracle):
+    ex = orbx.Extractor(nfeatures=500, scale_factor=1.5, nlevels=5, ini_th=30, min_th=10,
+                        max_width=640, max_height=480, max_batch=2)
+    oex = oracle.OracleExtractor(500, 1.5, 5, 30, 10)
+    for (w, h, seed) in [(640, 480, 11), (512, 384, 12), (640, 480, 13)]:
+        img = synth_frame(seed, w, h)
+        kps, desc, counts = ex.extract_host(img)
+        _compare_frame(oracle, ex, oex, img, 0, kps, desc, counts)
+
+
+def test_empty_image_returns_zero_counts(orbx):
+    ex = orbx.Extractor(max_width=64, max_height=64, max_batch=1)
+    counts = np.full(1, 7, np.int32)
+    ex.extract_host_ptr(None, 0, 0, 0, 0, 1, None, None, counts.ctypes.data)
+    assert counts[0] == 0
+
+
+def test_capacity_errors(orbx):
+    ex = orbx.Extractor(max_width=320, max_height=240, max_batch=1)
+    with pytest.raises(orbx.OrbxError):
+        ex.extract_host(np.zeros((480, 640), np.uint8))
+    with pytest.raises(orbx.OrbxError):
+        ex.extract_host(np.zeros((2, 240, 320), np.uint8))
