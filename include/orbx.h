@@ -114,6 +114,14 @@ int orbx_download_kept(orbx_extractor *ex, int frame, int level, orbx_cand *out,
 int orbx_max_candidates(const orbx_extractor *ex, int level);
 /* kernels launched by this handle since creation (for bench.py's gpu_launches) */
 long long orbx_launch_count(const orbx_extractor *ex);
+/* Per-stage device timing.  When enabled, every extract call brackets its stages with CUDA events
+ * on the launch stream; orbx_stage_times returns the mean durations (ms) over the calls made since
+ * profiling was enabled (at most the last 64) for
+ * stages {level0, resize chain, FAST, octree, blur, describe} (ORBX_NUM_STAGES floats).
+ * Synchronises the stream. */
+#define ORBX_NUM_STAGES 6
+int orbx_set_profiling(orbx_extractor *ex, int enabled);
+int orbx_stage_times(orbx_extractor *ex, float *ms);
 
 /* ---------------- matcher ---------------- */
 int orbm_create(int max_queries, int max_db, int device, orbm_matcher **out);
@@ -134,10 +142,16 @@ int orbm_knn2_host(orbm_matcher *m, const uint8_t *query, int nq, const uint8_t 
 /* match[i] = idx1[i] if d1 <= th_low && (float)d1 < (float)d2 * ratio else -1 (ORBmatcher.cpp:65-67) */
 int orbm_ratio_select_device(orbm_matcher *m, const int32_t *d_d1, const int32_t *d_idx1, const int32_t *d_d2,
                              int nq, int th_low, float ratio, int32_t *d_match, void *stream);
-/* Merge `nshards` per-shard triples laid out [shard][nq] (shards in ascending index-range order)
- * into the unsharded result.  Outputs may alias shard 0 of the inputs. */
+/* Merge `nshards` per-shard triples (shards in ascending index-range order) into the unsharded
+ * result.  Shard s of each input array starts at element s * shard_stride (0 = nq, i.e. [shard][nq];
+ * 3 * nq for an all-gathered [shard][3][nq] buffer). */
 int orbm_merge_shards_device(orbm_matcher *m, const int32_t *d_d1, const int32_t *d_idx1, const int32_t *d_d2,
-                             int nshards, int nq, int32_t *d_od1, int32_t *d_oidx1, int32_t *d_od2, void *stream);
+                             int nshards, int nq, size_t shard_stride,
+                             int32_t *d_od1, int32_t *d_oidx1, int32_t *d_od2, void *stream);
+/* device time of the last orbm_knn2_device call's scan kernel and merge kernel (ms); needs
+ * orbm_set_profiling(m, 1) before the call.  Synchronises the stream. */
+int orbm_set_profiling(orbm_matcher *m, int enabled);
+int orbm_knn2_times(orbm_matcher *m, float *scan_ms, float *merge_ms);
 
 /* Integer-pipe microbenchmark used for the kNN roofline: runs a dependent-free POPC loop on every
  * SM and returns measured 32-bit POPC results per second (device-event timed). */

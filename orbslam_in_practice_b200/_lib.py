@@ -24,6 +24,7 @@ ABI_SYMBOLS = [
     "orbx_extract_host", "orbx_extract_device", "orbx_set_pyramid_border",
     "orbx_level_dims", "orbx_download_level", "orbx_level_device_ptr",
     "orbx_download_candidates", "orbx_download_kept", "orbx_max_candidates", "orbx_launch_count",
+    "orbx_set_profiling", "orbx_stage_times", "orbm_set_profiling", "orbm_knn2_times",
     "orbm_create", "orbm_destroy", "orbm_launch_count", "orbm_hamming_pairs_host",
     "orbm_knn2_device", "orbm_knn2_host", "orbm_ratio_select_device", "orbm_merge_shards_device",
     "orbm_popc_peak",
@@ -79,7 +80,11 @@ def load():
     L.orbm_knn2_device.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp, vp, vp]
     L.orbm_knn2_host.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp, vp]
     L.orbm_ratio_select_device.argtypes = [vp, vp, vp, vp, i32, i32, f32, vp, vp]
-    L.orbm_merge_shards_device.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp]
+    L.orbm_merge_shards_device.argtypes = [vp, vp, vp, vp, i32, i32, sz, vp, vp, vp, vp]
+    L.orbx_set_profiling.argtypes = [vp, i32]
+    L.orbx_stage_times.argtypes = [vp, vp]
+    L.orbm_set_profiling.argtypes = [vp, i32]
+    L.orbm_knn2_times.argtypes = [vp, C.POINTER(f32), C.POINTER(f32)]
     L.orbm_popc_peak.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _lib = L
     return L
@@ -168,6 +173,15 @@ class Extractor:
     def kept(self, frame, level):
         return self._cands(load().orbx_download_kept, frame, level, self.capacity)
 
+    def set_profiling(self, on):
+        check(load().orbx_set_profiling(self.h, int(on)))
+
+    def stage_times(self):
+        """ms per stage of the last call: level0, resize chain, FAST, octree, blur, describe"""
+        ms = np.zeros(6, np.float32)
+        check(load().orbx_stage_times(self.h, _p(ms)))
+        return ms
+
     @property
     def launches(self):
         return load().orbx_launch_count(self.h)
@@ -207,9 +221,18 @@ class Matcher:
     def ratio_select_device(self, d1_ptr, idx1_ptr, d2_ptr, nq, th_low, ratio, match_ptr, stream=0):
         check(load().orbm_ratio_select_device(self.h, d1_ptr, idx1_ptr, d2_ptr, nq, th_low, ratio, match_ptr, stream))
 
-    def merge_shards_device(self, d1_ptr, idx1_ptr, d2_ptr, nshards, nq, od1_ptr, oidx1_ptr, od2_ptr, stream=0):
-        check(load().orbm_merge_shards_device(self.h, d1_ptr, idx1_ptr, d2_ptr, nshards, nq, od1_ptr, oidx1_ptr,
-                                              od2_ptr, stream))
+    def merge_shards_device(self, d1_ptr, idx1_ptr, d2_ptr, nshards, nq, od1_ptr, oidx1_ptr, od2_ptr, stream=0,
+                            shard_stride=0):
+        check(load().orbm_merge_shards_device(self.h, d1_ptr, idx1_ptr, d2_ptr, nshards, nq, shard_stride,
+                                              od1_ptr, oidx1_ptr, od2_ptr, stream))
+
+    def set_profiling(self, on):
+        check(load().orbm_set_profiling(self.h, int(on)))
+
+    def knn2_times(self):
+        a, b = C.c_float(), C.c_float()
+        check(load().orbm_knn2_times(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     @property
     def launches(self):

@@ -15,10 +15,10 @@ namespace orbx {
 // knn.cu
 int knn_segments(int nq, int ndb, int sm_count, int *seg_rows_out);
 void launch_knn2(const uint8_t *d_query, int nq, const uint8_t *d_db, int ndb, int index_base, int nseg, int seg_rows,
-                 uint2 *partial, int *d1, int *idx1, int *d2, cudaStream_t s);
+                 uint2 *partial, int *d1, int *idx1, int *d2, cudaStream_t s, cudaEvent_t *ev);
 void launch_hamming_pairs(const uint8_t *a, const uint8_t *b, int n, int *dist, cudaStream_t s);
 void launch_ratio_select(const int *d1, const int *idx1, const int *d2, int nq, int th, float ratio, int *match, cudaStream_t s);
-void launch_merge_shards(const int *d1, const int *idx1, const int *d2, int nshards, int nq, int *od1, int *oidx1, int *od2, cudaStream_t s);
+void launch_merge_shards(const int *d1, const int *idx1, const int *d2, int nshards, int nq, size_t stride, int *od1, int *oidx1, int *od2, cudaStream_t s);
 int run_popc_bench(int mode, int sm_count, double *ops_per_second);
 } // namespace orbx
 
@@ -50,6 +50,10 @@ struct orbx_extractor {
     int nfeat[ORBX_MAX_LEVELS];
     int umax[16];
     int border_on;
+    int profiling;
+    static const int kProfCalls = 64;            // event sets kept (ring) while profiling
+    cudaEvent_t ev[kProfCalls][ORBX_NUM_STAGES + 1];
+    int prof_calls;                              // calls recorded since profiling was enabled
 };
 
 extern "C" const char *orbx_strerror(int code)
@@ -179,6 +183,7 @@ static int build_geometry(const orbx_extractor *ex, int w, int h, Geo &g, std::v
         L.scale = ex->scale[l];
         L.patch_size = (int)(31 * ex->scale[l]);                                // :794
         if (l > 0 && tables) {
+            while (tables->size() & 3) tables->push_back(make_int2(0, 0));   // 32-byte aligned runs for int4 loads
             L.tabx = (int)tables->size(); linear_table(g.lv[l - 1].w, L.w, true, *tables);
             L.taby = (int)tables->size(); linear_table(g.lv[l - 1].h, L.h, false, *tables);
         }
@@ -237,7 +242,8 @@ extern "C" int orbx_create(const orbx_params *p, int max_width, int max_height, 
     orbx_extractor *ex = new (std::nothrow) orbx_extractor();
     if (!ex) return ORBX_E_NOMEM;
     ex->params = *p; ex->device = device; ex->max_w = max_width; ex->max_h = max_height; ex->max_batch = max_batch;
-    ex->launches = 0; ex->last_frames = 0; ex->border_on = 1;
+    ex->launches = 0; ex->last_frames = 0; ex->border_on = 1; ex->profiling = 0; ex->prof_calls = 0;
+    for (auto &set : ex->ev) for (auto &e : set) e = nullptr;
     std::memset(&ex->buf, 0, sizeof(ex->buf));
     build_reference_tables(ex);
     int rc = build_geometry(ex, max_width, max_height, ex->full, nullptr);
@@ -252,7 +258,7 @@ extern "C" int orbx_create(const orbx_params *p, int max_width, int max_height, 
 #define TRY(x) do { rc = (x); if (rc) { orbx_destroy(ex); return rc; } } while (0)
     TRY(dev_alloc(ex, &b.pyr, g.pyr_frame_total));
     TRY(dev_alloc(ex, &b.blur, g.blur_frame_total));
-    TRY(dev_alloc(ex, &b.tables, ntab + 16));
+    TRY(dev_alloc(ex, &b.tables, ntab + 8 * ORBX_MAX_LEVELS));
     TRY(dev_alloc(ex, &b.cell_count, F * g.total_cells));
     TRY(dev_alloc(ex, &b.cell_slots, F * g.slots_per_frame));
     TRY(dev_alloc(ex, &b.keysA, F * g.keys_per_frame));
@@ -280,6 +286,7 @@ extern "C" int orbx_destroy(orbx_extractor *ex)
     cudaSetDevice(ex->device);
     if (ex->stream) { cudaStreamSynchronize(ex->stream); cudaStreamDestroy(ex->stream); }
     for (void *p : ex->allocs) cudaFree(p);
+    for (auto &set : ex->ev) for (auto &e : set) if (e) cudaEventDestroy(e);
     delete ex;
     return ORBX_OK;
 }
@@ -327,12 +334,24 @@ static int run_pipeline(orbx_extractor *ex, const uint8_t *d_imgs, size_t pitch,
         if (rc) return rc;
     }
     const Geo &g = ex->geo;
+    const bool prof = ex->profiling != 0;
+    cudaEvent_t *evs = ex->ev[ex->prof_calls % orbx_extractor::kProfCalls];
+#define STAGE_EVENT(i) do { if (prof) cudaEventRecord(evs[i], s); } while (0)
+    STAGE_EVENT(0);
     launch_level0(g, ex->buf, d_imgs, pitch, fstride, nframes, s);
+    STAGE_EVENT(1);
     for (int l = 1; l < g.nlevels; ++l) launch_resize(g, ex->buf, l, nframes, s);
+    STAGE_EVENT(2);
     if (g.total_cells > 0) launch_fast(g, ex->buf, nframes, s);
+    STAGE_EVENT(3);
     launch_octree(g, ex->buf, nframes, ex->oct_smem, s);
+    STAGE_EVENT(4);
     launch_blur(g, ex->buf, nframes, s);
+    STAGE_EVENT(5);
     launch_describe(g, ex->buf, nframes, d_kps, d_desc, d_counts, s);
+    STAGE_EVENT(6);
+#undef STAGE_EVENT
+    if (prof) ex->prof_calls++;
     ex->launches += 1 + (g.nlevels - 1) + (g.total_cells > 0) + 1 + g.nlevels + 1;
     ex->last_frames = nframes;
     CK(cudaGetLastError());
@@ -479,6 +498,36 @@ extern "C" int orbx_download_kept(orbx_extractor *ex, int frame, int level, orbx
 
 extern "C" long long orbx_launch_count(const orbx_extractor *ex) { return ex ? ex->launches : 0; }
 
+extern "C" int orbx_set_profiling(orbx_extractor *ex, int enabled)
+{
+    if (!ex) return ORBX_E_INVALID;
+    CK(cudaSetDevice(ex->device));
+    if (enabled) {
+        for (auto &set : ex->ev) for (auto &e : set) if (!e) CK(cudaEventCreate(&e));
+        ex->prof_calls = 0;
+    }
+    ex->profiling = enabled ? 1 : 0;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_stage_times(orbx_extractor *ex, float *ms)
+{
+    if (!ex || !ms || ex->prof_calls < 1) return ORBX_E_INVALID;
+    CK(cudaSetDevice(ex->device));
+    // average over the calls recorded since profiling was enabled (at most the last kProfCalls)
+    const int n = ex->prof_calls < orbx_extractor::kProfCalls ? ex->prof_calls : orbx_extractor::kProfCalls;
+    for (int i = 0; i < ORBX_NUM_STAGES; ++i) ms[i] = 0.f;
+    for (int c = 0; c < n; ++c) {
+        CK(cudaEventSynchronize(ex->ev[c][ORBX_NUM_STAGES]));
+        for (int i = 0; i < ORBX_NUM_STAGES; ++i) {
+            float t = 0.f;
+            CK(cudaEventElapsedTime(&t, ex->ev[c][i], ex->ev[c][i + 1]));
+            ms[i] += t / n;
+        }
+    }
+    return ORBX_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // matcher
 // ------------------------------------------------------------------------------------------------
@@ -488,6 +537,8 @@ struct orbm_matcher {
     uint2 *partial; size_t partial_elems;
     uint8_t *d_q, *d_db; int *d_out;   // device staging for the host-pointer entry points
     long long launches;
+    int profiling; bool ev_valid;
+    cudaEvent_t ev[3];
 };
 
 extern "C" int orbm_create(int max_queries, int max_db, int device, orbm_matcher **out)
@@ -519,11 +570,31 @@ extern "C" int orbm_destroy(orbm_matcher *m)
     cudaSetDevice(m->device);
     if (m->stream) { cudaStreamSynchronize(m->stream); cudaStreamDestroy(m->stream); }
     cudaFree(m->partial); cudaFree(m->d_q); cudaFree(m->d_db); cudaFree(m->d_out);
+    for (auto &e : m->ev) if (e) cudaEventDestroy(e);
     delete m;
     return ORBX_OK;
 }
 
 extern "C" long long orbm_launch_count(const orbm_matcher *m) { return m ? m->launches : 0; }
+
+extern "C" int orbm_set_profiling(orbm_matcher *m, int enabled)
+{
+    if (!m) return ORBX_E_INVALID;
+    CK(cudaSetDevice(m->device));
+    if (enabled) for (auto &e : m->ev) if (!e) CK(cudaEventCreate(&e));
+    m->profiling = enabled ? 1 : 0; m->ev_valid = false;
+    return ORBX_OK;
+}
+
+extern "C" int orbm_knn2_times(orbm_matcher *m, float *scan_ms, float *merge_ms)
+{
+    if (!m || !m->ev_valid) return ORBX_E_INVALID;
+    CK(cudaSetDevice(m->device));
+    CK(cudaEventSynchronize(m->ev[2]));
+    if (scan_ms) CK(cudaEventElapsedTime(scan_ms, m->ev[0], m->ev[1]));
+    if (merge_ms) CK(cudaEventElapsedTime(merge_ms, m->ev[1], m->ev[2]));
+    return ORBX_OK;
+}
 
 extern "C" int orbm_knn2_device(orbm_matcher *m, const uint8_t *d_query, int nq, const uint8_t *d_db, int ndb,
                                 int index_base, int32_t *d_d1, int32_t *d_idx1, int32_t *d_d2, void *stream)
@@ -537,7 +608,8 @@ extern "C" int orbm_knn2_device(orbm_matcher *m, const uint8_t *d_query, int nq,
     int seg_rows = 0;
     const int nseg = ndb > 0 ? knn_segments(nq, ndb, m->sm_count, &seg_rows) : 0;
     if ((size_t)nseg * nq > m->partial_elems) return ORBX_E_CAPACITY;
-    launch_knn2(d_query, nq, d_db, ndb, index_base, nseg, seg_rows, m->partial, d_d1, d_idx1, d_d2, s);
+    launch_knn2(d_query, nq, d_db, ndb, index_base, nseg, seg_rows, m->partial, d_d1, d_idx1, d_d2, s, m->profiling ? m->ev : nullptr);
+    m->ev_valid = m->profiling && ndb > 0;
     m->launches += ndb > 0 ? 2 : 1;
     CK(cudaGetLastError());
     return ORBX_OK;
@@ -604,11 +676,12 @@ extern "C" int orbm_ratio_select_device(orbm_matcher *m, const int32_t *d_d1, co
 }
 
 extern "C" int orbm_merge_shards_device(orbm_matcher *m, const int32_t *d_d1, const int32_t *d_idx1, const int32_t *d_d2,
-                                        int nshards, int nq, int32_t *d_od1, int32_t *d_oidx1, int32_t *d_od2, void *stream)
+                                        int nshards, int nq, size_t shard_stride,
+                                        int32_t *d_od1, int32_t *d_oidx1, int32_t *d_od2, void *stream)
 {
     if (!m || nq < 0 || nshards < 1 || (nq && (!d_d1 || !d_idx1 || !d_d2 || !d_od1 || !d_oidx1 || !d_od2))) return ORBX_E_INVALID;
     CK(cudaSetDevice(m->device));
-    launch_merge_shards(d_d1, d_idx1, d_d2, nshards, nq, d_od1, d_oidx1, d_od2, stream ? (cudaStream_t)stream : m->stream);
+    launch_merge_shards(d_d1, d_idx1, d_d2, nshards, nq, shard_stride, d_od1, d_oidx1, d_od2, stream ? (cudaStream_t)stream : m->stream);
     m->launches += nq > 0;
     CK(cudaGetLastError());
     return ORBX_OK;

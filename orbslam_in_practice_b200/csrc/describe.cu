@@ -65,10 +65,6 @@ void launch_blur(const Geo &g, const DevBuffers &b, int nframes, cudaStream_t s)
 // ---------------------------------------------------------------------------------------------
 // orientation + descriptor + epilogue: one warp per output keypoint slot.
 // ---------------------------------------------------------------------------------------------
-__constant__ signed char c_pattern[1024] = {
-#include "orb_pattern_31.inc"
-};
-
 // cv::fastAtan2; separate roundings (no FMA) to match the scalar C++ build.
 __device__ __forceinline__ float fast_atan2_deg(float y, float x)
 {
@@ -93,84 +89,120 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
 }
 
 constexpr int kDescWarps = 8;
+constexpr int kSlotsPerWarp = 4;          // keypoints handled by one warp (amortises the pattern load)
 
 __global__ void __launch_bounds__(kDescWarps * 32)
 k_describe(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, const uint8_t *__restrict__ blur,
            const uint32_t *__restrict__ kept, const int *__restrict__ nkept,
-           orbx_keypoint *__restrict__ out_kps, uint8_t *__restrict__ out_desc, int *__restrict__ out_counts)
+           orbx_keypoint *__restrict__ out_kps, uint8_t *__restrict__ out_desc, int *__restrict__ out_counts,
+           const uint32_t *__restrict__ pattern_words)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int f = blockIdx.y;
-    const int slot = blockIdx.x * kDescWarps + warp;          // output row inside the frame
-    // level-major concatenation (:1036-1063): find the level this slot falls in
+    // lane i owns descriptor byte i = pattern points 16i .. 16i+15 = 32 signed bytes = 8 words
+    uint32_t pw[8];
+    {
+        const uint4 p0 = __ldg(reinterpret_cast<const uint4 *>(pattern_words) + lane * 2);
+        const uint4 p1 = __ldg(reinterpret_cast<const uint4 *>(pattern_words) + lane * 2 + 1);
+        pw[0] = p0.x; pw[1] = p0.y; pw[2] = p0.z; pw[3] = p0.w; pw[4] = p1.x; pw[5] = p1.y; pw[6] = p1.z; pw[7] = p1.w;
+    }
     const int *nk = nkept + f * g.nlevels;
-    int level = -1, first = 0, total = 0;
+    int total = 0;
 #pragma unroll 1
-    for (int l = 0; l < g.nlevels; ++l) {
-        const int c = nk[l];
-        if (level < 0 && slot < total + c) { level = l; first = total; }
-        total += c;
-    }
-    if (slot == 0 && lane == 0) out_counts[f] = total;
-    if (level < 0) return;
-    const LevelGeom &L = g.lv[level];
-    const uint32_t key = kept[(size_t)f * g.kept_total + L.kept_base + (slot - first)];
-    const int x = cand_x(key) + kMinBorder, y = cand_y(key) + kMinBorder;   // :801-802
+    for (int l = 0; l < g.nlevels; ++l) total += nk[l];
+    if (blockIdx.x == 0 && threadIdx.x == 0) out_counts[f] = total;
 
-    // ---- IC_Angle on the un-blurred level: lane = column u, loop rows v ----
-    const uint8_t *img = pyr + L.base + (size_t)f * L.frame_stride + (size_t)(kPadY + y) * L.pitch + kPadX + x;
-    int m10 = 0, m01 = 0;
-    const int u = lane - kHalfPatch;
-    if (lane < 2 * kHalfPatch + 1) {
-        const int au = u < 0 ? -u : u;
+    const int slot0 = (blockIdx.x * kDescWarps + warp) * kSlotsPerWarp;
 #pragma unroll 1
-        for (int v = -kHalfPatch; v <= kHalfPatch; ++v) {
-            if (au <= g.umax[v < 0 ? -v : v]) {
-                const int I = img[v * L.pitch + u];
-                m10 += u * I; m01 += v * I;
-            }
+    for (int si = 0; si < kSlotsPerWarp; ++si) {
+        const int slot = slot0 + si;                          // output row inside the frame
+        if (slot >= total) return;
+        // level-major concatenation (:1036-1063): find the level this slot falls in
+        int level = 0, first = 0;
+#pragma unroll 1
+        for (int l = 0, acc = 0; l < g.nlevels; ++l) {
+            const int c = nk[l];
+            if (slot >= acc && slot < acc + c) { level = l; first = acc; }
+            acc += c;
         }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o); m01 += __shfl_xor_sync(0xffffffffu, m01, o); }
-    const float angle = fast_atan2_deg((float)m01, (float)m10);
+        const LevelGeom &L = g.lv[level];
+        const uint32_t key = kept[(size_t)f * g.kept_total + L.kept_base + (slot - first)];
+        const int x = cand_x(key) + kMinBorder, y = cand_y(key) + kMinBorder;   // :801-802
 
-    // ---- rotated BRIEF: lane i produces descriptor byte i from 16 pattern points ----
-    const float factorPI = (float)(3.14159265358979323846 / (double)180.f);
-    const float ang = __fmul_rn(angle, factorPI);
-    const float a = (float)cos((double)ang), b = (float)sin((double)ang);
-    const uint8_t *center = blur + L.blur_base + (size_t)f * L.blur_frame_stride + (size_t)y * L.blur_pitch + x;
-    const signed char *pat = c_pattern + lane * 32;
-    int val = 0;
+        // ---- IC_Angle on the un-blurred level: lane = column u, all 31 row loads in flight ----
+        const int pitch = L.pitch;
+        const uint8_t *img = pyr + L.base + (size_t)f * L.frame_stride + (size_t)(kPadY + y) * pitch + kPadX + x;
+        int m10 = 0, m01 = 0;
+        const int u = lane - kHalfPatch;
+        const int au = u < 0 ? -u : u;
+        if (lane < 2 * kHalfPatch + 1) {
+            int colsum = 0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        const float x0 = (float)pat[4 * k], y0 = (float)pat[4 * k + 1], x1 = (float)pat[4 * k + 2], y1 = (float)pat[4 * k + 3];
-        const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
-        const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
-        const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
-        const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-        const int t0 = center[r0 * L.blur_pitch + c0], t1 = center[r1 * L.blur_pitch + c1];
-        val |= (t0 < t1) << k;
-    }
-    out_desc[((size_t)f * g.capacity + slot) * 32 + lane] = (uint8_t)val;
+            for (int v = -kHalfPatch; v <= kHalfPatch; ++v) {
+                if (au <= g.umax[v < 0 ? -v : v]) {
+                    const int I = img[v * pitch + u];
+                    colsum += I; m01 += v * I;
+                }
+            }
+            m10 = u * colsum;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o); m01 += __shfl_xor_sync(0xffffffffu, m01, o); }
+        const float angle = fast_atan2_deg((float)m01, (float)m10);
 
-    if (lane == 0) {
-        orbx_keypoint kp;
-        kp.x = (float)x; kp.y = (float)y;
-        if (level != 0) { kp.x = __fmul_rn(kp.x, L.scale); kp.y = __fmul_rn(kp.y, L.scale); }   // :1055-1061
-        kp.size = (float)L.patch_size;
-        kp.angle = angle;
-        kp.response = (float)cand_score(key);
-        kp.octave = level;
-        kp.class_id = -1;
-        out_kps[(size_t)f * g.capacity + slot] = kp;
+        // ---- rotated BRIEF: lane i produces descriptor byte i from its 16 pattern points ----
+        const float factorPI = (float)(3.14159265358979323846 / (double)180.f);
+        const float ang = __fmul_rn(angle, factorPI);
+        const float a = (float)cos((double)ang), b = (float)sin((double)ang);
+        const int bp = L.blur_pitch;
+        const uint8_t *center = blur + L.blur_base + (size_t)f * L.blur_frame_stride + (size_t)y * bp + x;
+        int t[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const uint32_t w = pw[k >> 1];
+            const float px = (float)(int)(signed char)(w >> ((k & 1) * 16));
+            const float py = (float)(int)(signed char)(w >> ((k & 1) * 16 + 8));
+            const int r = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
+            const int c = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
+            t[k] = center[r * bp + c];
+        }
+        int val = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) val |= (t[2 * k] < t[2 * k + 1]) << k;
+        out_desc[((size_t)f * g.capacity + slot) * 32 + lane] = (uint8_t)val;
+
+        if (lane == 0) {
+            orbx_keypoint kp;
+            kp.x = (float)x; kp.y = (float)y;
+            if (level != 0) { kp.x = __fmul_rn(kp.x, L.scale); kp.y = __fmul_rn(kp.y, L.scale); }   // :1055-1061
+            kp.size = (float)L.patch_size;
+            kp.angle = angle;
+            kp.response = (float)cand_score(key);
+            kp.octave = level;
+            kp.class_id = -1;
+            out_kps[(size_t)f * g.capacity + slot] = kp;
+        }
     }
 }
 
+static uint32_t *g_pattern_dev[64] = { nullptr };   // per device copy of the pattern as packed words
+
 void launch_describe(const Geo &g, const DevBuffers &b, int nframes, orbx_keypoint *d_kps, uint8_t *d_desc, int *d_counts, cudaStream_t s)
 {
-    dim3 grd((g.capacity + kDescWarps - 1) / kDescWarps, nframes);
-    k_describe<<<grd, kDescWarps * 32, 0, s>>>(g, b.pyr, b.blur, b.kept, b.nkept, d_kps, d_desc, d_counts);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !g_pattern_dev[dev]) {
+        static const signed char h_pattern[1024] = {
+#include "orb_pattern_31.inc"
+        };
+        uint32_t *p = nullptr;
+        cudaMalloc(&p, 1024);
+        cudaMemcpy(p, h_pattern, 1024, cudaMemcpyHostToDevice);
+        g_pattern_dev[dev] = p;
+    }
+    const int per_block = kDescWarps * kSlotsPerWarp;
+    dim3 grd((g.capacity + per_block - 1) / per_block, nframes);
+    k_describe<<<grd, kDescWarps * 32, 0, s>>>(g, b.pyr, b.blur, b.kept, b.nkept, d_kps, d_desc, d_counts, g_pattern_dev[dev]);
 }
 
 } // namespace orbx

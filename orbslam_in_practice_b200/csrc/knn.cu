@@ -150,13 +150,13 @@ __global__ void k_ratio_select(const int *__restrict__ d1, const int *__restrict
 
 // shard merge: re-run the :52-61 update over (d1, d2) of each shard in ascending shard order
 __global__ void k_merge_shards(const int *__restrict__ d1, const int *__restrict__ idx1, const int *__restrict__ d2,
-                               int nshards, int nq, int *__restrict__ od1, int *__restrict__ oidx1, int *__restrict__ od2)
+                               int nshards, int nq, size_t stride, int *__restrict__ od1, int *__restrict__ oidx1, int *__restrict__ od2)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nq) return;
     int best = INT_MAX, best2 = INT_MAX, bidx = -1;
     for (int s = 0; s < nshards; ++s) {
-        const size_t k = (size_t)s * nq + i;
+        const size_t k = (size_t)s * stride + i;
         const int id = idx1[k];
         if (id < 0) continue;
         const int a = d1[k], b = d2[k];
@@ -211,13 +211,16 @@ int knn_segments(int nq, int ndb, int sm_count, int *seg_rows_out)
 }
 
 void launch_knn2(const uint8_t *d_query, int nq, const uint8_t *d_db, int ndb, int index_base, int nseg, int seg_rows,
-                 uint2 *partial, int *d1, int *idx1, int *d2, cudaStream_t s)
+                 uint2 *partial, int *d1, int *idx1, int *d2, cudaStream_t s, cudaEvent_t *ev)
 {
     if (nq <= 0) return;
     if (ndb <= 0) { k_knn2_empty<<<(nq + 255) / 256, 256, 0, s>>>(nq, d1, idx1, d2); return; }
     dim3 grd((nq + kQPB - 1) / kQPB, nseg);
+    if (ev) cudaEventRecord(ev[0], s);
     k_knn2<<<grd, kKnnThreads, 0, s>>>((const uint4 *)d_query, nq, (const uint4 *)d_db, ndb, seg_rows, partial);
+    if (ev) cudaEventRecord(ev[1], s);
     k_knn2_merge<<<(nq + 255) / 256, 256, 0, s>>>(partial, nq, nseg, seg_rows, index_base, d1, idx1, d2);
+    if (ev) cudaEventRecord(ev[2], s);
 }
 
 void launch_hamming_pairs(const uint8_t *a, const uint8_t *b, int n, int *dist, cudaStream_t s)
@@ -228,9 +231,9 @@ void launch_ratio_select(const int *d1, const int *idx1, const int *d2, int nq, 
 {
     if (nq > 0) k_ratio_select<<<(nq + 255) / 256, 256, 0, s>>>(d1, idx1, d2, nq, th, ratio, match);
 }
-void launch_merge_shards(const int *d1, const int *idx1, const int *d2, int nshards, int nq, int *od1, int *oidx1, int *od2, cudaStream_t s)
+void launch_merge_shards(const int *d1, const int *idx1, const int *d2, int nshards, int nq, size_t stride, int *od1, int *oidx1, int *od2, cudaStream_t s)
 {
-    if (nq > 0) k_merge_shards<<<(nq + 255) / 256, 256, 0, s>>>(d1, idx1, d2, nshards, nq, od1, oidx1, od2);
+    if (nq > 0) k_merge_shards<<<(nq + 255) / 256, 256, 0, s>>>(d1, idx1, d2, nshards, nq, stride ? stride : (size_t)nq, od1, oidx1, od2);
 }
 
 int run_popc_bench(int mode, int sm_count, double *ops_per_second)
