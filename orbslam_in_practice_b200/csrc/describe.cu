@@ -14,51 +14,82 @@ __device__ __forceinline__ int reflect101d(int i, int n)
 }
 
 // ---------------------------------------------------------------------------------------------
-// 7x7 sigma-2 Gaussian in OpenCV's Q8.8 fixed point: taps 18,34,48,56,48,34,18;
-// horizontal pass exact in u16, vertical pass u32, dst = (v + 32768) >> 16.  Border: reflect-101
-// of the level itself (the blur runs on a border-less clone in the reference).
-// One block = 64 x 16 output tile, all levels and frames in one launch (tile table by level).
+// 7x7 sigma-2 Gaussian in OpenCV's Q8.8 fixed point: taps 18,34,48,56,48,34,18,
+// dst = (sum_ij k_i k_j p + 32768) >> 16.  OpenCV runs the horizontal pass first; with exact
+// integer intermediates the order is irrelevant, so this kernel runs the VERTICAL pass first:
+//   * a lane owns one 4-pixel word column and slides down the rows, keeping the last 7 source
+//     words split into even/odd byte lanes (2 x 16 bit per register); the vertical 7-tap sum is
+//     SIMD-within-a-register: every 16-bit lane stays <= 65280, so no carries cross lanes
+//   * the horizontal pass reads the neighbouring word columns with warp shuffles and folds pairs
+//     of 16-bit values with DP2A (2 MACs per instruction) into 32-bit sums
+// No shared memory, no barriers; the reflect-101 border comes for free from the bordered pyramid
+// buffer (>= 4 px are always written).  ncu, round 1: the shared-memory tile version issued 44
+// lane-instructions per pixel; this one ~13.
+// A warp covers 30 output word columns (120 px; lanes 0 and 31 are halo) x kBlurRows rows.
 // ---------------------------------------------------------------------------------------------
-constexpr int kBlurTW = 64, kBlurTH = 16;
+constexpr int kBlurRows = 32;
+constexpr int kBlurWarps = 4;
 
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ uint32_t dp2(uint32_t a, uint32_t wts, uint32_t c) { return __dp2a_lo(a, wts, c); }
+
+__global__ void __launch_bounds__(32 * kBlurWarps)
 k_blur(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, uint8_t *__restrict__ blur, int level)
 {
-    __shared__ uint8_t src[(kBlurTH + 6)][kBlurTW + 8];
-    __shared__ uint16_t hor[(kBlurTH + 6)][kBlurTW];
     const LevelGeom &L = g.lv[level];
-    const int f = blockIdx.z;
-    const int x0 = blockIdx.x * kBlurTW, y0 = blockIdx.y * kBlurTH;
-    const uint8_t *img = pyr + L.base + (size_t)f * L.frame_stride + (size_t)kPadY * L.pitch + kPadX;
-    const int tid = threadIdx.x;
-    for (int i = tid; i < (kBlurTH + 6) * (kBlurTW + 6); i += 256) {
-        const int r = i / (kBlurTW + 6), c = i - r * (kBlurTW + 6);
-        const int y = reflect101d(y0 + r - 3, L.h), x = reflect101d(x0 + c - 3, L.w);
-        src[r][c] = img[(size_t)y * L.pitch + x];
+    const int lane = threadIdx.x, f = blockIdx.z;
+    const int y0 = (blockIdx.y * kBlurWarps + threadIdx.y) * kBlurRows;
+    if (y0 >= L.h) return;
+    const int y1 = min(y0 + kBlurRows, L.h);
+    const int wc_raw = (int)blockIdx.x * 30 + lane - 1;                 // word column (4 px) in the level, -1 = left halo
+    const int wc_max = ((L.pitch - kPadX) >> 2) - 1;
+    const int wc = min(wc_raw, wc_max);
+    const uint8_t *src = pyr + L.base + (size_t)f * L.frame_stride + (size_t)kPadY * L.pitch + kPadX + 4 * wc;
+    uint8_t *dst = blur + L.blur_base + (size_t)f * L.blur_frame_stride + 4 * wc;
+    const bool writer = lane >= 1 && lane <= 30 && 4 * wc_raw < L.w;
+
+    // weights packed for DP2A: low byte multiplies the low 16-bit lane, next byte the high lane
+    constexpr uint32_t K0 = 18, K1 = 34, K2 = 48, K3 = 56;             // k4 = k2, k5 = k1, k6 = k0
+#define W2(a, b) ((uint32_t)(a) | ((uint32_t)(b) << 8))
+    uint32_t lo[7], hi[7];                                             // sliding window of split source rows
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(src + (ptrdiff_t)(y0 - 3 + i) * L.pitch));
+        lo[i] = w & 0x00ff00ffu; hi[i] = (w >> 8) & 0x00ff00ffu;
     }
-    __syncthreads();
-    for (int i = tid; i < (kBlurTH + 6) * kBlurTW; i += 256) {
-        const int r = i / kBlurTW, c = i - r * kBlurTW;
-        const uint8_t *p = &src[r][c];
-        hor[r][c] = (uint16_t)(18 * (p[0] + p[6]) + 34 * (p[1] + p[5]) + 48 * (p[2] + p[4]) + 56 * p[3]);
+    for (int yb = y0; yb < y1; yb += 7) {
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            const int y = yb + j;
+            if (y < y1) {
+                // window slot (j + 6) % 7 receives source row y + 3; rows y-3 .. y+3 are slots j .. j+6 (mod 7)
+                const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(src + (ptrdiff_t)(y + 3) * L.pitch));
+                lo[(j + 6) % 7] = w & 0x00ff00ffu; hi[(j + 6) % 7] = (w >> 8) & 0x00ff00ffu;
+                // vertical 7-tap, two 16-bit lanes per register: V_lo = (V[4c], V[4c+2]), V_hi = (V[4c+1], V[4c+3])
+                const uint32_t vlo = K0 * (lo[j % 7] + lo[(j + 6) % 7]) + K1 * (lo[(j + 1) % 7] + lo[(j + 5) % 7]) +
+                                     K2 * (lo[(j + 2) % 7] + lo[(j + 4) % 7]) + K3 * lo[(j + 3) % 7];
+                const uint32_t vhi = K0 * (hi[j % 7] + hi[(j + 6) % 7]) + K1 * (hi[(j + 1) % 7] + hi[(j + 5) % 7]) +
+                                     K2 * (hi[(j + 2) % 7] + hi[(j + 4) % 7]) + K3 * hi[(j + 3) % 7];
+                const uint32_t plo = __shfl_up_sync(0xffffffffu, vlo, 1), phi = __shfl_up_sync(0xffffffffu, vhi, 1);     // column c-1
+                const uint32_t nlo = __shfl_down_sync(0xffffffffu, vlo, 1), nhi = __shfl_down_sync(0xffffffffu, vhi, 1); // column c+1
+                // horizontal 7-tap on 16-bit values with 32-bit sums (+ rounding), SURVEY.md A2
+                uint32_t o0 = dp2(phi, W2(K0, K2), 32768u); o0 = dp2(plo, W2(0, K1), o0); o0 = dp2(vlo, W2(K3, K1), o0); o0 = dp2(vhi, W2(K2, K0), o0);
+                uint32_t o1 = dp2(plo, W2(0, K0), 32768u);  o1 = dp2(phi, W2(0, K1), o1); o1 = dp2(vlo, W2(K2, K2), o1); o1 = dp2(vhi, W2(K3, K1), o1); o1 = dp2(nlo, W2(K0, 0), o1);
+                uint32_t o2 = dp2(phi, W2(0, K0), 32768u);  o2 = dp2(vlo, W2(K1, K3), o2); o2 = dp2(vhi, W2(K2, K2), o2); o2 = dp2(nlo, W2(K1, 0), o2); o2 = dp2(nhi, W2(K0, 0), o2);
+                uint32_t o3 = dp2(vlo, W2(K0, K2), 32768u); o3 = dp2(vhi, W2(K1, K3), o3); o3 = dp2(nlo, W2(K2, K0), o3); o3 = dp2(nhi, W2(K1, 0), o3);
+                const uint32_t out = (o0 >> 16) | ((o1 >> 16) << 8) | ((o2 >> 16) << 16) | ((o3 >> 16) << 24);
+                if (writer) *reinterpret_cast<uint32_t *>(dst + (size_t)y * L.blur_pitch) = out;
+            }
+        }
     }
-    __syncthreads();
-    uint8_t *dst = blur + L.blur_base + (size_t)f * L.blur_frame_stride;
-    for (int i = tid; i < kBlurTH * kBlurTW; i += 256) {
-        const int r = i / kBlurTW, c = i - r * kBlurTW;
-        const int x = x0 + c, y = y0 + r;
-        if (x >= L.w || y >= L.h) continue;
-        const uint32_t v = 18u * (hor[r][c] + hor[r + 6][c]) + 34u * (hor[r + 1][c] + hor[r + 5][c]) +
-                           48u * (hor[r + 2][c] + hor[r + 4][c]) + 56u * hor[r + 3][c];
-        dst[(size_t)y * L.blur_pitch + x] = (uint8_t)((v + 32768u) >> 16);
-    }
+#undef W2
 }
 
 void launch_blur(const Geo &g, const DevBuffers &b, int nframes, cudaStream_t s)
 {
     for (int l = 0; l < g.nlevels; ++l) {
-        dim3 grd((g.lv[l].w + kBlurTW - 1) / kBlurTW, (g.lv[l].h + kBlurTH - 1) / kBlurTH, nframes);
-        k_blur<<<grd, 256, 0, s>>>(g, b.pyr, b.blur, l);
+        const int words = (g.lv[l].w + 3) / 4;
+        dim3 grd((words + 29) / 30, (g.lv[l].h + kBlurRows * kBlurWarps - 1) / (kBlurRows * kBlurWarps), nframes);
+        k_blur<<<grd, dim3(32, kBlurWarps), 0, s>>>(g, b.pyr, b.blur, l);
     }
 }
 

@@ -12,6 +12,7 @@ namespace orbx {
 constexpr int kPadX = 32;            // left pad of every pyramid row (>= 19, keeps the interior 32 B aligned)
 constexpr int kPadY = ORBX_EDGE_THRESHOLD;
 constexpr int kBorder = ORBX_EDGE_THRESHOLD;
+constexpr int kMinBlurBorder = 4;     // border always written: the blur kernel reads 3 px (+1 for word alignment) outside the level
 constexpr int kHalfPatch = 15;       // HALF_PATCH_SIZE, ORBextractor.cpp:23
 constexpr int kMinBorder = 16;       // EDGE_THRESHOLD - 3, ORBextractor.cpp:729
 

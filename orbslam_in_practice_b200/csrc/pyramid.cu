@@ -31,7 +31,7 @@ k_level0(const __grid_constant__ Geo g, uint8_t *__restrict__ pyr, const uint8_t
          size_t in_pitch, size_t in_fstride, int src_aligned)
 {
     const LevelGeom &L = g.lv[0];
-    const int B = g.border_on ? kBorder : 0;
+    const int B = g.border_on ? kBorder : kMinBlurBorder;
     const int Y = (int)(blockIdx.y * 4 + threadIdx.y) - B;   // bordered row
     const int f = blockIdx.z;
     const int chunk = blockIdx.x * 32 + threadIdx.x;
@@ -78,7 +78,7 @@ k_resize(const __grid_constant__ Geo g, uint8_t *__restrict__ pyr, const int2 *_
 {
     const LevelGeom &D = g.lv[level];
     const LevelGeom &S = g.lv[level - 1];
-    const int B = g.border_on ? kBorder : 0;
+    const int B = g.border_on ? kBorder : kMinBlurBorder;
     const int Y = (int)(blockIdx.y * 4 + threadIdx.y) - B;
     const int f = blockIdx.z;
     const int chunk = blockIdx.x * 32 + threadIdx.x;
@@ -113,7 +113,7 @@ k_resize(const __grid_constant__ Geo g, uint8_t *__restrict__ pyr, const int2 *_
 
 void launch_level0(const Geo &g, const DevBuffers &b, const uint8_t *d_imgs, size_t pitch, size_t fstride, int nframes, cudaStream_t s)
 {
-    const int B = g.border_on ? kBorder : 0;
+    const int B = g.border_on ? kBorder : kMinBlurBorder;
     const int chunks = g.lv[0].pitch / 16;
     const int aligned = ((((uintptr_t)d_imgs) | pitch | fstride) & 15) == 0;
     dim3 grd((chunks + 31) / 32, (g.lv[0].h + 2 * B + 3) / 4, nframes);
@@ -122,7 +122,7 @@ void launch_level0(const Geo &g, const DevBuffers &b, const uint8_t *d_imgs, siz
 
 void launch_resize(const Geo &g, const DevBuffers &b, int level, int nframes, cudaStream_t s)
 {
-    const int B = g.border_on ? kBorder : 0;
+    const int B = g.border_on ? kBorder : kMinBlurBorder;
     const int chunks = g.lv[level].pitch / 4;
     dim3 grd((chunks + 31) / 32, (g.lv[level].h + 2 * B + 3) / 4, nframes);
     k_resize<<<grd, dim3(32, 4), 0, s>>>(g, b.pyr, b.tables, level);
