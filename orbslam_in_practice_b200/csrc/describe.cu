@@ -121,15 +121,23 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
 
 constexpr int kDescWarps = 8;
 constexpr int kSlotsPerWarp = 4;          // keypoints handled by one warp (amortises the pattern load)
+constexpr int kPatchR = 18;               // largest |rotated pattern offset| (18 px)
+constexpr int kPatchRows = 2 * kPatchR + 1;               // 37
+constexpr int kPatchWords = (2 * kPatchR + 1 + 3 + 3) / 4; // 37 px + up to 3 px of alignment slack = 11 words
 
-__global__ void __launch_bounds__(kDescWarps * 32)
+// One warp per keypoint.  ncu, round 1: the direct-gather version needed ~20 L1 wavefronts for each
+// of the 16 scattered descriptor loads per lane; the 37x37 blurred patch is therefore staged in
+// shared memory with coalesced word loads and gathered from there (<= 4-way bank conflicts).
+__global__ void __launch_bounds__(kDescWarps * 32, 4)
 k_describe(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, const uint8_t *__restrict__ blur,
            const uint32_t *__restrict__ kept, const int *__restrict__ nkept,
            orbx_keypoint *__restrict__ out_kps, uint8_t *__restrict__ out_desc, int *__restrict__ out_counts,
            const uint32_t *__restrict__ pattern_words)
 {
+    __shared__ uint32_t patch_all[kDescWarps][kPatchRows * kPatchWords];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int f = blockIdx.y;
+    uint32_t *patch = patch_all[warp];
     // lane i owns descriptor byte i = pattern points 16i .. 16i+15 = 32 signed bytes = 8 words
     uint32_t pw[8];
     {
@@ -137,42 +145,55 @@ k_describe(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, const
         const uint4 p1 = __ldg(reinterpret_cast<const uint4 *>(pattern_words) + lane * 2 + 1);
         pw[0] = p0.x; pw[1] = p0.y; pw[2] = p0.z; pw[3] = p0.w; pw[4] = p1.x; pw[5] = p1.y; pw[6] = p1.z; pw[7] = p1.w;
     }
-    const int *nk = nkept + f * g.nlevels;
-    int total = 0;
-#pragma unroll 1
-    for (int l = 0; l < g.nlevels; ++l) total += nk[l];
+    // per-level keypoint counts -> inclusive prefix in lanes 0..nlevels-1 (level-major concatenation, :1036-1063)
+    const int myc = lane < g.nlevels ? nkept[f * g.nlevels + lane] : 0;
+    int incl = myc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
     if (blockIdx.x == 0 && threadIdx.x == 0) out_counts[f] = total;
+    const uint32_t lvl_mask = g.nlevels >= 32 ? 0xffffffffu : ((1u << g.nlevels) - 1u);
 
     const int slot0 = (blockIdx.x * kDescWarps + warp) * kSlotsPerWarp;
 #pragma unroll 1
     for (int si = 0; si < kSlotsPerWarp; ++si) {
         const int slot = slot0 + si;                          // output row inside the frame
         if (slot >= total) return;
-        // level-major concatenation (:1036-1063): find the level this slot falls in
-        int level = 0, first = 0;
-#pragma unroll 1
-        for (int l = 0, acc = 0; l < g.nlevels; ++l) {
-            const int c = nk[l];
-            if (slot >= acc && slot < acc + c) { level = l; first = acc; }
-            acc += c;
-        }
+        const int level = __popc(__ballot_sync(0xffffffffu, slot >= incl) & lvl_mask);
+        const int first = __shfl_sync(0xffffffffu, incl - myc, level);
         const LevelGeom &L = g.lv[level];
         const uint32_t key = kept[(size_t)f * g.kept_total + L.kept_base + (slot - first)];
         const int x = cand_x(key) + kMinBorder, y = cand_y(key) + kMinBorder;   // :801-802
 
-        // ---- IC_Angle on the un-blurred level: lane = column u, all 31 row loads in flight ----
+        // ---- stage the blurred 37x37 patch (word aligned) ----
+        const int bp = L.blur_pitch;
+        const int xa = (x - kPatchR) & ~3;                    // first staged column (keypoints sit >= 19 px inside)
+        const uint8_t *bsrc = blur + L.blur_base + (size_t)f * L.blur_frame_stride + (size_t)(y - kPatchR) * bp + xa;
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < (kPatchRows * kPatchWords + 31) / 32; ++it) {
+            const int idx = it * 32 + lane;
+            if (idx < kPatchRows * kPatchWords) {
+                const int r = idx / kPatchWords, wx = idx - r * kPatchWords;
+                patch[idx] = __ldg(reinterpret_cast<const uint32_t *>(bsrc + (size_t)r * bp) + wx);
+            }
+        }
+
+        // ---- IC_Angle on the un-blurred level (:27-54): lane = column u, rows walked in +/- pairs ----
         const int pitch = L.pitch;
-        const uint8_t *img = pyr + L.base + (size_t)f * L.frame_stride + (size_t)(kPadY + y) * pitch + kPadX + x;
+        const uint8_t *ctr = pyr + L.base + (size_t)f * L.frame_stride + (size_t)(kPadY + y) * pitch + kPadX + x;
         int m10 = 0, m01 = 0;
         const int u = lane - kHalfPatch;
         const int au = u < 0 ? -u : u;
         if (lane < 2 * kHalfPatch + 1) {
-            int colsum = 0;
+            const uint8_t *pu = ctr + u, *pd = ctr + u;
+            int colsum = pu[0];
 #pragma unroll
-            for (int v = -kHalfPatch; v <= kHalfPatch; ++v) {
-                if (au <= g.umax[v < 0 ? -v : v]) {
-                    const int I = img[v * pitch + u];
-                    colsum += I; m01 += v * I;
+            for (int v = 1; v <= kHalfPatch; ++v) {
+                pu -= pitch; pd += pitch;
+                if (au <= g.umax[v]) {
+                    const int a_ = pd[0], b_ = pu[0];          // val_plus, val_minus
+                    colsum += a_ + b_; m01 += v * (a_ - b_);
                 }
             }
             m10 = u * colsum;
@@ -185,21 +206,21 @@ k_describe(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, const
         const float factorPI = (float)(3.14159265358979323846 / (double)180.f);
         const float ang = __fmul_rn(angle, factorPI);
         const float a = (float)cos((double)ang), b = (float)sin((double)ang);
-        const int bp = L.blur_pitch;
-        const uint8_t *center = blur + L.blur_base + (size_t)f * L.blur_frame_stride + (size_t)y * bp + x;
-        int t[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const uint32_t w = pw[k >> 1];
-            const float px = (float)(int)(signed char)(w >> ((k & 1) * 16));
-            const float py = (float)(int)(signed char)(w >> ((k & 1) * 16 + 8));
-            const int r = __float2int_rn(__fadd_rn(__fmul_rn(px, b), __fmul_rn(py, a)));
-            const int c = __float2int_rn(__fsub_rn(__fmul_rn(px, a), __fmul_rn(py, b)));
-            t[k] = center[r * bp + c];
-        }
+        __syncwarp();
+        const uint8_t *pc = reinterpret_cast<const uint8_t *>(patch) + kPatchR * (kPatchWords * 4) + (x - xa);   // patch centre
         int val = 0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) val |= (t[2 * k] < t[2 * k + 1]) << k;
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t w = pw[k];
+            const float x0 = (float)(int)(signed char)(w), y0 = (float)(int)(signed char)(w >> 8);
+            const float x1 = (float)(int)(signed char)(w >> 16), y1 = (float)(int)(signed char)(w >> 24);
+            const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
+            const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
+            const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
+            const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
+            const int t0 = pc[r0 * (kPatchWords * 4) + c0], t1 = pc[r1 * (kPatchWords * 4) + c1];
+            val |= (t0 < t1) << k;
+        }
         out_desc[((size_t)f * g.capacity + slot) * 32 + lane] = (uint8_t)val;
 
         if (lane == 0) {
