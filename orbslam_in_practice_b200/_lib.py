@@ -119,8 +119,8 @@ class Extractor:
          self.features_per_level, self.umax) = t
 
     def close(self):
-        if getattr(self, "h", None) and self.h.value:
-            load().orbx_destroy(self.h)
+        if getattr(self, "h", None) and self.h.value and _lib is not None:
+            _lib.orbx_destroy(self.h)
             self.h = C.c_void_p()
 
     __del__ = close
@@ -196,8 +196,8 @@ class Matcher:
         check(load().orbm_create(max_queries, max_db, device, C.byref(self.h)))
 
     def close(self):
-        if getattr(self, "h", None) and self.h.value:
-            load().orbm_destroy(self.h)
+        if getattr(self, "h", None) and self.h.value and _lib is not None:
+            _lib.orbm_destroy(self.h)
             self.h = C.c_void_p()
 
     __del__ = close

@@ -42,7 +42,9 @@ struct orbx_extractor {
     Geo full;                    // geometry of (max_w, max_h): sized every buffer
     DevBuffers buf;
     std::vector<void *> allocs;
-    cudaStream_t stream;
+    cudaStream_t stream, stream2, s_h2d, s_d2h;   // compute (two, alternating chunks) / upload / download
+    static const int kMaxChunks = 8;
+    cudaEvent_t ev_h2d[kMaxChunks], ev_done[kMaxChunks];
     int oct_smem;
     long long launches;
     // reference tables
@@ -245,11 +247,20 @@ extern "C" int orbx_create(const orbx_params *p, int max_width, int max_height, 
     ex->launches = 0; ex->last_frames = 0; ex->border_on = 1; ex->profiling = 0; ex->prof_calls = 0;
     for (auto &set : ex->ev) for (auto &e : set) e = nullptr;
     std::memset(&ex->buf, 0, sizeof(ex->buf));
+    ex->stream = ex->stream2 = ex->s_h2d = ex->s_d2h = nullptr;
+    for (int i = 0; i < orbx_extractor::kMaxChunks; ++i) { ex->ev_h2d[i] = nullptr; ex->ev_done[i] = nullptr; }
     build_reference_tables(ex);
     int rc = build_geometry(ex, max_width, max_height, ex->full, nullptr);
     if (rc) { delete ex; return rc; }
     ex->geo = ex->full;
-    if (cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ex; return cuda_fail(cudaGetLastError(), "stream"); }
+    if (cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ex->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ex->s_h2d, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ex->s_d2h, cudaStreamNonBlocking) != cudaSuccess) { delete ex; return cuda_fail(cudaGetLastError(), "stream"); }
+    for (int i = 0; i < orbx_extractor::kMaxChunks; ++i) {
+        cudaEventCreateWithFlags(&ex->ev_h2d[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ex->ev_done[i], cudaEventDisableTiming);
+    }
     const Geo &g = ex->full;
     const size_t F = (size_t)max_batch;
     DevBuffers &b = ex->buf;
@@ -285,6 +296,10 @@ extern "C" int orbx_destroy(orbx_extractor *ex)
     if (!ex) return ORBX_OK;
     cudaSetDevice(ex->device);
     if (ex->stream) { cudaStreamSynchronize(ex->stream); cudaStreamDestroy(ex->stream); }
+    if (ex->stream2) cudaStreamDestroy(ex->stream2);
+    if (ex->s_h2d) cudaStreamDestroy(ex->s_h2d);
+    if (ex->s_d2h) cudaStreamDestroy(ex->s_d2h);
+    for (int i = 0; i < orbx_extractor::kMaxChunks; ++i) { if (ex->ev_h2d[i]) cudaEventDestroy(ex->ev_h2d[i]); if (ex->ev_done[i]) cudaEventDestroy(ex->ev_done[i]); }
     for (void *p : ex->allocs) cudaFree(p);
     for (auto &set : ex->ev) for (auto &e : set) if (e) cudaEventDestroy(e);
     delete ex;
@@ -325,15 +340,22 @@ extern "C" int orbx_set_pyramid_border(orbx_extractor *ex, int enabled)
     return ORBX_OK;
 }
 
-static int run_pipeline(orbx_extractor *ex, const uint8_t *d_imgs, size_t pitch, size_t fstride, int w, int h, int nframes,
+static int ensure_geometry(orbx_extractor *ex, int w, int h)
+{
+    if (w == ex->cur_w && h == ex->cur_h) return ORBX_OK;
+    CK(cudaStreamSynchronize(ex->stream));
+    return upload_geometry(ex, w, h);
+}
+
+// frames [frame0, frame0 + nframes) of the batch; all buffers (inputs, scratch, outputs) are indexed
+// by the absolute frame number, so chunks of one batch can be in flight on different streams
+static int run_pipeline(orbx_extractor *ex, const uint8_t *d_imgs, size_t pitch, size_t fstride, int w, int h, int frame0, int nframes,
                         orbx_keypoint *d_kps, uint8_t *d_desc, int *d_counts, cudaStream_t s)
 {
-    if (w != ex->cur_w || h != ex->cur_h) {
-        CK(cudaStreamSynchronize(ex->stream));
-        int rc = upload_geometry(ex, w, h);
-        if (rc) return rc;
-    }
-    const Geo &g = ex->geo;
+    int rc = ensure_geometry(ex, w, h);
+    if (rc) return rc;
+    Geo g = ex->geo;
+    g.frame0 = frame0;
     const bool prof = ex->profiling != 0;
     cudaEvent_t *evs = ex->ev[ex->prof_calls % orbx_extractor::kProfCalls];
 #define STAGE_EVENT(i) do { if (prof) cudaEventRecord(evs[i], s); } while (0)
@@ -353,7 +375,7 @@ static int run_pipeline(orbx_extractor *ex, const uint8_t *d_imgs, size_t pitch,
 #undef STAGE_EVENT
     if (prof) ex->prof_calls++;
     ex->launches += 1 + (g.nlevels - 1) + (g.total_cells > 0) + 1 + g.nlevels + 1;
-    ex->last_frames = nframes;
+    ex->last_frames = frame0 + nframes;
     CK(cudaGetLastError());
     return ORBX_OK;
 }
@@ -372,7 +394,7 @@ extern "C" int orbx_extract_device(orbx_extractor *ex, const uint8_t *d_imgs, si
     }
     if (width > ex->max_w || height > ex->max_h || nframes > ex->max_batch) return ORBX_E_CAPACITY;
     if (row_pitch < (size_t)width) return ORBX_E_INVALID;
-    return run_pipeline(ex, d_imgs, row_pitch, frame_stride, width, height, nframes, d_kps, d_desc, d_counts, s);
+    return run_pipeline(ex, d_imgs, row_pitch, frame_stride, width, height, 0, nframes, d_kps, d_desc, d_counts, s);
 }
 
 extern "C" int orbx_extract_host(orbx_extractor *ex, const uint8_t *imgs, size_t row_pitch, size_t frame_stride,
@@ -386,25 +408,47 @@ extern "C" int orbx_extract_host(orbx_extractor *ex, const uint8_t *imgs, size_t
     if (width > ex->max_w || height > ex->max_h || nframes > ex->max_batch) return ORBX_E_CAPACITY;
     if (row_pitch < (size_t)width) return ORBX_E_INVALID;
     CK(cudaSetDevice(ex->device));
-    cudaStream_t s = ex->stream;
     const size_t cap = (size_t)ex->full.capacity;
-    // one 2-D copy for the whole batch when frames are evenly strided, straight from the caller's
-    // buffer (pinned or pageable); tight rows on the device side
-    if (frame_stride == row_pitch * (size_t)height || nframes == 1) {
-        CK(cudaMemcpy2DAsync(ex->buf.staging, (size_t)width, imgs, row_pitch, (size_t)width, (size_t)height * nframes,
-                             cudaMemcpyHostToDevice, s));
-    } else {
-        for (int f = 0; f < nframes; ++f)
-            CK(cudaMemcpy2DAsync(ex->buf.staging + (size_t)f * width * height, (size_t)width, imgs + (size_t)f * frame_stride, row_pitch,
-                                 (size_t)width, (size_t)height, cudaMemcpyHostToDevice, s));
-    }
-    int rc = run_pipeline(ex, ex->buf.staging, (size_t)width, (size_t)width * height, width, height, nframes,
-                          ex->buf.out_kps, ex->buf.out_desc, ex->buf.out_counts, s);
+    int rc = ensure_geometry(ex, width, height);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(kps, ex->buf.out_kps, (size_t)nframes * cap * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(desc, ex->buf.out_desc, (size_t)nframes * cap * 32, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(counts, ex->buf.out_counts, (size_t)nframes * sizeof(int), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
+    // Chunked three-stream pipeline: the H2D copy of chunk c+1 and the D2H copy of chunk c-1 overlap
+    // the kernels of chunk c (PCIe is full duplex; frames are independent).
+    int nchunks = nframes >= 64 ? 4 : (nframes >= 8 ? 2 : 1);
+    if (const char *e = std::getenv("ORBX_HOST_CHUNKS")) { const int v = std::atoi(e); if (v >= 1 && v <= orbx_extractor::kMaxChunks && v <= nframes) nchunks = v; }
+    const size_t fbytes = (size_t)width * height;
+    for (int c = 0; c < nchunks; ++c) {
+        const int f0 = (int)((long long)nframes * c / nchunks), f1 = (int)((long long)nframes * (c + 1) / nchunks);
+        const int n = f1 - f0;
+        if (n <= 0) continue;
+        if (row_pitch == (size_t)width && (frame_stride == fbytes || n == 1)) {
+            // fully contiguous frames: one linear copy (a 2-D copy of 640-byte rows is slower on the DMA engine)
+            CK(cudaMemcpyAsync(ex->buf.staging + f0 * fbytes, imgs + (size_t)f0 * frame_stride, (size_t)n * fbytes,
+                               cudaMemcpyHostToDevice, ex->s_h2d));
+        } else if (frame_stride == row_pitch * (size_t)height || n == 1) {
+            CK(cudaMemcpy2DAsync(ex->buf.staging + f0 * fbytes, (size_t)width, imgs + (size_t)f0 * frame_stride, row_pitch,
+                                 (size_t)width, (size_t)height * n, cudaMemcpyHostToDevice, ex->s_h2d));
+        } else {
+            for (int f = f0; f < f1; ++f)
+                CK(cudaMemcpy2DAsync(ex->buf.staging + f * fbytes, (size_t)width, imgs + (size_t)f * frame_stride, row_pitch,
+                                     (size_t)width, (size_t)height, cudaMemcpyHostToDevice, ex->s_h2d));
+        }
+        CK(cudaEventRecord(ex->ev_h2d[c], ex->s_h2d));
+        // chunks alternate between two compute streams so one chunk's kernels fill the launch gaps
+        // and tail waves of the other (per-frame buffers are disjoint)
+        cudaStream_t cs = (c & 1) ? ex->stream2 : ex->stream;
+        CK(cudaStreamWaitEvent(cs, ex->ev_h2d[c], 0));
+        rc = run_pipeline(ex, ex->buf.staging, (size_t)width, fbytes, width, height, f0, n,
+                          ex->buf.out_kps, ex->buf.out_desc, ex->buf.out_counts, cs);
+        if (rc) return rc;
+        CK(cudaEventRecord(ex->ev_done[c], cs));
+        CK(cudaStreamWaitEvent(ex->s_d2h, ex->ev_done[c], 0));
+        CK(cudaMemcpyAsync(kps + f0 * cap, ex->buf.out_kps + f0 * cap, (size_t)n * cap * sizeof(orbx_keypoint), cudaMemcpyDeviceToHost, ex->s_d2h));
+        CK(cudaMemcpyAsync(desc + f0 * cap * 32, ex->buf.out_desc + f0 * cap * 32, (size_t)n * cap * 32, cudaMemcpyDeviceToHost, ex->s_d2h));
+        CK(cudaMemcpyAsync(counts + f0, ex->buf.out_counts + f0, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ex->s_d2h));
+    }
+    CK(cudaStreamSynchronize(ex->s_d2h));
+    CK(cudaStreamSynchronize(ex->stream));
+    CK(cudaStreamSynchronize(ex->stream2));
     return ORBX_OK;
 }
 

@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(32 * kBlurWarps)
 k_blur(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, uint8_t *__restrict__ blur, int level)
 {
     const LevelGeom &L = g.lv[level];
-    const int lane = threadIdx.x, f = blockIdx.z;
+    const int lane = threadIdx.x, f = blockIdx.z + g.frame0;
     const int y0 = (blockIdx.y * kBlurWarps + threadIdx.y) * kBlurRows;
     if (y0 >= L.h) return;
     const int y1 = min(y0 + kBlurRows, L.h);
@@ -136,7 +136,7 @@ k_describe(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, const
 {
     __shared__ uint32_t patch_all[kDescWarps][kPatchRows * kPatchWords];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int f = blockIdx.y;
+    const int f = blockIdx.y + g.frame0;
     uint32_t *patch = patch_all[warp];
     // lane i owns descriptor byte i = pattern points 16i .. 16i+15 = 32 signed bytes = 8 words
     uint32_t pw[8];

@@ -56,7 +56,7 @@ k_fast_cells(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr,
 {
     extern __shared__ __align__(16) unsigned char fast_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int cell = blockIdx.x * kFastWarps + warp, f = blockIdx.y;
+    const int cell = blockIdx.x * kFastWarps + warp, f = blockIdx.y + g.frame0;
     if (cell >= g.total_cells) return;
     unsigned char *mine = fast_smem + warp * sm.per_warp;
     uint8_t *tile = mine;                                                     // [tile_rows][tp]

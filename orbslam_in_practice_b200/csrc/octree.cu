@@ -98,7 +98,7 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ OctShared S;
 
-    const int level = blockIdx.x, f = blockIdx.y, tid = threadIdx.x;
+    const int level = blockIdx.x, f = blockIdx.y + g.frame0, tid = threadIdx.x;
     const LevelGeom &L = g.lv[level];
     const int NC = L.node_cap;
     // dynamic shared memory carve-up (sized by the largest level's node_cap)

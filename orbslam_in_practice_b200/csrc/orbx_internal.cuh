@@ -50,6 +50,7 @@ struct LevelGeom {
 
 struct Geo {
     int nlevels, ini_th, min_th, border_on;
+    int frame0;               // first frame handled by this launch (chunked host pipeline)
     int total_cells;          // cells per frame, all levels
     int capacity;             // output keypoint slots per frame
     int kept_total;           // kept slots per frame (= capacity)

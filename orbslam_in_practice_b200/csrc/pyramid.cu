@@ -33,7 +33,7 @@ k_level0(const __grid_constant__ Geo g, uint8_t *__restrict__ pyr, const uint8_t
     const LevelGeom &L = g.lv[0];
     const int B = g.border_on ? kBorder : kMinBlurBorder;
     const int Y = (int)(blockIdx.y * 4 + threadIdx.y) - B;   // bordered row
-    const int f = blockIdx.z;
+    const int f = blockIdx.z + g.frame0;
     const int chunk = blockIdx.x * 32 + threadIdx.x;
     const int X0 = chunk * 16 - kPadX;                       // first pixel of this chunk
     if (chunk * 16 >= L.pitch || X0 + 15 < -B || X0 >= L.w + B || Y >= L.h + B) return;
@@ -74,7 +74,7 @@ k_resize(const __grid_constant__ Geo g, uint8_t *__restrict__ pyr, const int2 *_
     const LevelGeom &D = g.lv[level];
     const LevelGeom &S = g.lv[level - 1];
     const int B = g.border_on ? kBorder : kMinBlurBorder;
-    const int f = blockIdx.z;
+    const int f = blockIdx.z + g.frame0;
     const int chunk = blockIdx.x * 128 + threadIdx.x;
     const int X0 = chunk * 4 - kPadX;
     if (chunk * 4 >= D.pitch || X0 + 3 < -B || X0 >= D.w + B) return;
