@@ -343,21 +343,17 @@ def run_match(args, _lib, torch, dist, dev, world, rank, local, stream, K, barri
     """Hamming best-2 kNN, database sharded over the ranks."""
     from orbslam_in_practice_b200.synth import synth_descriptor_db, synth_queries
     db = synth_descriptor_db(KNN_NDB); q = synth_queries(db, KNN_NQ)
-    lo, hi = KNN_NDB * rank // world, KNN_NDB * (rank + 1) // world
+    from orbslam_in_practice_b200 import sharding
+    lo, hi = sharding.db_shard(KNN_NDB, rank, world)
     m = _lib.Matcher(KNN_NQ, hi - lo, local)
     t_q = torch.from_numpy(q).to(dev); t_db = torch.from_numpy(db[lo:hi]).to(dev)
     tri = torch.empty((3, KNN_NQ), dtype=torch.int32, device=dev)
-    gathered = torch.empty((world, 3, KNN_NQ), dtype=torch.int32, device=dev)
     out = torch.empty((4, KNN_NQ), dtype=torch.int32, device=dev)
 
     def knn_step():
         m.knn2_device(t_q.data_ptr(), KNN_NQ, t_db.data_ptr(), hi - lo, lo, tri[0].data_ptr(), tri[1].data_ptr(),
                       tri[2].data_ptr(), stream)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, tri)
-            src, stride = gathered, 3 * KNN_NQ
-        else:
-            src, stride = tri.view(1, 3, KNN_NQ), 3 * KNN_NQ
+        src, stride = sharding.gather_triples(tri, world), 3 * KNN_NQ     # NCCL all-gather over NVLink when world > 1
         m.merge_shards_device(src[0, 0].data_ptr(), src[0, 1].data_ptr(), src[0, 2].data_ptr(), world, KNN_NQ,
                               out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), stream, shard_stride=stride)
         m.ratio_select_device(out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), KNN_NQ, 50, 0.7,
