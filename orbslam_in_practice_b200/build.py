@@ -29,5 +29,22 @@ def build(force=False, verbose=False):
     return SO
 
 
+CPP_DIR = os.path.join(HERE, "cpp")
+FRONTEND_SO = os.path.join(HERE, "liborbslam_frontend.so")
+
+
+def build_cpp(force=False):
+    """Host-side C++ mirror of the reference classes (ORBSlam::ORBextractor / ORBmatcher) over the C ABI."""
+    srcs = [os.path.join(CPP_DIR, f) for f in ("ORBextractor.cc", "ORBmatcher.cc")]
+    deps = srcs + [os.path.join(CPP_DIR, f) for f in ("ORBextractor.h", "ORBmatcher.h", "cv_compat.h")] + [SO]
+    if not force and os.path.exists(FRONTEND_SO) and all(os.path.getmtime(FRONTEND_SO) >= os.path.getmtime(d) for d in deps):
+        return FRONTEND_SO
+    cmd = ["g++", "-std=c++14", "-O2", "-fPIC", "-shared", "-Wall", "-I", CPP_DIR, "-o", FRONTEND_SO] + srcs + \
+          ["-L", HERE, "-lorbx", "-Wl,-rpath,$ORIGIN"]
+    subprocess.check_call(cmd, cwd=HERE)
+    return FRONTEND_SO
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_cpp(force="--force" in sys.argv))

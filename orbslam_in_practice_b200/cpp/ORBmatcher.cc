@@ -1,0 +1,73 @@
+// ORBmatcher.cc -- host-side mirror of the reference matcher core over the C ABI (see ORBmatcher.h).
+#include "ORBmatcher.h"
+
+#include <climits>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#include "../../include/orbx.h"
+
+namespace ORBSlam {
+
+const int ORBmatcher::TH_LOW = 50;          // src/ORBmatcher.cpp:7
+const int ORBmatcher::HISTO_LENGTH = 30;    // src/ORBmatcher.cpp:6
+
+static void check(int rc, const char *what)
+{
+    if (rc != ORBX_OK) throw std::runtime_error(std::string("ORBmatcher: ") + what + ": " + orbx_strerror(rc));
+}
+
+ORBmatcher::ORBmatcher(float nnratio, bool checkOri)
+    : mfNNratio(nnratio), mbCheckOrientation(checkOri), mHandle(nullptr), mMaxQ(0), mMaxDb(0) {}
+
+ORBmatcher::~ORBmatcher() { if (mHandle) orbm_destroy(mHandle); }
+
+void ORBmatcher::Ensure(int nq, int ndb)
+{
+    if (mHandle && nq <= mMaxQ && ndb <= mMaxDb) return;
+    if (mHandle) { orbm_destroy(mHandle); mHandle = nullptr; }
+    mMaxQ = nq > mMaxQ ? nq : mMaxQ; mMaxDb = ndb > mMaxDb ? ndb : mMaxDb;
+    if (mMaxQ < 1) mMaxQ = 1;
+    check(orbm_create(mMaxQ, mMaxDb, 0, &mHandle), "create");
+}
+
+static std::vector<unsigned char> pack_rows(const cv::Mat &m)
+{
+    std::vector<unsigned char> v((size_t)m.rows * 32);
+    for (int r = 0; r < m.rows; ++r) std::memcpy(&v[(size_t)r * 32], m.ptr(r), 32);
+    return v;
+}
+
+int ORBmatcher::DescriptorDistance(const cv::Mat &a, const cv::Mat &b)
+{
+    Ensure(1, 1);
+    int dist = 0;
+    check(orbm_hamming_pairs_host(mHandle, a.ptr(0), b.ptr(0), 1, &dist), "hamming");
+    return dist;
+}
+
+void ORBmatcher::BestTwo(const cv::Mat &queries, const cv::Mat &database, std::vector<int> &bestDist, std::vector<int> &bestIdx,
+                         std::vector<int> &bestDist2)
+{
+    const int nq = queries.rows, ndb = database.rows;
+    bestDist.assign((size_t)nq, INT_MAX); bestIdx.assign((size_t)nq, -1); bestDist2.assign((size_t)nq, INT_MAX);
+    if (nq == 0) return;
+    if (queries.cols != 32 || (ndb && database.cols != 32)) throw std::runtime_error("ORBmatcher: descriptors must be N x 32 bytes");
+    Ensure(nq, ndb);
+    const std::vector<unsigned char> q = pack_rows(queries), d = pack_rows(database);
+    check(orbm_knn2_host(mHandle, q.data(), nq, d.data(), ndb, 0, bestDist.data(), bestIdx.data(), bestDist2.data()), "knn2");
+}
+
+int ORBmatcher::SearchBruteForce(const cv::Mat &queries, const cv::Mat &database, std::vector<int> &vnMatches12)
+{
+    std::vector<int> d1, i1, d2;
+    BestTwo(queries, database, d1, i1, d2);
+    vnMatches12.assign(d1.size(), -1);
+    int nmatches = 0;
+    for (size_t i = 0; i < d1.size(); ++i)                           // src/ORBmatcher.cpp:65-67
+        if (i1[i] >= 0 && d1[i] <= TH_LOW && d1[i] < (float)d2[i] * mfNNratio) { vnMatches12[i] = i1[i]; ++nmatches; }
+    return nmatches;
+}
+
+} // namespace ORBSlam

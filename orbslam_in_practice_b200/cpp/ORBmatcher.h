@@ -1,0 +1,48 @@
+// ORBmatcher.h -- ORBSlam::ORBmatcher's distance and candidate-search core on the GPU.
+//
+// Mirrors include/ORBmatcher.h:8-32 for the hot path: ctor(nnratio, checkOri), the non-static
+// DescriptorDistance(a, b) (src/ORBmatcher.cpp:128-144), and the brute-force best-2 candidate scan with
+// TH_LOW / ratio acceptance (src/ORBmatcher.cpp:37-67) that SearchForInitialization, SearchByProjection
+// and SearchByBoW are built on.  The Frame/KeyFrame-typed entry points stay in the caller's code base
+// (SearchByBoW / SearchByProjection have empty bodies in the reference, ORBmatcher.h:22,24).
+#pragma once
+
+#include <vector>
+
+#include "cv_compat.h"
+
+struct orbm_matcher;
+
+namespace ORBSlam {
+
+class ORBmatcher {
+public:
+    ORBmatcher(float nnratio = 0.6, bool checkOri = true);
+    ~ORBmatcher();
+    ORBmatcher(const ORBmatcher &) = delete;
+    ORBmatcher &operator=(const ORBmatcher &) = delete;
+
+    // Hamming distance of two 32-byte descriptor rows (one pair per call: kept for API fidelity, slow by nature)
+    int DescriptorDistance(const cv::Mat &a, const cv::Mat &b);
+
+    // best-2 scan of every query row against every database row, in ascending database order with strict '<'
+    // (first minimal index wins).  Outputs have one entry per query; empty database -> (INT_MAX, -1, INT_MAX).
+    void BestTwo(const cv::Mat &queries, const cv::Mat &database, std::vector<int> &bestDist, std::vector<int> &bestIdx,
+                 std::vector<int> &bestDist2);
+
+    // BestTwo + acceptance: bestDist <= TH_LOW && bestDist < (float)bestDist2 * mfNNratio; returns #matches,
+    // vnMatches12[i] = database row or -1
+    int SearchBruteForce(const cv::Mat &queries, const cv::Mat &database, std::vector<int> &vnMatches12);
+
+    static const int TH_LOW;
+    static const int HISTO_LENGTH;
+
+private:
+    void Ensure(int nq, int ndb);
+    float mfNNratio;
+    bool mbCheckOrientation;
+    orbm_matcher *mHandle;
+    int mMaxQ, mMaxDb;
+};
+
+} // namespace ORBSlam
