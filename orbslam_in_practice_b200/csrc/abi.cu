@@ -45,6 +45,9 @@ struct orbx_extractor {
     cudaStream_t stream, stream2, s_h2d, s_d2h;   // compute (two, alternating chunks) / upload / download
     static const int kMaxChunks = 8;
     cudaEvent_t ev_h2d[kMaxChunks], ev_done[kMaxChunks];
+    cudaStream_t s_aux[2];                        // blur runs here, concurrent with FAST + octree
+    cudaEvent_t ev_fork[kMaxChunks], ev_join[kMaxChunks];
+    unsigned fork_slot;
     int oct_smem;
     long long launches;
     // reference tables
@@ -247,19 +250,23 @@ extern "C" int orbx_create(const orbx_params *p, int max_width, int max_height, 
     ex->launches = 0; ex->last_frames = 0; ex->border_on = 1; ex->profiling = 0; ex->prof_calls = 0;
     for (auto &set : ex->ev) for (auto &e : set) e = nullptr;
     std::memset(&ex->buf, 0, sizeof(ex->buf));
-    ex->stream = ex->stream2 = ex->s_h2d = ex->s_d2h = nullptr;
-    for (int i = 0; i < orbx_extractor::kMaxChunks; ++i) { ex->ev_h2d[i] = nullptr; ex->ev_done[i] = nullptr; }
+    ex->stream = ex->stream2 = ex->s_h2d = ex->s_d2h = nullptr; ex->s_aux[0] = ex->s_aux[1] = nullptr; ex->fork_slot = 0;
+    for (int i = 0; i < orbx_extractor::kMaxChunks; ++i) { ex->ev_h2d[i] = nullptr; ex->ev_done[i] = nullptr; ex->ev_fork[i] = nullptr; ex->ev_join[i] = nullptr; }
     build_reference_tables(ex);
     int rc = build_geometry(ex, max_width, max_height, ex->full, nullptr);
     if (rc) { delete ex; return rc; }
     ex->geo = ex->full;
     if (cudaStreamCreateWithFlags(&ex->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ex->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ex->s_aux[0], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ex->s_aux[1], cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ex->s_h2d, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ex->s_d2h, cudaStreamNonBlocking) != cudaSuccess) { delete ex; return cuda_fail(cudaGetLastError(), "stream"); }
     for (int i = 0; i < orbx_extractor::kMaxChunks; ++i) {
         cudaEventCreateWithFlags(&ex->ev_h2d[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ex->ev_done[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ex->ev_fork[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ex->ev_join[i], cudaEventDisableTiming);
     }
     const Geo &g = ex->full;
     const size_t F = (size_t)max_batch;
@@ -297,9 +304,11 @@ extern "C" int orbx_destroy(orbx_extractor *ex)
     cudaSetDevice(ex->device);
     if (ex->stream) { cudaStreamSynchronize(ex->stream); cudaStreamDestroy(ex->stream); }
     if (ex->stream2) cudaStreamDestroy(ex->stream2);
+    for (auto &a : ex->s_aux) if (a) { cudaStreamSynchronize(a); cudaStreamDestroy(a); }
     if (ex->s_h2d) cudaStreamDestroy(ex->s_h2d);
     if (ex->s_d2h) cudaStreamDestroy(ex->s_d2h);
-    for (int i = 0; i < orbx_extractor::kMaxChunks; ++i) { if (ex->ev_h2d[i]) cudaEventDestroy(ex->ev_h2d[i]); if (ex->ev_done[i]) cudaEventDestroy(ex->ev_done[i]); }
+    for (int i = 0; i < orbx_extractor::kMaxChunks; ++i) { if (ex->ev_h2d[i]) cudaEventDestroy(ex->ev_h2d[i]); if (ex->ev_done[i]) cudaEventDestroy(ex->ev_done[i]);
+        if (ex->ev_fork[i]) cudaEventDestroy(ex->ev_fork[i]); if (ex->ev_join[i]) cudaEventDestroy(ex->ev_join[i]); }
     for (void *p : ex->allocs) cudaFree(p);
     for (auto &set : ex->ev) for (auto &e : set) if (e) cudaEventDestroy(e);
     delete ex;
@@ -364,12 +373,27 @@ static int run_pipeline(orbx_extractor *ex, const uint8_t *d_imgs, size_t pitch,
     STAGE_EVENT(1);
     for (int l = 1; l < g.nlevels; ++l) launch_resize(g, ex->buf, l, nframes, s);
     STAGE_EVENT(2);
-    if (g.total_cells > 0) launch_fast(g, ex->buf, nframes, s);
-    STAGE_EVENT(3);
-    launch_octree(g, ex->buf, nframes, ex->oct_smem, s);
-    STAGE_EVENT(4);
-    launch_blur(g, ex->buf, nframes, s);
-    STAGE_EVENT(5);
+    if (prof) {
+        // profiling: strictly serial so that every stage's event interval is that stage alone
+        if (g.total_cells > 0) launch_fast(g, ex->buf, nframes, s);
+        STAGE_EVENT(3);
+        launch_octree(g, ex->buf, nframes, ex->oct_smem, s);
+        STAGE_EVENT(4);
+        launch_blur(g, ex->buf, nframes, s);
+        STAGE_EVENT(5);
+    } else {
+        // the blur needs only the pyramid: fork it to an auxiliary stream so it fills the SMs the
+        // latency-bound octree blocks and the kernel tails leave idle; join before describe
+        const int slot = ex->fork_slot++ % orbx_extractor::kMaxChunks;
+        cudaStream_t aux = ex->s_aux[slot & 1];
+        CK(cudaEventRecord(ex->ev_fork[slot], s));
+        CK(cudaStreamWaitEvent(aux, ex->ev_fork[slot], 0));
+        launch_blur(g, ex->buf, nframes, aux);
+        CK(cudaEventRecord(ex->ev_join[slot], aux));
+        if (g.total_cells > 0) launch_fast(g, ex->buf, nframes, s);
+        launch_octree(g, ex->buf, nframes, ex->oct_smem, s);
+        CK(cudaStreamWaitEvent(s, ex->ev_join[slot], 0));
+    }
     launch_describe(g, ex->buf, nframes, d_kps, d_desc, d_counts, s);
     STAGE_EVENT(6);
 #undef STAGE_EVENT

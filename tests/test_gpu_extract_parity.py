@@ -113,3 +113,30 @@ def test_capacity_errors(orbx):
         ex.extract_host(np.zeros((480, 640), np.uint8))
     with pytest.raises(orbx.OrbxError):
         ex.extract_host(np.zeros((2, 240, 320), np.uint8))
+
+
+def test_4k_frame_nfeatures_8000(orbx, oracle):
+    """BASELINE configs[4] frame size: 3840x2160, nfeatures=8000 (one frame here; the oracle needs ~1 s for it)."""
+    img = synth_frame(0, 3840, 2160)
+    ex = orbx.Extractor(nfeatures=8000, max_width=3840, max_height=2160, max_batch=2)
+    oex = oracle.OracleExtractor(nfeatures=8000)
+    imgs = np.stack([img, img[::-1].copy()])
+    kps, desc, counts = ex.extract_host(imgs)
+    n = _compare_frame(oracle, ex, oex, imgs[0], 0, kps, desc, counts)
+    assert n >= 7900
+    _compare_frame(oracle, ex, oex, imgs[1], 1, kps, desc, counts, check_stages=False)
+
+
+def test_stereo_left_right_matching(orbx, oracle):
+    """BASELINE configs[2]: KITTI-sized pair, 2000 features per side, left->right brute-force best-2 + ratio 0.7."""
+    imgs = synth_batch([0, 1], 1241, 376)
+    imgs[1] = np.roll(imgs[0], 7, axis=1)                      # a shifted copy so that matches exist
+    ex = orbx.Extractor(nfeatures=2000, max_width=1241, max_height=376, max_batch=2)
+    kps, desc, counts = ex.extract_host(imgs)
+    nl, nr = int(counts[0]), int(counts[1])
+    m = orbx.Matcher(nl, nr)
+    d1, i1, d2 = m.knn2_host(desc[0, :nl], desc[1, :nr])
+    o1, oi, o2 = oracle.knn2(desc[0, :nl], desc[1, :nr], 0, 4)
+    assert np.array_equal(d1, o1) and np.array_equal(i1, oi) and np.array_equal(d2, o2)
+    match = oracle.ratio_select(d1, i1, d2, 50, 0.7)
+    assert (match >= 0).sum() > nl // 4
