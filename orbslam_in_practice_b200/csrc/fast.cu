@@ -42,14 +42,6 @@ __device__ __forceinline__ int arc9_maxmin(const int (&e)[16])
     return max3(max3(b0, b1, b2), max3(b3, b4, m9[15]), -512);
 }
 
-// warp-local push: lanes with pred append value; count is a warp-uniform register
-__device__ __forceinline__ void warp_push(bool pred, uint16_t value, uint16_t *queue, int &count)
-{
-    const uint32_t bal = __ballot_sync(0xffffffffu, pred);
-    if (pred) queue[count + __popc(bal & ((1u << (threadIdx.x & 31)) - 1u))] = value;
-    count += __popc(bal);
-}
-
 __global__ void __launch_bounds__(kFastThreads)
 k_fast_cells(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr,
              int *__restrict__ cell_count, uint32_t *__restrict__ cell_slots, const FastSmem sm)
@@ -62,7 +54,6 @@ k_fast_cells(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr,
     uint8_t *tile = mine;                                                     // [tile_rows][tp]
     uint8_t *score = mine + sm.off_score;                                     // [tile_rows - 4][sp]
     uint16_t *queue = reinterpret_cast<uint16_t *>(mine + sm.off_queue);      // phase A survivors
-    uint16_t *corners = reinterpret_cast<uint16_t *>(mine + sm.off_corner);   // phase B corners
     uint32_t *bm_ini = reinterpret_cast<uint32_t *>(mine + sm.off_bm);
     uint32_t *bm_min = bm_ini + (sm.npix_max + 31) / 32;
     const int kTP = sm.tp, kSP = sm.sp;
@@ -111,33 +102,49 @@ k_fast_cells(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr,
     const int minTh = g.min_th, iniTh = g.ini_th;
     const int lowTh = min(minTh, iniTh);
 
-    // ---- phase A: compass pre-test, lane = column ----
+    // ---- phase A: compass pre-test, lane = column.  Each lane collects its column's verdicts for
+    //      up to 32 rows in two bitmasks (3 instructions per row and polarity instead of a ballot +
+    //      popc + store per row), then the warp compacts them into the queue with one scan. ----
     int nq = 0;
     for (int x0 = 0; x0 < iw; x0 += 32) {
         const int x = x0 + lane;
         const bool inx = x < iw;
-        const uint8_t *p = tile + 3 * kTP + 3 + xoff + (inx ? x : 0);
-#pragma unroll 2
-        for (int y = 0; y < ih; ++y, p += kTP) {
-            const int v = p[0];
-            const int n = p[3 * kTP], s = p[-3 * kTP], e = p[3], w = p[-3];
-            const int hiv = min(max(n, s), max(e, w)) - v;          // > t: a bright arc is possible
-            const int lov = v - max(min(n, s), min(e, w));          // > t: a dark arc is possible
-            const bool bright = inx && hiv > lowTh, dark = inx && lov > lowTh;
-            // queue entry: x | y << 6 | bright << 12 | dark << 13   (x, y < 64)
-            warp_push(bright | dark, (uint16_t)(x | (y << 6) | (bright ? 0x1000 : 0) | (dark ? 0x2000 : 0)), queue, nq);
+        for (int yb = 0; yb < ih; yb += 32) {
+            const int rows = min(32, ih - yb);
+            const uint8_t *p = tile + (yb + 3) * kTP + 3 + xoff + (inx ? x : 0);
+            uint32_t mb = 0, md = 0, bit = 1;
+#pragma unroll 4
+            for (int y = 0; y < rows; ++y, p += kTP, bit <<= 1) {
+                const int v = p[0];
+                const int n = p[3 * kTP], s = p[-3 * kTP], e = p[3], w = p[-3];
+                const int hiv = min(max(n, s), max(e, w)) - v;          // > t: a bright arc is possible
+                const int lov = v - max(min(n, s), min(e, w));          // > t: a dark arc is possible
+                mb |= hiv > lowTh ? bit : 0u;
+                md |= lov > lowTh ? bit : 0u;
+            }
+            if (!inx) { mb = 0; md = 0; }
+            uint32_t any = mb | md;
+            const int cnt = __popc(any);
+            int inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            int pos = nq + inc - cnt;
+            while (any) {
+                const int y = __ffs(any) - 1;
+                any &= any - 1;
+                // queue entry: x | y << 6 | bright << 12 | dark << 13   (x, y < 64)
+                queue[pos++] = (uint16_t)(x | ((yb + y) << 6) | (((mb >> y) & 1u) << 12) | (((md >> y) & 1u) << 13));
+            }
+            nq += __shfl_sync(0xffffffffu, inc, 31);
         }
     }
     __syncwarp();
 
     // ---- phase B: exact score of the candidate polarity ----
-    int nc = 0;
     for (int i0 = 0; i0 < nq; i0 += 32) {
         const int i = i0 + lane;
-        bool corner = false;
-        uint32_t ent = 0;
         if (i < nq) {
-            ent = queue[i];
+            const uint32_t ent = queue[i];
             const int x = ent & 63, y = (ent >> 6) & 63;
             const uint8_t *p = tile + (y + 3) * kTP + (x + 3 + xoff);
             const int v = p[0];
@@ -156,21 +163,19 @@ k_fast_cells(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr,
                 e[12] = sgn * p[-3] + off;          e[13] = sgn * p[kTP - 3] + off;     e[14] = sgn * p[2 * kTP - 2] + off;  e[15] = sgn * p[3 * kTP - 1] + off;
                 best = max(best, arc9_maxmin(e));
             }
-            if (best > lowTh) {                       // corner at lowTh; cornerScore = best - 1 >= lowTh
-                corner = true;
+            if (best > lowTh)                         // corner at lowTh; cornerScore = best - 1 >= lowTh
                 score[(y + 1) * kSP + (x + 1)] = (uint8_t)(best - 1);
-            }
         }
-        warp_push(corner, (uint16_t)(ent & 0xfff), corners, nc);
     }
     __syncwarp();
 
-    // ---- phase C: NMS at both thresholds, corners only ----
-    for (int i = lane; i < nc; i += 32) {
-        const uint32_t ent = corners[i];
-        const int x = ent & 63, y = ent >> 6;
+    // ---- phase C: NMS at both thresholds; walks the same queue (non-corners have score 0) ----
+    for (int i = lane; i < nq; i += 32) {
+        const uint32_t ent = queue[i];
+        const int x = ent & 63, y = (ent >> 6) & 63;
         const uint8_t *q = score + (y + 1) * kSP + (x + 1);
         const int s = q[0];
+        if (s < lowTh) continue;
         int nmax_min = 0, nmax_ini = 0;
 #pragma unroll
         for (int dy = -1; dy <= 1; ++dy)
@@ -225,8 +230,8 @@ void launch_fast(const Geo &g, const DevBuffers &b, int nframes, cudaStream_t s)
     sm.npix_max = (mw * mh + 1) / 2 * 2;
     sm.off_score = up16(sm.tile_rows * sm.tp);
     sm.off_queue = sm.off_score + up16((mh + 2) * sm.sp);
-    sm.off_corner = sm.off_queue + up16(sm.npix_max * 2);
-    sm.off_bm = sm.off_corner + up16(sm.npix_max * 2);
+    sm.off_corner = 0;
+    sm.off_bm = sm.off_queue + up16(sm.npix_max * 2);
     sm.per_warp = sm.off_bm + up16(2 * ((sm.npix_max + 31) / 32) * 4);
     const size_t bytes = (size_t)sm.per_warp * kFastWarps;
     static size_t configured = 0;

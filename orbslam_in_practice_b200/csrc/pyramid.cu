@@ -69,7 +69,8 @@ k_level0(const __grid_constant__ Geo g, uint8_t *__restrict__ pyr, const uint8_t
 constexpr int kResizeRows = 8;
 
 __global__ void __launch_bounds__(128)
-k_resize(const __grid_constant__ Geo g, uint8_t *__restrict__ pyr, const int2 *__restrict__ tables, int level)
+k_resize(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr_src, uint8_t *__restrict__ pyr_dst,
+         const int2 *__restrict__ tables, int level)
 {
     const LevelGeom &D = g.lv[level];
     const LevelGeom &S = g.lv[level - 1];
@@ -97,13 +98,15 @@ k_resize(const __grid_constant__ Geo g, uint8_t *__restrict__ pyr, const int2 *_
         o1[k] = min(o0[k] + 1, S.w - 1);
         c1[k] = c0[k] >> 16; c0[k] = (short)(c0[k] & 0xffff);
     }
-    const uint8_t *src = pyr + S.base + (size_t)f * S.frame_stride + (size_t)kPadY * S.pitch + kPadX;
-    uint8_t *dst = pyr + D.base + (size_t)f * D.frame_stride + (size_t)chunk * 4;
+    // source and destination levels live in the same allocation but never overlap: separate restrict
+    // pointers let the compiler hoist the next row's loads above this row's store
+    const uint8_t *__restrict__ src = pyr_src + S.base + (size_t)f * S.frame_stride + (size_t)kPadY * S.pitch + kPadX;
+    uint8_t *__restrict__ dst = pyr_dst + D.base + (size_t)f * D.frame_stride + (size_t)chunk * 4;
     const int2 *taby = tables + D.taby;
     const int Ybase = (int)blockIdx.y * kResizeRows - B;
     int prev_sy1 = -0x7fffffff;
     int hp[4] = { 0, 0, 0, 0 };
-#pragma unroll 1
+#pragma unroll 2
     for (int r = 0; r < kResizeRows; ++r) {
         const int Y = Ybase + r;
         if (Y >= D.h + B) break;
@@ -152,7 +155,7 @@ void launch_resize(const Geo &g, const DevBuffers &b, int level, int nframes, cu
     const int B = g.border_on ? kBorder : kMinBlurBorder;
     const int chunks = g.lv[level].pitch / 4;
     dim3 grd((chunks + 127) / 128, (g.lv[level].h + 2 * B + kResizeRows - 1) / kResizeRows, nframes);
-    k_resize<<<grd, 128, 0, s>>>(g, b.pyr, b.tables, level);
+    k_resize<<<grd, 128, 0, s>>>(g, b.pyr, b.pyr, b.tables, level);
 }
 
 } // namespace orbx
