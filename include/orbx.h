@@ -12,6 +12,7 @@
  *   orbx_download_level              mvImagePyramid (public member)    include/ORBextractor.h:71, src/ORBextractor.cpp:1071-1096
  *   orbm_hamming_pairs_host          ORBmatcher::DescriptorDistance    include/ORBmatcher.h:19, src/ORBmatcher.cpp:128-144
  *   orbm_knn2_* / orbm_ratio_select  best-2 scan + acceptance          src/ORBmatcher.cpp:37-67
+ *   orbm_search_init_device          ORBmatcher::SearchForInitialization + Frame grid   src/ORBmatcher.cpp:9-126, src/Frame.cpp:144-168,219-271
  *   orbm_merge_shards_device         (database sharding; no reference counterpart)
  *
  * All functions return 0 on success or a negative ORBX_E_* code; nothing throws across the ABI.
@@ -152,6 +153,24 @@ int orbm_merge_shards_device(orbm_matcher *m, const int32_t *d_d1, const int32_t
  * orbm_set_profiling(m, 1) before the call.  Synchronises the stream. */
 int orbm_set_profiling(orbm_matcher *m, int enabled);
 int orbm_knn2_times(orbm_matcher *m, float *scan_ms, float *merge_ms);
+
+/* ORBmatcher::SearchForInitialization (src/ORBmatcher.cpp:9-126) on extractor outputs, including the Frame grid
+ * it queries (Frame::AssignFeaturesToGrid / GetFeaturesInArea, src/Frame.cpp:144-168, 219-271): windowed best-2
+ * with the sequential one-to-one gate, TH_LOW / ratio acceptance, rotation-histogram filter, prev-matched update.
+ *   d_kps/d_desc/d_counts: [nframes][capacity] arrays as written by orbx_extract_device
+ *   pair p matches frame d_pair_a[p] (reference frame F1) against frame d_pair_b[p] (F2)
+ *   d_prev_matched [npairs][capacity][2] float, in/out (vbPrevMatched);  d_matches12 [npairs][capacity] (vnMatches12)
+ *   d_nmatches [npairs]: the return value of the reference function, or -1 if the workspace was too small
+ *   width/height: image size (grid bounds of an undistorted frame, src/Frame.cpp:113-118)
+ *   literal_gridid_bug != 0 reproduces src/Frame.cpp:164 as written (y cell computed against miMaxY: no candidates)
+ *   workspace: device scratch, orbm_search_init_workspace_bytes(capacity, npairs) always suffices.
+ * capacity must be < 65536. */
+size_t orbm_search_init_workspace_bytes(int capacity, int npairs);
+int orbm_search_init_device(orbm_matcher *m, const orbx_keypoint *d_kps, const uint8_t *d_desc, const int32_t *d_counts,
+                            int capacity, const int32_t *d_pair_a, const int32_t *d_pair_b, int npairs,
+                            float *d_prev_matched, int32_t *d_matches12, int32_t *d_nmatches,
+                            int window, float nnratio, int check_orientation, int width, int height,
+                            int literal_gridid_bug, void *d_workspace, size_t workspace_bytes, void *stream);
 
 /* Integer-pipe microbenchmark used for the kNN roofline: runs a dependent-free POPC loop on every
  * SM and returns measured 32-bit POPC results per second (device-event timed). */

@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "orbx_set_profiling", "orbx_stage_times", "orbm_set_profiling", "orbm_knn2_times",
     "orbm_create", "orbm_destroy", "orbm_launch_count", "orbm_hamming_pairs_host",
     "orbm_knn2_device", "orbm_knn2_host", "orbm_ratio_select_device", "orbm_merge_shards_device",
-    "orbm_popc_peak",
+    "orbm_popc_peak", "orbm_search_init_workspace_bytes", "orbm_search_init_device",
 ]
 
 
@@ -86,6 +86,9 @@ def load():
     L.orbm_set_profiling.argtypes = [vp, i32]
     L.orbm_knn2_times.argtypes = [vp, C.POINTER(f32), C.POINTER(f32)]
     L.orbm_popc_peak.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.orbm_search_init_workspace_bytes.restype = sz
+    L.orbm_search_init_workspace_bytes.argtypes = [i32, i32]
+    L.orbm_search_init_device.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, vp, i32, f32, i32, i32, i32, i32, vp, sz, vp]
     _lib = L
     return L
 
@@ -225,6 +228,13 @@ class Matcher:
                             shard_stride=0):
         check(load().orbm_merge_shards_device(self.h, d1_ptr, idx1_ptr, d2_ptr, nshards, nq, shard_stride,
                                               od1_ptr, oidx1_ptr, od2_ptr, stream))
+
+    def search_init_device(self, kps_ptr, desc_ptr, counts_ptr, capacity, pair_a_ptr, pair_b_ptr, npairs, prev_ptr,
+                           matches_ptr, nmatches_ptr, window, nnratio, check_ori, width, height, ws_ptr, ws_bytes,
+                           stream=0, literal_bug=False):
+        check(load().orbm_search_init_device(self.h, kps_ptr, desc_ptr, counts_ptr, capacity, pair_a_ptr, pair_b_ptr, npairs,
+                                             prev_ptr, matches_ptr, nmatches_ptr, window, nnratio, int(check_ori), width,
+                                             height, int(literal_bug), ws_ptr, ws_bytes, stream))
 
     def set_profiling(self, on):
         check(load().orbm_set_profiling(self.h, int(on)))

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "liborbx.so")
-SOURCES = ["abi.cu", "pyramid.cu", "fast.cu", "octree.cu", "describe.cu", "knn.cu"]
+SOURCES = ["abi.cu", "pyramid.cu", "fast.cu", "octree.cu", "describe.cu", "knn.cu", "search_init.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--fmad=true", "-shared", "-cudart", "static"]
 

@@ -20,6 +20,16 @@ void launch_hamming_pairs(const uint8_t *a, const uint8_t *b, int n, int *dist, 
 void launch_ratio_select(const int *d1, const int *idx1, const int *d2, int nq, int th, float ratio, int *match, cudaStream_t s);
 void launch_merge_shards(const int *d1, const int *idx1, const int *d2, int nshards, int nq, size_t stride, int *od1, int *oidx1, int *od2, cudaStream_t s);
 int run_popc_bench(int mode, int sm_count, double *ops_per_second);
+// search_init.cu
+struct SearchInitArgs {
+    const orbx_keypoint *kps; const uint8_t *desc; const int *counts; int cap;
+    const int *pair_a, *pair_b; int npairs;
+    float *prev_matched; int *matches12; int *nmatches;
+    int window; float nnratio; int check_ori; float max_x, max_y; int literal_bug;
+    uint32_t *workspace; unsigned long long ws_words_per_pair;
+    int sort_n;
+};
+int launch_search_init(const SearchInitArgs &a, cudaStream_t s);
 } // namespace orbx
 
 using namespace orbx;
@@ -751,6 +761,39 @@ extern "C" int orbm_merge_shards_device(orbm_matcher *m, const int32_t *d_d1, co
     CK(cudaSetDevice(m->device));
     launch_merge_shards(d_d1, d_idx1, d_d2, nshards, nq, shard_stride, d_od1, d_oidx1, d_od2, stream ? (cudaStream_t)stream : m->stream);
     m->launches += nq > 0;
+    CK(cudaGetLastError());
+    return ORBX_OK;
+}
+
+extern "C" size_t orbm_search_init_workspace_bytes(int capacity, int npairs)
+{
+    if (capacity < 1 || npairs < 1) return 0;
+    return (size_t)capacity * ((size_t)capacity + 1) * sizeof(uint32_t) * (size_t)npairs;
+}
+
+extern "C" int orbm_search_init_device(orbm_matcher *m, const orbx_keypoint *d_kps, const uint8_t *d_desc, const int32_t *d_counts,
+                                       int capacity, const int32_t *d_pair_a, const int32_t *d_pair_b, int npairs,
+                                       float *d_prev_matched, int32_t *d_matches12, int32_t *d_nmatches,
+                                       int window, float nnratio, int check_orientation, int width, int height,
+                                       int literal_gridid_bug, void *d_workspace, size_t workspace_bytes, void *stream)
+{
+    if (!m || npairs < 0 || capacity < 1 || capacity >= 65536 || width < 1 || height < 1 || window < 0) return ORBX_E_INVALID;
+    if (npairs == 0) return ORBX_OK;
+    if (!d_kps || !d_desc || !d_counts || !d_pair_a || !d_pair_b || !d_prev_matched || !d_matches12 || !d_nmatches || !d_workspace)
+        return ORBX_E_INVALID;
+    if (((uintptr_t)d_desc & 15) || ((uintptr_t)d_workspace & 3)) return ORBX_E_INVALID;
+    CK(cudaSetDevice(m->device));
+    SearchInitArgs a;
+    a.kps = d_kps; a.desc = d_desc; a.counts = d_counts; a.cap = capacity;
+    a.pair_a = d_pair_a; a.pair_b = d_pair_b; a.npairs = npairs;
+    a.prev_matched = d_prev_matched; a.matches12 = d_matches12; a.nmatches = d_nmatches;
+    a.window = window; a.nnratio = nnratio; a.check_ori = check_orientation ? 1 : 0;
+    a.max_x = (float)width; a.max_y = (float)height; a.literal_bug = literal_gridid_bug ? 1 : 0;
+    a.workspace = (uint32_t *)d_workspace; a.ws_words_per_pair = workspace_bytes / sizeof(uint32_t) / (size_t)npairs;
+    int sn = 32; while (sn < capacity) sn <<= 1;
+    a.sort_n = sn;
+    if (launch_search_init(a, stream ? (cudaStream_t)stream : m->stream)) return cuda_fail(cudaGetLastError(), "search_init smem");
+    m->launches += 1;
     CK(cudaGetLastError());
     return ORBX_OK;
 }

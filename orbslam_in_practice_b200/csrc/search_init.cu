@@ -1,0 +1,248 @@
+// search_init.cu -- ORBmatcher::SearchForInitialization (src/ORBmatcher.cpp:9-126) with the Frame grid it
+// queries (Frame::AssignFeaturesToGrid / GetGridId src/Frame.cpp:144-168, GetFeaturesInArea :219-271).
+//
+// One thread block per frame pair (F1 = reference frame, F2 = current frame):
+//   1  grid of F2: keys (cell << 16 | keypoint index) of the octave-0 keypoints, bitonic-sorted in shared memory.
+//      Cell id = ix * 48 + iy, so the reference's enumeration order (ix outer, iy inner, push_back order inside a
+//      cell) is exactly ascending key order, and for a fixed ix the cells iy0..iy1 are ONE contiguous range.
+//   2a parallel, warp per octave-0 query: window query -> candidate list (index, Hamming distance) in reference
+//      scan order, written to the caller's workspace.  This is the data-parallel part (all the POPC work).
+//   2b sequential, one warp: the reference's order-dependent part -- the gate `vMatchedDistance[i2] <= dist`
+//      (:49-50) makes every query depend on the acceptances before it -- replayed over the compact lists:
+//      best-2 with first-minimum-wins, TH_LOW / ratio acceptance, one-to-one displacement (:65-77), rotation
+//      histogram pushes (:79-90).
+//   3  ComputeThreeMaxima (:147-188) and the histogram filter (:93-118), then the prev-matched update (:121-124).
+#include "orbx_internal.cuh"
+
+#include <climits>
+
+namespace orbx {
+
+constexpr int kGridRows = 48, kGridCols = 64;   // Frame.h:11-12
+constexpr int kHistoLength = 30;                // ORBmatcher.cpp:6
+constexpr int kThLow = 50;                      // ORBmatcher.cpp:7
+constexpr int kSiThreads = 256;
+constexpr uint32_t kInfKey = 0xffffffffu;
+
+struct SearchInitArgs {                      // keep in sync with the declaration in abi.cu
+    const orbx_keypoint *kps; const uint8_t *desc; const int *counts; int cap;      // extractor outputs [F][cap]
+    const int *pair_a, *pair_b; int npairs;
+    float *prev_matched; int *matches12; int *nmatches;                              // [npairs][cap][2], [npairs][cap], [npairs]
+    int window; float nnratio; int check_ori; float max_x, max_y; int literal_bug;
+    uint32_t *workspace; unsigned long long ws_words_per_pair;
+    int sort_n;                                                                      // power of two >= cap
+};
+
+__device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const uint4 *__restrict__ b)
+{
+    const uint4 b0 = __ldg(b), b1 = __ldg(b + 1);
+    return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+           __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+__global__ void __launch_bounds__(kSiThreads)
+k_search_init(const SearchInitArgs A)
+{
+    extern __shared__ __align__(16) unsigned char si_smem[];
+    uint32_t *keys = reinterpret_cast<uint32_t *>(si_smem);                         // [sort_n] sorted grid keys of F2
+    unsigned short *cellstart = reinterpret_cast<unsigned short *>(keys + A.sort_n);// [64 * 49 + 1] first key of (ix, iy)
+    int *matchedDist = reinterpret_cast<int *>(cellstart + ((kGridCols * (kGridRows + 1) + 2) & ~1));   // [cap]
+    int *m21 = matchedDist + A.cap;                                                  // [cap]
+    __shared__ int hist[kHistoLength];
+    __shared__ int s_nvalid, s_nmatches, s_keep[3];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int pair = blockIdx.x;
+    const int fa = A.pair_a[pair], fb = A.pair_b[pair];
+    const int n1 = A.counts[fa], n2 = A.counts[fb];
+    const orbx_keypoint *kp1 = A.kps + (size_t)fa * A.cap, *kp2 = A.kps + (size_t)fb * A.cap;
+    const uint4 *d1 = reinterpret_cast<const uint4 *>(A.desc + (size_t)fa * A.cap * 32);
+    const uint4 *d2 = reinterpret_cast<const uint4 *>(A.desc + (size_t)fb * A.cap * 32);
+    float *prev = A.prev_matched + (size_t)pair * A.cap * 2;
+    int *m12 = A.matches12 + (size_t)pair * A.cap;
+    uint32_t *ws = A.workspace + (size_t)pair * A.ws_words_per_pair;
+
+    // image bounds for zero distortion (Frame.cpp:113-118) and grid cell sizes (:59-60)
+    const float minX = 0.f, minY = 0.f, maxX = A.max_x, maxY = A.max_y;
+    const float wInv = (float)kGridCols / (maxX - minX), hInv = (float)kGridRows / (maxY - minY);
+
+    // ---- 1: grid keys of F2 (octave 0 only: SearchForInitialization queries minLevel = maxLevel = 0) ----
+    for (int i = tid; i < A.sort_n; i += kSiThreads) {
+        uint32_t key = kInfKey;
+        if (i < n2) {
+            const orbx_keypoint k = kp2[i];
+            // GetGridId takes doubles (Frame.cpp:161-168); std::round = half away from zero
+            const int ix = (int)round(((double)k.x - (double)minX) * (double)wInv);
+            const int iy = (int)round(((double)k.y - (double)(A.literal_bug ? maxY : minY)) * (double)hInv);
+            if (k.octave == 0 && ix >= 0 && ix < kGridCols && iy >= 0 && iy < kGridRows)
+                key = ((uint32_t)(ix * kGridRows + iy) << 16) | (uint32_t)i;
+        }
+        keys[i] = key;
+    }
+    for (int i = tid; i < A.cap; i += kSiThreads) { matchedDist[i] = INT_MAX; m21[i] = -1; m12[i] = -1; }
+    if (tid < kHistoLength) hist[tid] = 0;
+    if (tid == 0) s_nmatches = 0;
+    __syncthreads();
+    for (int k = 2; k <= A.sort_n; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < A.sort_n; i += kSiThreads) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const uint32_t a = keys[i], b = keys[p];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { keys[i] = b; keys[p] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    // first key position of every (ix, iy) and the end sentinel: lower_bound by binary search
+    for (int c = tid; c <= kGridCols * kGridRows; c += kSiThreads) {
+        const uint32_t target = (uint32_t)c << 16;
+        int lo = 0, hi = A.sort_n;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < target) lo = mid + 1; else hi = mid; }
+        cellstart[c] = (unsigned short)lo;
+        if (c == kGridCols * kGridRows) s_nvalid = lo;
+    }
+    __syncthreads();
+    const int nvalid = s_nvalid;                        // octave-0 keypoints of F2 that landed in the grid
+    // workspace rows: one candidate list per query of F1, stride = nvalid entries (+1 word for the count)
+    const unsigned long long stride = (unsigned long long)nvalid + 1ull;
+    const bool ws_ok = stride * (unsigned long long)n1 <= A.ws_words_per_pair;
+    if (!ws_ok) { if (tid == 0) A.nmatches[pair] = -1; return; }          // caller's workspace too small
+
+    // ---- 2a: candidate lists, warp per query ----
+    const float r = (float)A.window;
+    for (int q = warp; q < n1; q += kSiThreads / 32) {
+        uint32_t *list = ws + (unsigned long long)q * stride;
+        const orbx_keypoint kq = kp1[q];
+        int cnt = 0;
+        if (kq.octave == 0) {                                              // :25-27 level1 > 0 -> continue
+            const float x = prev[2 * q], y = prev[2 * q + 1];
+            // GetFeaturesInArea cell window, Frame.cpp:225-239 (float math)
+            const int cx0 = max(0, (int)floorf((x - minX - r) * wInv));
+            const int cx1 = min(kGridCols - 1, (int)ceilf((x - minX + r) * wInv));
+            const int cy0 = max(0, (int)floorf((y - minY - r) * hInv));
+            const int cy1 = min(kGridRows - 1, (int)ceilf((y - minY + r) * hInv));
+            if (cx0 < kGridCols && cx1 >= 0 && cy0 < kGridRows && cy1 >= 0) {
+                const uint4 a0 = __ldg(d1 + 2 * q), a1 = __ldg(d1 + 2 * q + 1);
+                for (int ix = cx0; ix <= cx1; ++ix) {
+                    const int s = cellstart[ix * kGridRows + cy0], e = cellstart[ix * kGridRows + cy1 + 1];
+                    for (int b0 = s; b0 < e; b0 += 32) {
+                        const int p = b0 + lane;
+                        bool ok = false; uint32_t ent = 0;
+                        if (p < e) {
+                            const int i2 = (int)(keys[p] & 0xffffu);
+                            const orbx_keypoint k2 = kp2[i2];
+                            const float dx = k2.x - x, dy = k2.y - y;                  // Frame.cpp:263-266
+                            if (fabsf(dx) < r && fabsf(dy) < r) {
+                                ok = true;
+                                ent = (uint32_t)i2 | ((uint32_t)hamming256(a0, a1, d2 + 2 * i2) << 16);
+                            }
+                        }
+                        const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+                        if (ok) list[1 + cnt + __popc(bal & ((1u << lane) - 1u))] = ent;
+                        cnt += __popc(bal);
+                    }
+                }
+            }
+        }
+        if (lane == 0) list[0] = (uint32_t)cnt;
+    }
+    __syncthreads();
+
+    // ---- 2b: the order-dependent replay, one warp ----
+    if (warp == 0) {
+        const float factor = kHistoLength / 360.0f;                          // :17
+        int nmatches = 0;
+        for (int q = 0; q < n1; ++q) {
+            const uint32_t *list = ws + (unsigned long long)q * stride;
+            const int cnt = (int)list[0];
+            if (cnt == 0) continue;                                            // :32-33 (also covers octave > 0)
+            uint32_t k1 = kInfKey, k2 = kInfKey;                              // two smallest (dist << 16 | scan position)
+            for (int b0 = 0; b0 < cnt; b0 += 32) {
+                const int p = b0 + lane;
+                uint32_t key = kInfKey;
+                if (p < cnt) {
+                    const uint32_t ent = list[1 + p];
+                    const int i2 = (int)(ent & 0xffffu), dist = (int)(ent >> 16);
+                    if (!(matchedDist[i2] <= dist)) key = ((uint32_t)dist << 16) | (uint32_t)p;   // :49-50 gate
+                }
+                const uint32_t hi = max(k1, key);
+                k1 = min(k1, key); k2 = min(k2, hi);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {                                // merge the lanes' sorted pairs
+                const uint32_t o1 = __shfl_xor_sync(0xffffffffu, k1, o), o2 = __shfl_xor_sync(0xffffffffu, k2, o);
+                const uint32_t lo = min(k1, o1), mid = max(k1, o1);
+                k2 = min(min(k2, o2), mid); k1 = lo;
+            }
+            if (lane == 0 && k1 != kInfKey) {
+                const int bestDist = (int)(k1 >> 16);
+                const int bestDist2 = k2 == kInfKey ? INT_MAX : (int)(k2 >> 16);
+                const int bestIdx2 = (int)(list[1 + (k1 & 0xffffu)] & 0xffffu);
+                if (bestDist <= kThLow && (float)bestDist < __fmul_rn((float)bestDist2, A.nnratio)) {   // :65-67
+                    if (m21[bestIdx2] >= 0) { m12[m21[bestIdx2]] = -1; nmatches--; }
+                    m12[q] = bestIdx2; m21[bestIdx2] = q; matchedDist[bestIdx2] = bestDist; nmatches++;
+                    if (A.check_ori) {                                        // :79-90
+                        float rot = __fsub_rn(kp1[q].angle, kp2[bestIdx2].angle);
+                        if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+                        int bin = (int)roundf(__fmul_rn(rot, factor));
+                        if (bin == kHistoLength) bin = 0;
+                        hist[bin]++;
+                        ws[(unsigned long long)q * stride] = 0x80000000u | (uint32_t)bin;   // remember the bin (count no longer needed)
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        if (lane == 0) {
+            s_nmatches = nmatches;
+            // ComputeThreeMaxima :147-188
+            int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+            for (int i = 0; i < kHistoLength; ++i) {
+                const int s = hist[i];
+                if (s > max1) { max3 = max2; max2 = max1; max1 = s; ind3 = ind2; ind2 = ind1; ind1 = i; }
+                else if (s > max2) { max3 = max2; max2 = s; ind3 = ind2; ind2 = i; }
+                else if (s > max3) { max3 = s; ind3 = i; }
+            }
+            if ((float)max2 < 0.1f * (float)max1) { ind2 = -1; ind3 = -1; }
+            else if ((float)max3 < 0.1f * (float)max1) { ind3 = -1; }
+            s_keep[0] = ind1; s_keep[1] = ind2; s_keep[2] = ind3;
+        }
+    }
+    __syncthreads();
+
+    // ---- 3: histogram filter (:93-118) and prev-matched update (:121-124) ----
+    int removed = 0;
+    for (int q = tid; q < n1; q += kSiThreads) {
+        int m = m12[q];
+        if (m >= 0 && A.check_ori) {
+            const uint32_t tag = ws[(unsigned long long)q * stride];
+            const int bin = (int)(tag & 0xffu);
+            if ((tag & 0x80000000u) && bin != s_keep[0] && bin != s_keep[1] && bin != s_keep[2]) { m12[q] = -1; m = -1; ++removed; }
+        }
+        if (m >= 0) { prev[2 * q] = kp2[m].x; prev[2 * q + 1] = kp2[m].y; }
+    }
+    if (removed) atomicSub(&s_nmatches, removed);
+    __syncthreads();
+    if (tid == 0) A.nmatches[pair] = s_nmatches;
+}
+
+size_t search_init_smem_bytes(int cap, int sort_n)
+{
+    return (size_t)sort_n * 4 + (size_t)((kGridCols * (kGridRows + 1) + 2) & ~1) * 2 + (size_t)cap * 8 + 16;
+}
+
+int launch_search_init(const SearchInitArgs &a, cudaStream_t s)
+{
+    const size_t smem = search_init_smem_bytes(a.cap, a.sort_n);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+        if (cudaFuncSetAttribute(k_search_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+        configured = smem;
+    }
+    k_search_init<<<a.npairs, kSiThreads, smem, s>>>(a);
+    return 0;
+}
+
+} // namespace orbx

@@ -1,0 +1,84 @@
+"""GPU parity, SURVEY.md 8f-1: ORBmatcher::SearchForInitialization + the Frame grid (AssignFeaturesToGrid /
+GetFeaturesInArea) on the device vs the oracle (which is pinned against the reference's own ORBmatcher.cpp)."""
+import numpy as np
+import pytest
+
+from orbslam_in_practice_b200.synth import synth_frame
+
+pytestmark = pytest.mark.gpu
+
+
+def _frames():
+    a = synth_frame(0); b = np.roll(np.roll(a, 5, axis=1), 3, axis=0)
+    c = synth_frame(1); d = np.roll(np.roll(c, -12, axis=1), 9, axis=0)
+    return np.stack([a, b, c, d])
+
+
+@pytest.mark.parametrize("ratio,ori,bug", [(0.9, True, False), (0.7, False, False), (0.9, True, True)])
+def test_search_for_initialization_matches_oracle(orbx, oracle, ratio, ori, bug):
+    import torch
+    imgs = _frames()
+    F = len(imgs)
+    ex = orbx.Extractor(nfeatures=2000, max_width=640, max_height=480, max_batch=F)
+    cap = ex.capacity
+    dev = torch.device("cuda:0")
+    d_img = torch.from_numpy(imgs).to(dev)
+    d_kps = torch.zeros((F, cap, 7), dtype=torch.float32, device=dev)
+    d_desc = torch.zeros((F, cap, 32), dtype=torch.uint8, device=dev)
+    d_cnt = torch.zeros(F, dtype=torch.int32, device=dev)
+    st = torch.cuda.Stream(); torch.cuda.set_stream(st); s = st.cuda_stream
+    ex.extract_device(d_img.data_ptr(), 640, 640 * 480, 640, 480, F, d_kps.data_ptr(), d_desc.data_ptr(), d_cnt.data_ptr(), s)
+    pairs = [(0, 1), (1, 0), (2, 3), (0, 2)]
+    P = len(pairs)
+    pa = torch.tensor([p[0] for p in pairs], dtype=torch.int32, device=dev)
+    pb = torch.tensor([p[1] for p in pairs], dtype=torch.int32, device=dev)
+    prev = torch.stack([d_kps[p[0], :, :2] for p in pairs]).contiguous()      # Tracking.cpp:170-176: prev = F1 keypoints
+    prev0 = prev.clone()
+    m12 = torch.full((P, cap), -7, dtype=torch.int32, device=dev)
+    nm = torch.zeros(P, dtype=torch.int32, device=dev)
+    m = orbx.Matcher(cap, cap)
+    wsb = orbx.load().orbm_search_init_workspace_bytes(cap, P)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+    m.search_init_device(d_kps.data_ptr(), d_desc.data_ptr(), d_cnt.data_ptr(), cap, pa.data_ptr(), pb.data_ptr(), P,
+                         prev.data_ptr(), m12.data_ptr(), nm.data_ptr(), 100, ratio, ori, 640, 480, ws.data_ptr(), wsb, s, bug)
+    torch.cuda.synchronize()
+    kps = d_kps.cpu().numpy().view(np.float32).reshape(F, cap, 7)
+    kps_s = np.zeros((F, cap), oracle.KEYPOINT_DTYPE)
+    for i, fld in enumerate(("x", "y", "size", "angle", "response")):
+        kps_s[fld] = kps[:, :, i]
+    kps_s["octave"] = kps[:, :, 5].view(np.int32); kps_s["class_id"] = kps[:, :, 6].view(np.int32)
+    desc = d_desc.cpu().numpy(); cnt = d_cnt.cpu().numpy()
+    got_m, got_n, got_prev = m12.cpu().numpy(), nm.cpu().numpy(), prev.cpu().numpy()
+    for p, (a, b) in enumerate(pairs):
+        n1, n2 = int(cnt[a]), int(cnt[b])
+        n_o, m_o, p_o = oracle.search_for_initialization(kps_s[a, :n1], desc[a, :n1], kps_s[b, :n2], desc[b, :n2],
+                                                         prev0[p, :n1].cpu().numpy(), 100, ratio, ori, 640, 480, bug)
+        assert got_n[p] == n_o, "pair %s: nmatches %d vs %d" % ((a, b), got_n[p], n_o)
+        assert np.array_equal(got_m[p, :n1], m_o)
+        assert np.array_equal(got_prev[p, :n1], p_o)
+        if bug:
+            assert n_o == 0
+        elif (a, b) in ((0, 1), (1, 0), (2, 3)):
+            assert n_o > 50
+
+
+def test_search_init_workspace_too_small_is_reported(orbx):
+    import torch
+    imgs = _frames()[:2]
+    ex = orbx.Extractor(nfeatures=500, max_width=640, max_height=480, max_batch=2)
+    cap = ex.capacity
+    dev = torch.device("cuda:0")
+    d_img = torch.from_numpy(imgs).to(dev)
+    d_kps = torch.zeros((2, cap, 7), dtype=torch.float32, device=dev); d_desc = torch.zeros((2, cap, 32), dtype=torch.uint8, device=dev)
+    d_cnt = torch.zeros(2, dtype=torch.int32, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+    ex.extract_device(d_img.data_ptr(), 640, 640 * 480, 640, 480, 2, d_kps.data_ptr(), d_desc.data_ptr(), d_cnt.data_ptr(), s)
+    torch.cuda.synchronize()
+    pa = torch.tensor([0], dtype=torch.int32, device=dev); pb = torch.tensor([1], dtype=torch.int32, device=dev)
+    prev = d_kps[0:1, :, :2].contiguous(); m12 = torch.zeros((1, cap), dtype=torch.int32, device=dev); nm = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws = torch.empty(64, dtype=torch.uint8, device=dev)
+    m = orbx.Matcher(cap, cap)
+    m.search_init_device(d_kps.data_ptr(), d_desc.data_ptr(), d_cnt.data_ptr(), cap, pa.data_ptr(), pb.data_ptr(), 1,
+                         prev.data_ptr(), m12.data_ptr(), nm.data_ptr(), 100, 0.9, True, 640, 480, ws.data_ptr(), 64, s)
+    torch.cuda.synchronize()
+    assert int(nm[0]) == -1
