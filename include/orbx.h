@@ -172,6 +172,14 @@ int orbm_search_init_device(orbm_matcher *m, const orbx_keypoint *d_kps, const u
                             int window, float nnratio, int check_orientation, int width, int height,
                             int literal_gridid_bug, void *d_workspace, size_t workspace_bytes, void *stream);
 
+/* Host-pointer convenience for ONE frame pair (what ORBSlam::ORBmatcher::SearchForInitialization forwards to):
+ * copies both frames' keypoints/descriptors and prev_matched in, runs the kernel, copies matches12 (n1 ints),
+ * the updated prev_matched (n1 x 2 floats) and the match count out; synchronous.  n1, n2 < 65536. */
+int orbm_search_init_host(orbm_matcher *m, const orbx_keypoint *kp1, const uint8_t *desc1, int n1,
+                          const orbx_keypoint *kp2, const uint8_t *desc2, int n2,
+                          float *prev_matched, int32_t *matches12, int32_t *nmatches,
+                          int window, float nnratio, int check_orientation, int width, int height, int literal_gridid_bug);
+
 /* Integer-pipe microbenchmark used for the kNN roofline: runs a dependent-free POPC loop on every
  * SM and returns measured 32-bit POPC results per second (device-event timed). */
 int orbm_popc_peak(int device, double *popc_per_second, double *lop3_per_second);

@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "orbx_set_profiling", "orbx_stage_times", "orbm_set_profiling", "orbm_knn2_times",
     "orbm_create", "orbm_destroy", "orbm_launch_count", "orbm_hamming_pairs_host",
     "orbm_knn2_device", "orbm_knn2_host", "orbm_ratio_select_device", "orbm_merge_shards_device",
-    "orbm_popc_peak", "orbm_search_init_workspace_bytes", "orbm_search_init_device",
+    "orbm_popc_peak", "orbm_search_init_workspace_bytes", "orbm_search_init_device", "orbm_search_init_host",
 ]
 
 
@@ -88,6 +88,7 @@ def load():
     L.orbm_popc_peak.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.orbm_search_init_workspace_bytes.restype = sz
     L.orbm_search_init_workspace_bytes.argtypes = [i32, i32]
+    L.orbm_search_init_host.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, vp, C.POINTER(i32), i32, f32, i32, i32, i32, i32]
     L.orbm_search_init_device.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, vp, i32, f32, i32, i32, i32, i32, vp, sz, vp]
     _lib = L
     return L
@@ -235,6 +236,16 @@ class Matcher:
         check(load().orbm_search_init_device(self.h, kps_ptr, desc_ptr, counts_ptr, capacity, pair_a_ptr, pair_b_ptr, npairs,
                                              prev_ptr, matches_ptr, nmatches_ptr, window, nnratio, int(check_ori), width,
                                              height, int(literal_bug), ws_ptr, ws_bytes, stream))
+
+    def search_init_host(self, kp1, desc1, kp2, desc2, prev_matched, window=100, nnratio=0.9, check_ori=True,
+                         width=640, height=480, literal_bug=False):
+        kp1 = np.ascontiguousarray(kp1, KEYPOINT_DTYPE); kp2 = np.ascontiguousarray(kp2, KEYPOINT_DTYPE)
+        desc1 = np.ascontiguousarray(desc1, np.uint8); desc2 = np.ascontiguousarray(desc2, np.uint8)
+        prev = np.ascontiguousarray(prev_matched, np.float32).copy()
+        m12 = np.zeros(len(kp1), np.int32); n = C.c_int()
+        check(load().orbm_search_init_host(self.h, _p(kp1), _p(desc1), len(kp1), _p(kp2), _p(desc2), len(kp2), _p(prev), _p(m12),
+                                           C.byref(n), window, nnratio, int(check_ori), width, height, int(literal_bug)))
+        return n.value, m12, prev
 
     def set_profiling(self, on):
         check(load().orbm_set_profiling(self.h, int(on)))

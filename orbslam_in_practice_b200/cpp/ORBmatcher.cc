@@ -59,6 +59,27 @@ void ORBmatcher::BestTwo(const cv::Mat &queries, const cv::Mat &database, std::v
     check(orbm_knn2_host(mHandle, q.data(), nq, d.data(), ndb, 0, bestDist.data(), bestIdx.data(), bestDist2.data()), "knn2");
 }
 
+int ORBmatcher::SearchForInitialization(const std::vector<cv::KeyPoint> &vKeys1, const cv::Mat &Descriptors1,
+                                        const std::vector<cv::KeyPoint> &vKeys2, const cv::Mat &Descriptors2,
+                                        std::vector<cv::Point2f> &vbPrevMatched, std::vector<int> &vnMatches12, int windowSize,
+                                        int imageWidth, int imageHeight)
+{
+    const int n1 = (int)vKeys1.size(), n2 = (int)vKeys2.size();
+    vnMatches12.assign((size_t)n1, -1);                                       // src/ORBmatcher.cpp:13
+    if (n1 == 0) return 0;
+    if ((int)vbPrevMatched.size() != n1) throw std::runtime_error("ORBmatcher: vbPrevMatched must have one entry per keypoint of F1");
+    Ensure(n1 > n2 ? n1 : n2, n1 > n2 ? n1 : n2);
+    static_assert(sizeof(cv::KeyPoint) == sizeof(orbx_keypoint) && sizeof(cv::Point2f) == 8, "layout");
+    const std::vector<unsigned char> d1 = pack_rows(Descriptors1), d2 = n2 ? pack_rows(Descriptors2) : std::vector<unsigned char>();
+    int nmatches = 0;
+    check(orbm_search_init_host(mHandle, (const orbx_keypoint *)vKeys1.data(), d1.data(), n1,
+                                (const orbx_keypoint *)vKeys2.data(), d2.data(), n2, (float *)vbPrevMatched.data(),
+                                vnMatches12.data(), &nmatches, windowSize, mfNNratio, mbCheckOrientation ? 1 : 0,
+                                imageWidth, imageHeight, 0), "search_init");
+    if (nmatches < 0) throw std::runtime_error("ORBmatcher: search workspace too small");
+    return nmatches;
+}
+
 int ORBmatcher::SearchBruteForce(const cv::Mat &queries, const cv::Mat &database, std::vector<int> &vnMatches12)
 {
     std::vector<int> d1, i1, d2;

@@ -34,6 +34,14 @@ public:
     // vnMatches12[i] = database row or -1
     int SearchBruteForce(const cv::Mat &queries, const cv::Mat &database, std::vector<int> &vnMatches12);
 
+    // SearchForInitialization (src/ORBmatcher.cpp:9-126) on plain containers: F1 = (vKeys1, Descriptors1),
+    // F2 = (vKeys2, Descriptors2), undistorted keypoints, grid bounds [0,width) x [0,height) (src/Frame.cpp:113-118).
+    // The reference's Frame-typed overload forwards here with F.GetUnKeyPts() / F.GetDescriptors().
+    int SearchForInitialization(const std::vector<cv::KeyPoint> &vKeys1, const cv::Mat &Descriptors1,
+                                const std::vector<cv::KeyPoint> &vKeys2, const cv::Mat &Descriptors2,
+                                std::vector<cv::Point2f> &vbPrevMatched, std::vector<int> &vnMatches12, int windowSize,
+                                int imageWidth, int imageHeight);
+
     static const int TH_LOW;
     static const int HISTO_LENGTH;
 

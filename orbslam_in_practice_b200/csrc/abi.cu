@@ -614,6 +614,7 @@ struct orbm_matcher {
     cudaStream_t stream;
     uint2 *partial; size_t partial_elems;
     uint8_t *d_q, *d_db; int *d_out;   // device staging for the host-pointer entry points
+    void *si_buf; size_t si_bytes;     // scratch of orbm_search_init_host
     long long launches;
     int profiling; bool ev_valid;
     cudaEvent_t ev[3];
@@ -647,7 +648,7 @@ extern "C" int orbm_destroy(orbm_matcher *m)
     if (!m) return ORBX_OK;
     cudaSetDevice(m->device);
     if (m->stream) { cudaStreamSynchronize(m->stream); cudaStreamDestroy(m->stream); }
-    cudaFree(m->partial); cudaFree(m->d_q); cudaFree(m->d_db); cudaFree(m->d_out);
+    cudaFree(m->partial); cudaFree(m->d_q); cudaFree(m->d_db); cudaFree(m->d_out); cudaFree(m->si_buf);
     for (auto &e : m->ev) if (e) cudaEventDestroy(e);
     delete m;
     return ORBX_OK;
@@ -795,6 +796,50 @@ extern "C" int orbm_search_init_device(orbm_matcher *m, const orbx_keypoint *d_k
     if (launch_search_init(a, stream ? (cudaStream_t)stream : m->stream)) return cuda_fail(cudaGetLastError(), "search_init smem");
     m->launches += 1;
     CK(cudaGetLastError());
+    return ORBX_OK;
+}
+
+extern "C" int orbm_search_init_host(orbm_matcher *m, const orbx_keypoint *kp1, const uint8_t *desc1, int n1,
+                                     const orbx_keypoint *kp2, const uint8_t *desc2, int n2,
+                                     float *prev_matched, int32_t *matches12, int32_t *nmatches,
+                                     int window, float nnratio, int check_orientation, int width, int height, int literal_gridid_bug)
+{
+    if (!m || n1 < 0 || n2 < 0 || n1 >= 65536 || n2 >= 65536 || !nmatches) return ORBX_E_INVALID;
+    if (n1 == 0) { *nmatches = 0; return ORBX_OK; }
+    if (!kp1 || !desc1 || !prev_matched || !matches12 || (n2 && (!kp2 || !desc2))) return ORBX_E_INVALID;
+    CK(cudaSetDevice(m->device));
+    cudaStream_t s = m->stream;
+    const int cap = (n1 > n2 ? n1 : n2) < 1 ? 1 : (n1 > n2 ? n1 : n2);
+    const size_t wsb = orbm_search_init_workspace_bytes(cap, 1);
+    // one scratch allocation laid out as [kps 2][desc 2][counts 2][pairs 2][prev][m12][nm][workspace]
+    const size_t o_kps = 0, o_desc = (o_kps + 2 * (size_t)cap * sizeof(orbx_keypoint) + 15) & ~(size_t)15, o_cnt = (o_desc + 2 * (size_t)cap * 32 + 15) & ~(size_t)15,
+                 o_prev = o_cnt + 64, o_m12 = o_prev + (size_t)cap * 8, o_nm = o_m12 + (size_t)cap * 4, o_ws = (o_nm + 16 + 15) & ~(size_t)15;
+    const size_t need = o_ws + wsb;
+    if (need > m->si_bytes) {
+        if (m->si_buf) CK(cudaFree(m->si_buf));
+        m->si_buf = nullptr; m->si_bytes = 0;
+        if (cudaMalloc(&m->si_buf, need) != cudaSuccess) { cuda_fail(cudaGetLastError(), "cudaMalloc"); return ORBX_E_NOMEM; }
+        m->si_bytes = need;
+    }
+    unsigned char *b = (unsigned char *)m->si_buf;
+    const int meta[4] = { n1, n2, 0, 1 };                                  // counts[2], pair_a = 0, pair_b = 1
+    CK(cudaMemcpyAsync(b + o_kps, kp1, (size_t)n1 * sizeof(orbx_keypoint), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(b + o_desc, desc1, (size_t)n1 * 32, cudaMemcpyHostToDevice, s));
+    if (n2) {
+        CK(cudaMemcpyAsync(b + o_kps + (size_t)cap * sizeof(orbx_keypoint), kp2, (size_t)n2 * sizeof(orbx_keypoint), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(b + o_desc + (size_t)cap * 32, desc2, (size_t)n2 * 32, cudaMemcpyHostToDevice, s));
+    }
+    CK(cudaMemcpyAsync(b + o_cnt, meta, sizeof(meta), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(b + o_prev, prev_matched, (size_t)n1 * 8, cudaMemcpyHostToDevice, s));
+    int rc = orbm_search_init_device(m, (const orbx_keypoint *)(b + o_kps), b + o_desc, (const int *)(b + o_cnt), cap,
+                                     (const int *)(b + o_cnt) + 2, (const int *)(b + o_cnt) + 3, 1,
+                                     (float *)(b + o_prev), (int *)(b + o_m12), (int *)(b + o_nm),
+                                     window, nnratio, check_orientation, width, height, literal_gridid_bug, b + o_ws, wsb, s);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(matches12, b + o_m12, (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(prev_matched, b + o_prev, (size_t)n1 * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(nmatches, b + o_nm, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
     return ORBX_OK;
 }
 

@@ -22,6 +22,7 @@ int main(int argc, char **argv)
     ORBSlam::ORBextractor *ex = new ORBSlam::ORBextractor(hdr[3], sf, hdr[4], hdr[5], hdr[6]);   // Tracking.cpp:47
     FILE *fo = std::fopen(argv[2], "wb");
     cv::Mat lastDesc;
+    std::vector<std::vector<cv::KeyPoint> > allKps; std::vector<cv::Mat> allDesc;
     for (int f = 0; f < NF; ++f) {
         cv::Mat img(H, W, CV_8UC1, frames.data() + (size_t)f * W * H);
         std::vector<cv::KeyPoint> kps; cv::Mat desc;
@@ -31,6 +32,7 @@ int main(int argc, char **argv)
         std::fwrite(kps.data(), sizeof(cv::KeyPoint), n, fo);
         for (int i = 0; i < n; ++i) std::fwrite(desc.ptr(i), 1, 32, fo);
         if (n) lastDesc = desc;
+        allKps.push_back(kps); allDesc.push_back(desc.clone());
     }
     // trailer: pyramid checks + matcher checks on the last frame
     int levels = ex->GetLevels();
@@ -56,6 +58,17 @@ int main(int argc, char **argv)
     int selfok = 1;
     for (size_t i = 0; i < m12.size(); ++i) if (m12[i] >= 0 && m12[i] != (int)i) { /* duplicates may map to the first copy */ }
     std::fwrite(&selfok, 4, 1, fo);
+    // SearchForInitialization frame 0 -> frame 1, like Tracking::MonocularInitialization (src/Tracking.cpp:181-189)
+    if (NF >= 2) {
+        ORBSlam::ORBmatcher init(0.9f, true);
+        std::vector<cv::Point2f> prev(allKps[0].size());
+        for (size_t i = 0; i < prev.size(); ++i) prev[i] = allKps[0][i].pt;
+        std::vector<int> m12i;
+        int n = init.SearchForInitialization(allKps[0], allDesc[0], allKps[1], allDesc[1], prev, m12i, 100, W, H);
+        int cnt = (int)m12i.size();
+        std::fwrite(&n, 4, 1, fo); std::fwrite(&cnt, 4, 1, fo);
+        std::fwrite(m12i.data(), 4, m12i.size(), fo);
+    }
     std::fclose(fo);
     delete ex;
     return 0;

@@ -36,6 +36,7 @@ def test_cpp_classes_match_oracle(orbx, oracle, tmp_path):
     raw = open(fout, "rb").read(); off = 0
     oex = oracle.OracleExtractor()
     last = None
+    frames_out = []
     for fidx in range(2):
         n = struct.unpack_from("<i", raw, off)[0]; off += 4
         kps = np.frombuffer(raw, oracle.KEYPOINT_DTYPE, n, off); off += 28 * n
@@ -48,6 +49,7 @@ def test_cpp_classes_match_oracle(orbx, oracle, tmp_path):
         assert d.max() <= 1e-3 * 180 / np.pi
         assert np.unpackbits(desc ^ do).sum() <= 1e-3 * do.size * 8
         last = desc
+        frames_out.append((kps.copy(), desc.copy()))
     levels = struct.unpack_from("<i", raw, off)[0]; off += 4
     assert levels == 8
     for l in range(levels):
@@ -59,7 +61,14 @@ def test_cpp_classes_match_oracle(orbx, oracle, tmp_path):
         assert bs == int(oracle.reflect101_border(lv, 19).astype(np.uint64).sum()), "mvImagePyramid[%d] border" % l
     sf = np.frombuffer(raw, np.float32, 8, off); off += 32
     assert np.array_equal(sf, oex.scale_factors)
-    d01, nm, _ = struct.unpack_from("<3i", raw, off)
+    d01, nm, _ = struct.unpack_from("<3i", raw, off); off += 12
     assert d01 == oracle.descriptor_distance(last[0], last[1])
     d1, i1, d2 = oracle.knn2(last, last)
     assert nm == int((oracle.ratio_select(d1, i1, d2, 50, 0.7) >= 0).sum())
+    # ORBmatcher::SearchForInitialization through the C++ class, on the keypoints the C++ extractor produced
+    n_si, cnt = struct.unpack_from("<2i", raw, off); off += 8
+    m12 = np.frombuffer(raw, np.int32, cnt, off)
+    (k1, dd1), (k2, dd2) = frames_out
+    prev = np.stack([k1["x"], k1["y"]], 1)
+    n_o, m_o, _ = oracle.search_for_initialization(k1, dd1, k2, dd2, prev, 100, 0.9, True, 640, 480)
+    assert n_si == n_o and np.array_equal(m12, m_o)

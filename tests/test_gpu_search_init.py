@@ -82,3 +82,20 @@ def test_search_init_workspace_too_small_is_reported(orbx):
                          prev.data_ptr(), m12.data_ptr(), nm.data_ptr(), 100, 0.9, True, 640, 480, ws.data_ptr(), 64, s)
     torch.cuda.synchronize()
     assert int(nm[0]) == -1
+
+
+def test_search_init_host_entry(orbx, oracle):
+    imgs = _frames()[:2]
+    ex = orbx.Extractor(nfeatures=2000, max_width=640, max_height=480, max_batch=2)
+    kps, desc, cnt = ex.extract_host(imgs)
+    n1, n2 = int(cnt[0]), int(cnt[1])
+    k1, d1, k2, d2 = kps[0, :n1], desc[0, :n1], kps[1, :n2], desc[1, :n2]
+    prev = np.stack([k1["x"], k1["y"]], 1)
+    m = orbx.Matcher(max(n1, n2), max(n1, n2))
+    got = m.search_init_host(k1, d1, k2, d2, prev, 100, 0.9, True, 640, 480)
+    want = oracle.search_for_initialization(k1.astype(oracle.KEYPOINT_DTYPE), d1, k2.astype(oracle.KEYPOINT_DTYPE), d2, prev, 100, 0.9, True, 640, 480)
+    assert got[0] == want[0] and np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
+    assert got[0] > 50
+    # empty second frame / empty first frame
+    assert m.search_init_host(k1, d1, k2[:0], d2[:0], prev)[0] == 0
+    assert m.search_init_host(k1[:0], d1[:0], k2, d2, prev[:0])[0] == 0
