@@ -79,7 +79,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -312,10 +312,48 @@ def run_ours(args):
     dom_name = STAGES[dom]
     nlaunch = {"level0": 1, "resize": NLEVELS - 1, "fast": 1, "octree": 1, "blur": NLEVELS, "describe": 1}[dom_name]
     achieved = algo[dom_name] * BATCH / (stage_ms[dom] * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):          # dram bytes of this stage from the committed ncu --set full capture (same workload)
+        tj = json.load(open(tpath))
+        if dom_name in tj["bytes_per_step"]:
+            traffic = tj["bytes_per_step"][dom_name] / max(1, tj["launches"][dom_name])
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
+                "traffic_source": "profiles/r01_traffic.json (ncu dram__bytes_read+write per launch)" if traffic else None,
+                "algorithmic_bytes_per_launch": algo[dom_name] * BATCH / nlaunch, "peak_source": peak_src,
+                "note": "extraction is integer-issue bound, not HBM bound (DESIGN.md section 4): the HBM fraction is reported for completeness; ncu instruction counts are in profiles/",
                 "launches_in_stage": nlaunch, "stage_ms": {n: float(m) for n, m in zip(STAGES, stage_ms)},
                 "whole_pipeline_frac": value / world * ALGO_BYTES_PER_FRAME / 1e9 / peaks["hbm_gbs"]}
+
+    # ---------------- SearchForInitialization on consecutive frame pairs ----------------
+    search_init = None
+    if not args.skip_match:
+        P = BATCH - 1
+        pa = torch.arange(0, P, dtype=torch.int32, device=dev); pb = pa + 1
+        prev0 = d_kps[:P, :, :2].contiguous(); prev = prev0.clone()
+        m12 = torch.empty((P, cap), dtype=torch.int32, device=dev); nm = torch.empty(P, dtype=torch.int32, device=dev)
+        msi = _lib.Matcher(cap, cap, local)
+        wsb = _lib.load().orbm_search_init_workspace_bytes(cap, P)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+
+        def si_step():
+            prev.copy_(prev0)
+            msi.search_init_device(d_kps.data_ptr(), d_desc.data_ptr(), d_cnt.data_ptr(), cap, pa.data_ptr(), pb.data_ptr(), P,
+                                   prev.data_ptr(), m12.data_ptr(), nm.data_ptr(), 100, 0.9, True, W, H, ws.data_ptr(), wsb, stream)
+        for _ in range(3):
+            si_step()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(K):
+            si_step()
+        s1.record(); barrier()
+        si_ms = max_over_ranks(s0.elapsed_time(s1)) / K
+        search_init = {"metric": "search_for_initialization_pairs_per_s", "value": world * P / (si_ms * 1e-3), "unit": "frame pairs/s",
+                       "ms_per_step": si_ms, "config": {"workload": "%d consecutive 640x480 frame pairs per GPU, window 100, ratio 0.9, rotation check" % P},
+                       "mean_matches": float(nm.float().mean().item())}
+        del ws
 
     match = None
     if not args.skip_match:
@@ -336,6 +374,8 @@ def run_ours(args):
                 "roofline": roofline, "clocks": clocks}
         if match is not None:
             line["match"] = match
+        if search_init is not None:
+            line["search_init"] = search_init
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
