@@ -54,8 +54,6 @@ k_fast_cells(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr,
     uint8_t *tile = mine;                                                     // [tile_rows][tp]
     uint8_t *score = mine + sm.off_score;                                     // [tile_rows - 4][sp]
     uint16_t *queue = reinterpret_cast<uint16_t *>(mine + sm.off_queue);      // phase A survivors
-    uint32_t *bm_ini = reinterpret_cast<uint32_t *>(mine + sm.off_bm);
-    uint32_t *bm_min = bm_ini + (sm.npix_max + 31) / 32;
     const int kTP = sm.tp, kSP = sm.sp;
 
     int level = 0;
@@ -75,147 +73,145 @@ k_fast_cells(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr,
     const int iw = cw - 6, ih = ch - 6;                // pixels FAST actually tests
     if (iw <= 0 || ih <= 0) { if (lane == 0) *count_out = 0; return; }
 
-    // ---- phase 0: stage the tile (aligned words; tile column 0 = the 4-byte aligned pixel at or left
-    //      of iniX, so cell column c lives at tile column c + xoff), clear the score map and bitmaps ----
-    const int xoff = iniX & 3;
+    // ---- phase 0: stage the tile with aligned 16-byte loads: tile column 0 is the 16-byte aligned pixel at
+    //      or left of iniX (rows are 64-byte aligned, the interior starts at byte 32), so cell column c lives
+    //      at tile column c + xoff.  Eight rows per warp pass (4 lanes x 16 B cover <= 64 px + 15 slack). ----
+    const int xoff = iniX & 15;
     {
         const uint8_t *img = pyr + L.base + (size_t)f * L.frame_stride + (size_t)(kPadY + iniY) * L.pitch + kPadX + (iniX - xoff);
-        const int wpr = (cw + xoff + 3) >> 2;               // words per tile row
-        uint32_t *t32 = reinterpret_cast<uint32_t *>(tile);
-        const int tpw = kTP >> 2;
-        if (wpr <= 16) {                                    // two rows per warp pass
-            const int half = lane >> 4, wx = lane & 15;
-            for (int r = half; r < ch; r += 2)
-                if (wx < wpr) t32[r * tpw + wx] = __ldg(reinterpret_cast<const uint32_t *>(img + (size_t)r * L.pitch) + wx);
-        } else {
-            for (int r = 0; r < ch; ++r)
-                if (lane < wpr) t32[r * tpw + lane] = __ldg(reinterpret_cast<const uint32_t *>(img + (size_t)r * L.pitch) + lane);
-        }
-        uint32_t *s32 = reinterpret_cast<uint32_t *>(score);
-        const int nwords = ((ih + 2) * kSP + 3) >> 2;
-        for (int i = lane; i < nwords; i += 32) s32[i] = 0;
-        const int nbm = (iw * ih + 31) >> 5;
-        for (int i = lane; i < nbm; i += 32) { bm_ini[i] = 0; bm_min[i] = 0; }
+        const int vpr = (cw + xoff + 15) >> 4;              // 16-byte vectors per tile row (<= kTP / 16)
+        const int sub = lane & 7, rr = lane >> 3;           // up to 8 vectors per row, 4 rows per pass
+        if (sub < vpr)
+            for (int r = rr; r < ch; r += 4)
+                *reinterpret_cast<uint4 *>(tile + r * kTP + sub * 16) = __ldg(reinterpret_cast<const uint4 *>(img + (size_t)r * L.pitch) + sub);
     }
-    __syncwarp();
-
+    const int nbm = (iw * ih + 31) >> 5;
     const int minTh = g.min_th, iniTh = g.ini_th;
-    const int lowTh = min(minTh, iniTh);
+    uint32_t *bm = reinterpret_cast<uint32_t *>(mine + sm.off_bm);
 
-    // ---- phase A: compass pre-test, lane = column.  Each lane collects its column's verdicts for
-    //      up to 32 rows in two bitmasks (3 instructions per row and polarity instead of a ballot +
-    //      popc + store per row), then the warp compacts them into the queue with one scan. ----
-    int nq = 0;
-    for (int x0 = 0; x0 < iw; x0 += 32) {
-        const int x = x0 + lane;
-        const bool inx = x < iw;
-        for (int yb = 0; yb < ih; yb += 32) {
-            const int rows = min(32, ih - yb);
-            const uint8_t *p = tile + (yb + 3) * kTP + 3 + xoff + (inx ? x : 0);
-            uint32_t mb = 0, md = 0, bit = 1;
+    // The reference calls cv::FAST(cell, iniThFAST) and, only if that returns nothing, cv::FAST(cell, minThFAST)
+    // (:766-773).  Same here: the whole detect-score-NMS pipeline runs at iniThFAST first (fewer compass
+    // survivors and corners than at minThFAST) and is repeated at minThFAST only for cells left empty.
+    bool found = false;
+#pragma unroll 1
+    for (int attempt = 0; attempt < 2 && !found; ++attempt) {
+        const int th = attempt == 0 ? iniTh : minTh;
+        {
+            uint32_t *s32 = reinterpret_cast<uint32_t *>(score);
+            const int nwords = ((ih + 2) * kSP + 3) >> 2;
+            for (int i = lane; i < nwords; i += 32) s32[i] = 0;
+            for (int i = lane; i < nbm; i += 32) bm[i] = 0;
+        }
+        __syncwarp();
+
+        // ---- phase A: compass pre-test, lane = column.  Each lane collects its column's verdicts for up to
+        //      32 rows in two bitmasks, then the warp compacts them into the queue with one scan. ----
+        int nq = 0;
+        for (int x0 = 0; x0 < iw; x0 += 32) {
+            const int x = x0 + lane;
+            const bool inx = x < iw;
+            for (int yb = 0; yb < ih; yb += 32) {
+                const int rows = min(32, ih - yb);
+                const uint8_t *p = tile + (yb + 3) * kTP + 3 + xoff + (inx ? x : 0);
+                uint32_t mb = 0, md = 0, bit = 1;
 #pragma unroll 4
-            for (int y = 0; y < rows; ++y, p += kTP, bit <<= 1) {
-                const int v = p[0];
-                const int n = p[3 * kTP], s = p[-3 * kTP], e = p[3], w = p[-3];
-                const int hiv = min(max(n, s), max(e, w)) - v;          // > t: a bright arc is possible
-                const int lov = v - max(min(n, s), min(e, w));          // > t: a dark arc is possible
-                mb |= hiv > lowTh ? bit : 0u;
-                md |= lov > lowTh ? bit : 0u;
+                for (int y = 0; y < rows; ++y, p += kTP, bit <<= 1) {
+                    const int v = p[0];
+                    const int n = p[3 * kTP], s = p[-3 * kTP], e = p[3], w = p[-3];
+                    const int hiv = min(max(n, s), max(e, w)) - v;          // > t: a bright arc is possible
+                    const int lov = v - max(min(n, s), min(e, w));          // > t: a dark arc is possible
+                    mb |= hiv > th ? bit : 0u;
+                    md |= lov > th ? bit : 0u;
+                }
+                if (!inx) { mb = 0; md = 0; }
+                uint32_t any = mb | md;
+                const int cnt = __popc(any);
+                int inc = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+                int pos = nq + inc - cnt;
+                while (any) {
+                    const int y = __ffs(any) - 1;
+                    any &= any - 1;
+                    // queue entry: x | y << 6 | bright << 12 | dark << 13   (x, y < 64)
+                    queue[pos++] = (uint16_t)(x | ((yb + y) << 6) | (((mb >> y) & 1u) << 12) | (((md >> y) & 1u) << 13));
+                }
+                nq += __shfl_sync(0xffffffffu, inc, 31);
             }
-            if (!inx) { mb = 0; md = 0; }
-            uint32_t any = mb | md;
-            const int cnt = __popc(any);
+        }
+        __syncwarp();
+
+        // ---- phase B: exact score of the candidate polarity ----
+        for (int i0 = 0; i0 < nq; i0 += 32) {
+            const int i = i0 + lane;
+            if (i < nq) {
+                const uint32_t ent = queue[i];
+                const int x = ent & 63, y = (ent >> 6) & 63;
+                const uint8_t *p = tile + (y + 3) * kTP + (x + 3 + xoff);
+                const int v = p[0];
+                int best = -512;
+                // first pass: the lane's own candidate polarity (bright: e = ring - v, dark: e = v - ring), so
+                // lanes of both kinds run the same code; second pass only for the rare both-polarity survivors
+                const int npol = ((ent >> 12) & 1) + ((ent >> 13) & 1);
+#pragma unroll 1
+                for (int pass = 0; pass < npol; ++pass) {
+                    const bool dark = pass == 1 || !(ent & 0x1000u);
+                    const int sgn = dark ? -1 : 1, off = dark ? v : -v;
+                    int e[16];
+                    e[0] = sgn * p[3 * kTP] + off;      e[1] = sgn * p[3 * kTP + 1] + off;  e[2] = sgn * p[2 * kTP + 2] + off;  e[3] = sgn * p[kTP + 3] + off;
+                    e[4] = sgn * p[3] + off;            e[5] = sgn * p[-kTP + 3] + off;     e[6] = sgn * p[-2 * kTP + 2] + off; e[7] = sgn * p[-3 * kTP + 1] + off;
+                    e[8] = sgn * p[-3 * kTP] + off;     e[9] = sgn * p[-3 * kTP - 1] + off; e[10] = sgn * p[-2 * kTP - 2] + off; e[11] = sgn * p[-kTP - 3] + off;
+                    e[12] = sgn * p[-3] + off;          e[13] = sgn * p[kTP - 3] + off;     e[14] = sgn * p[2 * kTP - 2] + off;  e[15] = sgn * p[3 * kTP - 1] + off;
+                    best = max(best, arc9_maxmin(e));
+                }
+                if (best > th)                            // corner at th; cornerScore = best - 1 >= th
+                    score[(y + 1) * kSP + (x + 1)] = (uint8_t)(best - 1);
+            }
+        }
+        __syncwarp();
+
+        // ---- phase C: strict 3x3 NMS inside the cell; walks the same queue (non-corners have score 0) ----
+        bool mine_any = false;
+        for (int i = lane; i < nq; i += 32) {
+            const uint32_t ent = queue[i];
+            const int x = ent & 63, y = (ent >> 6) & 63;
+            const uint8_t *q = score + (y + 1) * kSP + (x + 1);
+            const int s = q[0];
+            if (s == 0) continue;                         // every stored score is >= th >= 1
+            const int nmax = max3(max3((int)q[-kSP - 1], (int)q[-kSP], (int)q[-kSP + 1]), max3((int)q[-1], (int)q[1], (int)q[kSP - 1]),
+                                  max((int)q[kSP], (int)q[kSP + 1]));
+            if (s > nmax) {
+                const int idx = y * iw + x;
+                atomicOr(&bm[idx >> 5], 1u << (idx & 31));
+                mine_any = true;
+            }
+        }
+        found = __any_sync(0xffffffffu, mine_any);
+        __syncwarp();
+    }
+
+    // ---- phase D: ordered emission (row-major = ascending bit index) ----
+    uint32_t *slots = cell_slots + (size_t)f * g.slots_per_frame + L.slot_base + (size_t)c * L.cell_cap;
+    int base = 0;
+    if (found) {
+        for (int w0 = 0; w0 < nbm; w0 += 32) {
+            const int wi = w0 + lane;
+            uint32_t bits = wi < nbm ? bm[wi] : 0u;
+            const int cnt = __popc(bits);
             int inc = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-            int pos = nq + inc - cnt;
-            while (any) {
-                const int y = __ffs(any) - 1;
-                any &= any - 1;
-                // queue entry: x | y << 6 | bright << 12 | dark << 13   (x, y < 64)
-                queue[pos++] = (uint16_t)(x | ((yb + y) << 6) | (((mb >> y) & 1u) << 12) | (((md >> y) & 1u) << 13));
+            int pos = base + inc - cnt;
+            while (bits) {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                const int idx = wi * 32 + b;
+                const int y = idx / iw, x = idx - y * iw;
+                // keypoint in level coordinates relative to (16,16): cell pixel (x+3, y+3) + (j*wCell, i*hCell)
+                slots[pos++] = pack_cand(x + 3 + cj * L.wCell, y + 3 + ci * L.hCell, score[(y + 1) * kSP + (x + 1)]);
             }
-            nq += __shfl_sync(0xffffffffu, inc, 31);
+            base += __shfl_sync(0xffffffffu, inc, 31);
         }
-    }
-    __syncwarp();
-
-    // ---- phase B: exact score of the candidate polarity ----
-    for (int i0 = 0; i0 < nq; i0 += 32) {
-        const int i = i0 + lane;
-        if (i < nq) {
-            const uint32_t ent = queue[i];
-            const int x = ent & 63, y = (ent >> 6) & 63;
-            const uint8_t *p = tile + (y + 3) * kTP + (x + 3 + xoff);
-            const int v = p[0];
-            int best = -512;
-            // first pass: the lane's own candidate polarity (bright: e = ring - v, dark: e = v - ring), so
-            // lanes of both kinds run the same code; second pass only for the rare both-polarity survivors
-            const int npol = ((ent >> 12) & 1) + ((ent >> 13) & 1);
-#pragma unroll 1
-            for (int pass = 0; pass < npol; ++pass) {
-                const bool dark = pass == 1 || !(ent & 0x1000u);
-                const int sgn = dark ? -1 : 1, off = dark ? v : -v;
-                int e[16];
-                e[0] = sgn * p[3 * kTP] + off;      e[1] = sgn * p[3 * kTP + 1] + off;  e[2] = sgn * p[2 * kTP + 2] + off;  e[3] = sgn * p[kTP + 3] + off;
-                e[4] = sgn * p[3] + off;            e[5] = sgn * p[-kTP + 3] + off;     e[6] = sgn * p[-2 * kTP + 2] + off; e[7] = sgn * p[-3 * kTP + 1] + off;
-                e[8] = sgn * p[-3 * kTP] + off;     e[9] = sgn * p[-3 * kTP - 1] + off; e[10] = sgn * p[-2 * kTP - 2] + off; e[11] = sgn * p[-kTP - 3] + off;
-                e[12] = sgn * p[-3] + off;          e[13] = sgn * p[kTP - 3] + off;     e[14] = sgn * p[2 * kTP - 2] + off;  e[15] = sgn * p[3 * kTP - 1] + off;
-                best = max(best, arc9_maxmin(e));
-            }
-            if (best > lowTh)                         // corner at lowTh; cornerScore = best - 1 >= lowTh
-                score[(y + 1) * kSP + (x + 1)] = (uint8_t)(best - 1);
-        }
-    }
-    __syncwarp();
-
-    // ---- phase C: NMS at both thresholds; walks the same queue (non-corners have score 0) ----
-    for (int i = lane; i < nq; i += 32) {
-        const uint32_t ent = queue[i];
-        const int x = ent & 63, y = (ent >> 6) & 63;
-        const uint8_t *q = score + (y + 1) * kSP + (x + 1);
-        const int s = q[0];
-        if (s < lowTh) continue;
-        int nmax_min = 0, nmax_ini = 0;
-#pragma unroll
-        for (int dy = -1; dy <= 1; ++dy)
-#pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) {
-                if (dx == 0 && dy == 0) continue;
-                const int n = q[dy * kSP + dx];
-                nmax_min = max(nmax_min, n >= minTh ? n : 0);
-                nmax_ini = max(nmax_ini, n >= iniTh ? n : 0);
-            }
-        const int idx = y * iw + x;
-        if (s >= minTh && s > nmax_min) atomicOr(&bm_min[idx >> 5], 1u << (idx & 31));
-        if (s >= iniTh && s > nmax_ini) atomicOr(&bm_ini[idx >> 5], 1u << (idx & 31));
-    }
-    __syncwarp();
-
-    // ---- phase D: retry rule + ordered emission (row-major = ascending bit index) ----
-    const int nbm = (iw * ih + 31) >> 5;
-    bool any = false;
-    for (int i = lane; i < nbm; i += 32) any |= (bm_ini[i] != 0);
-    const uint32_t *bm = __any_sync(0xffffffffu, any) ? bm_ini : bm_min;
-    uint32_t *slots = cell_slots + (size_t)f * g.slots_per_frame + L.slot_base + (size_t)c * L.cell_cap;
-    int base = 0;
-    for (int w0 = 0; w0 < nbm; w0 += 32) {
-        const int wi = w0 + lane;
-        uint32_t bits = wi < nbm ? bm[wi] : 0u;
-        const int cnt = __popc(bits);
-        int inc = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-        int pos = base + inc - cnt;
-        while (bits) {
-            const int b = __ffs(bits) - 1;
-            bits &= bits - 1;
-            const int idx = wi * 32 + b;
-            const int y = idx / iw, x = idx - y * iw;
-            // keypoint in level coordinates relative to (16,16): cell pixel (x+3, y+3) + (j*wCell, i*hCell)
-            slots[pos++] = pack_cand(x + 3 + cj * L.wCell, y + 3 + ci * L.hCell, score[(y + 1) * kSP + (x + 1)]);
-        }
-        base += __shfl_sync(0xffffffffu, inc, 31);
     }
     if (lane == 0) *count_out = base;
 }
@@ -226,13 +222,13 @@ void launch_fast(const Geo &g, const DevBuffers &b, int nframes, cudaStream_t s)
     for (int l = 0; l < g.nlevels; ++l) if (g.lv[l].nCols > 0) { mw = mw > g.lv[l].wCell ? mw : g.lv[l].wCell; mh = mh > g.lv[l].hCell ? mh : g.lv[l].hCell; }
     auto up16 = [](int v) { return (v + 15) / 16 * 16; };
     FastSmem sm;
-    sm.tp = (mw + 6 + 3 + 3) / 4 * 4; sm.sp = (mw + 2 + 3) / 4 * 4; sm.tile_rows = mh + 6;
+    sm.tp = (mw + 6 + 15 + 15) / 16 * 16; sm.sp = (mw + 2 + 3) / 4 * 4; sm.tile_rows = mh + 6;
     sm.npix_max = (mw * mh + 1) / 2 * 2;
     sm.off_score = up16(sm.tile_rows * sm.tp);
     sm.off_queue = sm.off_score + up16((mh + 2) * sm.sp);
     sm.off_corner = 0;
     sm.off_bm = sm.off_queue + up16(sm.npix_max * 2);
-    sm.per_warp = sm.off_bm + up16(2 * ((sm.npix_max + 31) / 32) * 4);
+    sm.per_warp = sm.off_bm + up16(((sm.npix_max + 31) / 32) * 4);
     const size_t bytes = (size_t)sm.per_warp * kFastWarps;
     static size_t configured = 0;
     if (bytes > 48 * 1024 && bytes > configured) {
