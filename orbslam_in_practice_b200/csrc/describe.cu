@@ -214,7 +214,9 @@ k_describe(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, const
         // ---- rotated BRIEF: lane i produces descriptor byte i from its 16 pattern points ----
         const float factorPI = (float)(3.14159265358979323846 / (double)180.f);
         const float ang = __fmul_rn(angle, factorPI);
-        const float a = (float)cos((double)ang), b = (float)sin((double)ang);
+        double sd, cd;
+        sincos((double)ang, &sd, &cd);                       // one range reduction for both
+        const float a = (float)cd, b = (float)sd;
         __syncwarp();
         const uint8_t *pc = reinterpret_cast<const uint8_t *>(patch) + kPatchR * (kPatchWords * 4) + (x - xa);   // patch centre
         int val = 0;
