@@ -95,8 +95,11 @@ int orbx_extract_device(orbx_extractor *ex, const uint8_t *d_imgs, size_t row_pi
                         int width, int height, int nframes,
                         orbx_keypoint *d_kps, uint8_t *d_desc, int32_t *d_counts, void *stream);
 
-/* Enable (1) / disable (0) writing the 19-px reflect-101 border of the pyramid levels.  The
- * extractor itself never reads it; it exists for consumers of mvImagePyramid.  Default: 1. */
+/* Pyramid border policy.  The extractor's own kernels read at most 4 px outside a level, and that much
+ * reflect-101 border is always written.  The full 19-px border of the reference's mvImagePyramid
+ * (src/ORBextractor.cpp:1086-1092) exists for outside consumers only: by default (0, lazy) it is
+ * materialised by orbx_download_level(border = 19) for the level/frame that is downloaded; with 1 (eager)
+ * every extract call writes it for all levels and frames on the device. */
 int orbx_set_pyramid_border(orbx_extractor *ex, int enabled);
 
 /* --- stage access of the LAST extract call (synchronous; for mvImagePyramid and parity tests) --- */

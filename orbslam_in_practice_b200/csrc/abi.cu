@@ -257,7 +257,7 @@ extern "C" int orbx_create(const orbx_params *p, int max_width, int max_height, 
     orbx_extractor *ex = new (std::nothrow) orbx_extractor();
     if (!ex) return ORBX_E_NOMEM;
     ex->params = *p; ex->device = device; ex->max_w = max_width; ex->max_h = max_height; ex->max_batch = max_batch;
-    ex->launches = 0; ex->last_frames = 0; ex->border_on = 1; ex->profiling = 0; ex->prof_calls = 0;
+    ex->launches = 0; ex->last_frames = 0; ex->border_on = 0; ex->profiling = 0; ex->prof_calls = 0;
     for (auto &set : ex->ev) for (auto &e : set) e = nullptr;
     std::memset(&ex->buf, 0, sizeof(ex->buf));
     ex->stream = ex->stream2 = ex->s_h2d = ex->s_d2h = nullptr; ex->s_aux[0] = ex->s_aux[1] = nullptr; ex->fork_slot = 0;
@@ -496,7 +496,7 @@ extern "C" int orbx_level_dims(const orbx_extractor *ex, int level, int *width, 
 extern "C" int orbx_download_level(orbx_extractor *ex, int frame, int level, int blurred, int border, uint8_t *dst, size_t dst_pitch)
 {
     if (!ex || !dst || level < 0 || level >= ex->params.nlevels || frame < 0 || frame >= ex->last_frames) return ORBX_E_INVALID;
-    if (border != 0 && (border != kBorder || blurred || !ex->border_on)) return ORBX_E_INVALID;
+    if (border != 0 && (border != kBorder || blurred)) return ORBX_E_INVALID;
     CK(cudaSetDevice(ex->device));
     const LevelGeom &L = ex->geo.lv[level];
     const size_t w = (size_t)L.w + 2 * border, h = (size_t)L.h + 2 * border;
@@ -505,6 +505,13 @@ extern "C" int orbx_download_level(orbx_extractor *ex, int frame, int level, int
     if (blurred) {
         CK(cudaMemcpy2D(dst, dst_pitch, ex->buf.blur + L.blur_base + (size_t)frame * L.blur_frame_stride, L.blur_pitch, w, h, cudaMemcpyDeviceToHost));
     } else {
+        // lazy mode (default): the hot path writes only the 4-px border its kernels read; the full 19-px
+        // reflect-101 border of mvImagePyramid is materialised here, when somebody actually asks for it
+        if (border && !ex->border_on) {
+            launch_fill_border(ex->geo, ex->buf, level, frame, ex->stream);
+            ex->launches += 1;
+            CK(cudaStreamSynchronize(ex->stream));
+        }
         const uint8_t *src = ex->buf.pyr + L.base + (size_t)frame * L.frame_stride + (size_t)(kPadY - border) * L.pitch + kPadX - border;
         CK(cudaMemcpy2D(dst, dst_pitch, src, L.pitch, w, h, cudaMemcpyDeviceToHost));
     }

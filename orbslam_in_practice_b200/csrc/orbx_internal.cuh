@@ -79,6 +79,7 @@ struct DevBuffers {
 // kernels (defined in the .cu files)
 void launch_level0(const Geo &g, const DevBuffers &b, const uint8_t *d_imgs, size_t pitch, size_t fstride, int nframes, cudaStream_t s);
 void launch_resize(const Geo &g, const DevBuffers &b, int level, int nframes, cudaStream_t s);
+void launch_fill_border(const Geo &g, const DevBuffers &b, int level, int frame, cudaStream_t s);
 void launch_fast(const Geo &g, const DevBuffers &b, int nframes, cudaStream_t s);
 void launch_octree(const Geo &g, const DevBuffers &b, int nframes, int smem_bytes, cudaStream_t s);
 void launch_blur(const Geo &g, const DevBuffers &b, int nframes, cudaStream_t s);

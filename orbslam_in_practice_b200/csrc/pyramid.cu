@@ -153,6 +153,23 @@ k_resize(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr_src, uin
     }
 }
 
+// copyMakeBorder(REFLECT_101) of one level of one frame, on demand (orbx_download_level with border = 19)
+__global__ void k_fill_border(const __grid_constant__ Geo g, uint8_t *__restrict__ pyr, int level, int frame)
+{
+    const LevelGeom &L = g.lv[level];
+    const int X = blockIdx.x * blockDim.x + threadIdx.x - kBorder, Y = blockIdx.y * blockDim.y + threadIdx.y - kBorder;
+    if (X >= L.w + kBorder || Y >= L.h + kBorder) return;
+    if (X >= 0 && X < L.w && Y >= 0 && Y < L.h) return;                  // interior stays as it is
+    uint8_t *img = pyr + L.base + (size_t)frame * L.frame_stride + (size_t)kPadY * L.pitch + kPadX;
+    img[(ptrdiff_t)Y * L.pitch + X] = img[(size_t)reflect101(Y, L.h) * L.pitch + reflect101(X, L.w)];
+}
+
+void launch_fill_border(const Geo &g, const DevBuffers &b, int level, int frame, cudaStream_t s)
+{
+    dim3 blk(32, 8), grd((g.lv[level].w + 2 * kBorder + 31) / 32, (g.lv[level].h + 2 * kBorder + 7) / 8);
+    k_fill_border<<<grd, blk, 0, s>>>(g, b.pyr, level, frame);
+}
+
 void launch_level0(const Geo &g, const DevBuffers &b, const uint8_t *d_imgs, size_t pitch, size_t fstride, int nframes, cudaStream_t s)
 {
     const int B = g.border_on ? kBorder : kMinBlurBorder;
