@@ -37,6 +37,7 @@ W, H, NFEAT, NLEVELS, SCALE, INI_TH, MIN_TH = 640, 480, 1000, 8, 1.2, 20, 7
 BATCH = 256
 KNN_NDB, KNN_NQ = 1_000_000, 100_000
 ALGO_BYTES_PER_FRAME = 1_010_532          # input + pyramid levels 1..7 + 1000 x 60 B
+WORKLOAD_DESC = ""
 STAGES = ["level0", "resize", "fast", "octree", "blur", "describe"]
 
 
@@ -60,8 +61,8 @@ def stage_algo_bytes():
     return {
         "level0": 2 * px[0],                               # read input, write level 0
         "resize": sum(px[l - 1] + px[l] for l in range(1, NLEVELS)),   # read l-1, write l
-        "fast": tot + 4 * 8000,                            # read every level once, write ~candidates
-        "octree": 8000 * 4 * 2 + NFEAT * 4,                # read candidates, write survivors
+        "fast": tot + 4 * 8 * NFEAT,                       # read every level once, write ~8x nfeatures candidates
+        "octree": 8 * NFEAT * 4 * 2 + NFEAT * 4,           # read candidates, write survivors
         "blur": 2 * tot,                                   # read level, write blurred level
         "describe": NFEAT * (749 + 512 + 60),              # patch reads + sample reads + outputs
     }
@@ -234,7 +235,7 @@ def run_ours(args):
         return float(t.item())
 
     # ---------------- extraction ----------------
-    nuniq = 32                                       # distinct synthetic frames, tiled to the batch
+    nuniq = 32 if W * H <= 1 << 20 else 4            # distinct synthetic frames, tiled to the batch
     base = synth_batch(range(rank * nuniq, rank * nuniq + nuniq), W, H)
     frames_np = np.ascontiguousarray(np.concatenate([base] * (BATCH // nuniq)))
     ex = _lib.Extractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, W, H, BATCH, local)
@@ -314,7 +315,7 @@ def run_ours(args):
     achieved = algo[dom_name] * BATCH / (stage_ms[dom] * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tpath):          # dram bytes of this stage from the committed ncu --set full capture (same workload)
+    if os.path.exists(tpath) and args.workload == "vga" and BATCH == 256:          # dram bytes of this stage from the committed ncu --set full capture (same workload)
         tj = json.load(open(tpath))
         if dom_name in tj["bytes_per_step"]:
             traffic = tj["bytes_per_step"][dom_name] / max(1, tj["launches"][dom_name])
@@ -364,7 +365,7 @@ def run_ours(args):
         line = {"metric": "orb_extract_frames_per_s", "value": value, "unit": "frames/s", "n_gpus": world, "steps": K,
                 "warmup": Wm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8", "data": "synthetic",
-                "config": {"workload": "256x 640x480 frames per GPU, nfeatures=1000, scale 1.2, 8 levels, FAST 20/7 (BASELINE configs[1])",
+                "config": {"workload": WORKLOAD_DESC,
                            "frames_per_gpu": BATCH, "keypoints_per_step_rank0": kp_total,
                            "l2": "per-step working set (inputs 79 MB + pyramid/blur 0.6 GB) exceeds the 126 MB L2; no flush needed",
                            "parallelism": "frames batch-sharded, no collective"},
@@ -436,6 +437,13 @@ def run_match(args, _lib, torch, dist, dev, world, rank, local, stream, K, barri
     return match
 
 
+WORKLOADS = {   # name: (W, H, nfeatures, frames per GPU, description)  -- BASELINE.json configs[1] / [2] / [4]
+    "vga": (640, 480, 1000, 256, "256x 640x480 frames per GPU, nfeatures=1000, scale 1.2, 8 levels, FAST 20/7 (BASELINE configs[1])"),
+    "kitti": (1241, 376, 2000, 128, "128x 1241x376 frames per GPU (64 stereo pairs), nfeatures=2000 per image (BASELINE configs[2])"),
+    "4k": (3840, 2160, 8000, 128, "128x 3840x2160 frames per GPU (1024 over 8 GPUs), nfeatures=8000 (BASELINE configs[4])"),
+}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -444,7 +452,17 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: no cpu_baseline leg")
     ap.add_argument("--skip-match", action="store_true", help="profiling runs: no Hamming kNN leg")
+    ap.add_argument("--workload", default="vga", choices=sorted(WORKLOADS),
+                    help="vga = the headline config (default); kitti / 4k = the other BASELINE configs (run by hand, results in profiles/)")
+    ap.add_argument("--frames", type=int, default=0, help="override frames per GPU")
     args = ap.parse_args()
+    global W, H, NFEAT, BATCH, ALGO_BYTES_PER_FRAME, WORKLOAD_DESC
+    W, H, NFEAT, BATCH, WORKLOAD_DESC = WORKLOADS[args.workload]
+    if args.frames:
+        BATCH = args.frames
+    if args.workload != "vga":
+        args.skip_match = True          # the kNN / SearchForInitialization legs are measured on the headline config only
+    ALGO_BYTES_PER_FRAME = W * H + sum(w * h for w, h in level_sizes()[1:]) + NFEAT * 60
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -20,8 +20,8 @@
 
 namespace orbx {
 
-constexpr int kOctThreads = 256;
-constexpr int kOctWarps = kOctThreads / 32;
+constexpr int kOctMaxThreads = 1024;          // block size is chosen per geometry: 256 (VGA-sized problems) or 1024 (4K)
+constexpr int kOctMaxWarps = kOctMaxThreads / 32;
 
 struct __align__(16) Node {
     short x0, y0, x1, y1;
@@ -29,8 +29,8 @@ struct __align__(16) Node {
 };
 
 struct OctShared {
-    int warp_i[kOctWarps + 1];
-    uint4 warp_v[kOctWarps + 1];
+    int warp_i[kOctMaxWarps + 1];
+    uint4 warp_v[kOctMaxWarps + 1];
     int size, n, nsplit, C, U, nToExpand, J, pending;
 };
 
@@ -43,6 +43,7 @@ __device__ __forceinline__ int warp_incl_scan(int v)
 }
 
 // exclusive scan of one int per thread over the block; returns exclusive prefix, total via ref
+template <int NW>
 __device__ __forceinline__ int block_excl_scan(int v, OctShared &S, int &total)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -51,7 +52,7 @@ __device__ __forceinline__ int block_excl_scan(int v, OctShared &S, int &total)
     __syncthreads();
     int off = 0, tot = 0;
 #pragma unroll
-    for (int w = 0; w < kOctWarps; ++w) { const int t = S.warp_i[w]; if (w < warp) off += t; tot += t; }
+    for (int w = 0; w < NW; ++w) { const int t = S.warp_i[w]; if (w < warp) off += t; tot += t; }
     __syncthreads();
     total = tot;
     return off + inc - v;
@@ -59,6 +60,7 @@ __device__ __forceinline__ int block_excl_scan(int v, OctShared &S, int &total)
 
 __device__ __forceinline__ uint4 add4(uint4 a, uint4 b) { return make_uint4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
+template <int NW>
 __device__ __forceinline__ uint4 block_excl_scan4(uint4 v, OctShared &S, uint4 &total)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -74,7 +76,7 @@ __device__ __forceinline__ uint4 block_excl_scan4(uint4 v, OctShared &S, uint4 &
     __syncthreads();
     uint4 off = make_uint4(0, 0, 0, 0), tot = off;
 #pragma unroll
-    for (int w = 0; w < kOctWarps; ++w) { const uint4 t = S.warp_v[w]; if (w < warp) off = add4(off, t); tot = add4(tot, t); }
+    for (int w = 0; w < NW; ++w) { const uint4 t = S.warp_v[w]; if (w < warp) off = add4(off, t); tot = add4(tot, t); }
     __syncthreads();
     total = tot;
     return make_uint4(off.x + inc.x - v.x, off.y + inc.y - v.y, off.z + inc.z - v.z, off.w + inc.w - v.w);
@@ -90,6 +92,7 @@ __device__ __forceinline__ int quadrant(uint32_t key, const Node &nd)
 
 __device__ __forceinline__ uint32_t comp(const uint4 &v, int q) { return q == 0 ? v.x : q == 1 ? v.y : q == 2 ? v.z : v.w; }
 
+template <int kOctThreads>
 __global__ void __launch_bounds__(kOctThreads)
 k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, const uint32_t *__restrict__ cell_slots,
          uint32_t *keysA_all, uint32_t *keysB_all, uint16_t *nodeA_all, uint16_t *nodeB_all, uint4 *scanE_all,
@@ -99,6 +102,7 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
     __shared__ OctShared S;
 
     const int level = blockIdx.x, f = blockIdx.y + g.frame0, tid = threadIdx.x;
+    constexpr int kOctWarps = kOctThreads / 32;
     const LevelGeom &L = g.lv[level];
     const int NC = L.node_cap;
     // dynamic shared memory carve-up (sized by the largest level's node_cap)
@@ -131,7 +135,7 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
             const int c = base + tid;
             const int v = c < nCells ? ccount[c] : 0;
             int tot;
-            const int ex = block_excl_scan(v, S, tot);
+            const int ex = block_excl_scan<kOctWarps>(v, S, tot);
             if (c < nCells) celloff[c] = carry + ex;
             carry += tot;
         }
@@ -164,7 +168,7 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
                     flag = (ri == r);
                 }
                 int tot;
-                const int ex = block_excl_scan(flag, S, tot);
+                const int ex = block_excl_scan<kOctWarps>(flag, S, tot);
                 if (flag) { kA[placed + carry + ex] = key; nA[placed + carry + ex] = (uint16_t)nroots; }
                 carry += tot;
             }
@@ -204,7 +208,7 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
                     }
                 }
                 uint4 tot;
-                const uint4 ex = block_excl_scan4(c, S, tot);
+                const uint4 ex = block_excl_scan4<kOctWarps>(c, S, tot);
                 if (p < n) E[p] = add4(carry, ex);
                 carry = add4(carry, tot);
             }
@@ -231,7 +235,7 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
                 const int gi = base + tid;
                 const int fl = gi < size ? (nodes[gi].count > 1) : 0;
                 int tot;
-                const int ex = block_excl_scan(fl, S, tot);
+                const int ex = block_excl_scan<kOctWarps>(fl, S, tot);
                 if (gi < size) { split[gi] = (unsigned char)fl; rank[gi] = carry + ex; }
                 carry += tot;
             }
@@ -262,7 +266,7 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
                 const int r = base + tid;
                 const int v = r < P ? arr[r] : 0;
                 int tot;
-                const int ex = block_excl_scan(v, S, tot);
+                const int ex = block_excl_scan<kOctWarps>(v, S, tot);
                 if (r < P && size + carry + ex + v >= N) atomicMin(&S.J, r);   // :684 break
                 carry += tot;
             }
@@ -282,7 +286,7 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
                 const int r = base + tid;
                 const int v = r < nsplit ? arr[r] : 0;
                 int tot;
-                const int ex = block_excl_scan(v, S, tot);
+                const int ex = block_excl_scan<kOctWarps>(v, S, tot);
                 if (r < nsplit) arr[r] = carry + ex;
                 carry += tot;
             }
@@ -292,7 +296,7 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
                 const int gi = base + tid;
                 const int fl = gi < size ? !split[gi] : 0;
                 int tot;
-                const int ex = block_excl_scan(fl, S, tot);
+                const int ex = block_excl_scan<kOctWarps>(fl, S, tot);
                 if (gi < size) ubase[gi] = ucarry + ex;
                 ucarry += tot;
             }
@@ -385,15 +389,23 @@ int octree_smem_bytes(const Geo &g)
 
 int octree_configure(int smem_bytes)
 {
-    cudaError_t e = cudaFuncSetAttribute(k_octree, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(k_octree<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_octree<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     return e == cudaSuccess ? 0 : -1;
 }
 
 void launch_octree(const Geo &g, const DevBuffers &b, int nframes, int smem_bytes, cudaStream_t s)
 {
     dim3 grd(g.nlevels, nframes);
-    k_octree<<<grd, kOctThreads, smem_bytes, s>>>(g, b.cell_count, b.cell_slots, b.keysA, b.keysB, b.nodeA, b.nodeB,
-                                                  b.scanE, b.ncand, b.kept, b.nkept);
+    // candidate counts scale with the level area: large levels (4K) get 1024 threads per problem
+    int big = 0;
+    for (int l = 0; l < g.nlevels; ++l) big = big > g.lv[l].regionW * g.lv[l].regionH ? big : g.lv[l].regionW * g.lv[l].regionH;
+    if (big > 1500000)
+        k_octree<1024><<<grd, 1024, smem_bytes, s>>>(g, b.cell_count, b.cell_slots, b.keysA, b.keysB, b.nodeA, b.nodeB,
+                                                     b.scanE, b.ncand, b.kept, b.nkept);
+    else
+        k_octree<256><<<grd, 256, smem_bytes, s>>>(g, b.cell_count, b.cell_slots, b.keysA, b.keysB, b.nodeA, b.nodeB,
+                                                   b.scanE, b.ncand, b.kept, b.nkept);
 }
 
 } // namespace orbx
