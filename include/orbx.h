@@ -9,6 +9,7 @@
  *   orbx_create / orbx_tables        ORBextractor::ORBextractor        include/ORBextractor.h:35-36, src/ORBextractor.cpp:360-420
  *                                    GetLevels/GetScaleFactor(s)/...   include/ORBextractor.h:47-69
  *   orbx_extract_host/_device        ORBextractor::operator()          include/ORBextractor.h:43-45, src/ORBextractor.cpp:1001-1065
+ *   orbx_set_input_format            cv::cvtColor(..2GRAY) before the extractor   src/Tracking.cpp:57-70
  *   orbx_download_level              mvImagePyramid (public member)    include/ORBextractor.h:71, src/ORBextractor.cpp:1071-1096
  *   orbm_hamming_pairs_host          ORBmatcher::DescriptorDistance    include/ORBmatcher.h:19, src/ORBmatcher.cpp:128-144
  *   orbm_knn2_* / orbm_ratio_select  best-2 scan + acceptance          src/ORBmatcher.cpp:37-67
@@ -94,6 +95,12 @@ int orbx_extract_host(orbx_extractor *ex, const uint8_t *imgs, size_t row_pitch,
 int orbx_extract_device(orbx_extractor *ex, const uint8_t *d_imgs, size_t row_pitch, size_t frame_stride,
                         int width, int height, int nframes,
                         orbx_keypoint *d_kps, uint8_t *d_desc, int32_t *d_counts, void *stream);
+
+/* Input pixel format of the following extract calls: channels = 1 (gray, default), 3 or 4 interleaved 8-bit
+ * channels; rgb_order = 0 for BGR(A), 1 for RGB(A).  Colour input is converted to gray inside the level-0 kernel with
+ * OpenCV's 8U fixed point (R*9798 + G*19235 + B*3735 + 16384) >> 15, replacing the cv::cvtColor call in front of the
+ * extractor (src/Tracking.cpp:57-70).  row_pitch / frame_stride of the extract calls stay in bytes. */
+int orbx_set_input_format(orbx_extractor *ex, int channels, int rgb_order);
 
 /* Pyramid border policy.  The extractor's own kernels read at most 4 px outside a level, and that much
  * reflect-101 border is always written.  The full 19-px border of the reference's mvImagePyramid

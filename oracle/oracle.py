@@ -72,6 +72,7 @@ def lib():
     L.orbo_ic_angle.restype = f32
     L.orbo_ic_angle.argtypes = [vp, sz, i32, i32, vp, C.POINTER(i32), C.POINTER(i32)]
     L.orbo_orb_descriptor.argtypes = [vp, sz, i32, i32, f32, vp]
+    L.orbo_cvt_gray_u8.argtypes = [vp, i32, i32, sz, i32, i32, vp, sz]
     L.orbo_descriptor_distance.restype = i32
     L.orbo_descriptor_distance.argtypes = [vp, vp]
     L.orbo_knn2.argtypes = [vp, i32, vp, i32, i32, vp, vp, vp]
@@ -225,6 +226,14 @@ def orb_descriptor(blurred, x, y, angle_deg):
     d = np.zeros(32, np.uint8)
     lib().orbo_orb_descriptor(_p(blurred), blurred.strides[0], x, y, float(angle_deg), _p(d))
     return d
+
+
+def cvt_gray(img, rgb_order=False):
+    img = _u8(img)
+    h, w, c = img.shape
+    dst = np.zeros((h, w), np.uint8)
+    lib().orbo_cvt_gray_u8(_p(img), w, h, img.strides[0], c, int(rgb_order), _p(dst), w)
+    return dst
 
 
 def descriptor_distance(a, b):

@@ -766,6 +766,19 @@ int orbo_level_candidates(const orbo_extractor *ex, int level, const orbo_cand *
 int orbo_level_kept(const orbo_extractor *ex, int level, const orbo_cand **c) { *c = ex->kept[level]; return ex->nkept[level]; }
 int orbo_level_retries(const orbo_extractor *ex, int level) { return ex->retries[level]; }
 
+void orbo_cvt_gray_u8(const uint8_t *src, int w, int h, size_t spitch, int channels, int rgb_order, uint8_t *dst, size_t dpitch)
+{
+    for (int y = 0; y < h; ++y) {
+        const uint8_t *S = src + (size_t)y * spitch;
+        uint8_t *D = dst + (size_t)y * dpitch;
+        for (int x = 0; x < w; ++x) {
+            const uint8_t *p = S + (size_t)x * channels;
+            const int r = rgb_order ? p[0] : p[2], g = p[1], b = rgb_order ? p[2] : p[0];
+            D[x] = (uint8_t)((r * 9798 + g * 19235 + b * 3735 + 16384) >> 15);
+        }
+    }
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* Matcher                                                                                    */
 /* ------------------------------------------------------------------------------------------ */

@@ -90,6 +90,10 @@ float orbo_ic_angle(const uint8_t *img, size_t pitch, int x, int y, const int32_
 /* computeOrbDescriptor (ORBextractor.cpp:58-97) */
 void orbo_orb_descriptor(const uint8_t *blurred, size_t pitch, int x, int y, float angle_deg, uint8_t *desc32);
 
+/* cv::cvtColor(RGB/BGR/RGBA/BGRA -> GRAY) for 8U, the step before the extractor (src/Tracking.cpp:57-70).
+ * OpenCV 4.13.0 fixed point: (R*9798 + G*19235 + B*3735 + 16384) >> 15 (pinned against cv2; the 2.4/3.x era used 14 bits). */
+void orbo_cvt_gray_u8(const uint8_t *src, int w, int h, size_t spitch, int channels, int rgb_order, uint8_t *dst, size_t dpitch);
+
 /* ---- matcher ---- */
 /* ORBmatcher::DescriptorDistance, ORBmatcher.cpp:128-144 (SWAR popcount on 8 x int32) */
 int orbo_descriptor_distance(const uint8_t *a, const uint8_t *b);

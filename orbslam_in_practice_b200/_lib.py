@@ -21,7 +21,7 @@ CAND_DTYPE = np.dtype([("x", "<i2"), ("y", "<i2"), ("score", "<i4")])
 ABI_SYMBOLS = [
     "orbx_strerror", "orbx_last_cuda_error", "orbx_version", "orbx_device_count",
     "orbx_create", "orbx_destroy", "orbx_nlevels", "orbx_capacity", "orbx_tables",
-    "orbx_extract_host", "orbx_extract_device", "orbx_set_pyramid_border",
+    "orbx_extract_host", "orbx_extract_device", "orbx_set_pyramid_border", "orbx_set_input_format",
     "orbx_level_dims", "orbx_download_level", "orbx_level_device_ptr",
     "orbx_download_candidates", "orbx_download_kept", "orbx_max_candidates", "orbx_launch_count",
     "orbx_set_profiling", "orbx_stage_times", "orbm_set_profiling", "orbm_knn2_times",
@@ -64,6 +64,7 @@ def load():
     L.orbx_extract_host.argtypes = [vp, vp, sz, sz, i32, i32, i32, vp, vp, vp]
     L.orbx_extract_device.argtypes = [vp, vp, sz, sz, i32, i32, i32, vp, vp, vp, vp]
     L.orbx_set_pyramid_border.argtypes = [vp, i32]
+    L.orbx_set_input_format.argtypes = [vp, i32, i32]
     L.orbx_level_dims.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
     L.orbx_download_level.argtypes = [vp, i32, i32, i32, i32, vp, sz]
     L.orbx_level_device_ptr.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(sz)]
@@ -129,16 +130,25 @@ class Extractor:
 
     __del__ = close
 
+    def set_input_format(self, channels, rgb_order=False):
+        check(load().orbx_set_input_format(self.h, channels, int(rgb_order)))
+        self.in_channels = channels
+
     def set_pyramid_border(self, on):
         check(load().orbx_set_pyramid_border(self.h, int(on)))
 
     def extract_host(self, imgs, out=None):
         """imgs: (F,H,W) or (H,W) u8 host array -> (kps [F,cap], desc [F,cap,32], counts [F])."""
         imgs = np.asarray(imgs)
-        if imgs.ndim == 2:
+        C_ = getattr(self, "in_channels", 1)
+        if imgs.ndim == (2 if C_ == 1 else 3):
             imgs = imgs[None]
-        assert imgs.dtype == np.uint8 and imgs.ndim == 3 and imgs.strides[2] == 1
-        F, H, W = imgs.shape
+        if C_ != 1:
+            assert imgs.dtype == np.uint8 and imgs.ndim == 4 and imgs.shape[3] == C_ and imgs.strides[3] == 1 and imgs.strides[2] == C_
+            F, H, W = imgs.shape[:3]
+        else:
+            assert imgs.dtype == np.uint8 and imgs.ndim == 3 and imgs.strides[2] == 1
+            F, H, W = imgs.shape
         if out is None:
             out = (np.zeros((F, self.capacity), KEYPOINT_DTYPE), np.zeros((F, self.capacity, 32), np.uint8),
                    np.zeros(F, np.int32))

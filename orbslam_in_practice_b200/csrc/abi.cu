@@ -65,6 +65,8 @@ struct orbx_extractor {
     int nfeat[ORBX_MAX_LEVELS];
     int umax[16];
     int border_on;
+    int in_channels, in_rgb;     // input pixel format (orbx_set_input_format)
+    uint8_t *staging_color; size_t staging_color_bytes;   // host-path staging for colour input
     int profiling;
     static const int kProfCalls = 64;            // event sets kept (ring) while profiling
     cudaEvent_t ev[kProfCalls][ORBX_NUM_STAGES + 1];
@@ -257,7 +259,8 @@ extern "C" int orbx_create(const orbx_params *p, int max_width, int max_height, 
     orbx_extractor *ex = new (std::nothrow) orbx_extractor();
     if (!ex) return ORBX_E_NOMEM;
     ex->params = *p; ex->device = device; ex->max_w = max_width; ex->max_h = max_height; ex->max_batch = max_batch;
-    ex->launches = 0; ex->last_frames = 0; ex->border_on = 0; ex->profiling = 0; ex->prof_calls = 0;
+    ex->launches = 0; ex->last_frames = 0; ex->border_on = 0; ex->in_channels = 1; ex->in_rgb = 0;
+    ex->staging_color = nullptr; ex->staging_color_bytes = 0; ex->profiling = 0; ex->prof_calls = 0;
     for (auto &set : ex->ev) for (auto &e : set) e = nullptr;
     std::memset(&ex->buf, 0, sizeof(ex->buf));
     ex->stream = ex->stream2 = ex->s_h2d = ex->s_d2h = nullptr; ex->s_aux[0] = ex->s_aux[1] = nullptr; ex->fork_slot = 0;
@@ -320,6 +323,7 @@ extern "C" int orbx_destroy(orbx_extractor *ex)
     for (int i = 0; i < orbx_extractor::kMaxChunks; ++i) { if (ex->ev_h2d[i]) cudaEventDestroy(ex->ev_h2d[i]); if (ex->ev_done[i]) cudaEventDestroy(ex->ev_done[i]);
         if (ex->ev_fork[i]) cudaEventDestroy(ex->ev_fork[i]); if (ex->ev_join[i]) cudaEventDestroy(ex->ev_join[i]); }
     for (void *p : ex->allocs) cudaFree(p);
+    if (ex->staging_color) cudaFree(ex->staging_color);
     for (auto &set : ex->ev) for (auto &e : set) if (e) cudaEventDestroy(e);
     delete ex;
     return ORBX_OK;
@@ -351,6 +355,13 @@ extern "C" int orbx_tables(const orbx_extractor *ex, float *scale, float *inv_sc
     return ORBX_OK;
 }
 
+extern "C" int orbx_set_input_format(orbx_extractor *ex, int channels, int rgb_order)
+{
+    if (!ex || (channels != 1 && channels != 3 && channels != 4)) return ORBX_E_INVALID;
+    ex->in_channels = channels; ex->in_rgb = rgb_order ? 1 : 0;
+    return ORBX_OK;
+}
+
 extern "C" int orbx_set_pyramid_border(orbx_extractor *ex, int enabled)
 {
     if (!ex) return ORBX_E_INVALID;
@@ -374,7 +385,7 @@ static int run_pipeline(orbx_extractor *ex, const uint8_t *d_imgs, size_t pitch,
     int rc = ensure_geometry(ex, w, h);
     if (rc) return rc;
     Geo g = ex->geo;
-    g.frame0 = frame0;
+    g.frame0 = frame0; g.in_channels = ex->in_channels; g.in_rgb = ex->in_rgb;
     const bool prof = ex->profiling != 0;
     cudaEvent_t *evs = ex->ev[ex->prof_calls % orbx_extractor::kProfCalls];
 #define STAGE_EVENT(i) do { if (prof) cudaEventRecord(evs[i], s); } while (0)
@@ -427,7 +438,7 @@ extern "C" int orbx_extract_device(orbx_extractor *ex, const uint8_t *d_imgs, si
         return ORBX_OK;
     }
     if (width > ex->max_w || height > ex->max_h || nframes > ex->max_batch) return ORBX_E_CAPACITY;
-    if (row_pitch < (size_t)width) return ORBX_E_INVALID;
+    if (row_pitch < (size_t)width * ex->in_channels) return ORBX_E_INVALID;
     return run_pipeline(ex, d_imgs, row_pitch, frame_stride, width, height, 0, nframes, d_kps, d_desc, d_counts, s);
 }
 
@@ -440,38 +451,51 @@ extern "C" int orbx_extract_host(orbx_extractor *ex, const uint8_t *imgs, size_t
     if (width <= 0 || height <= 0 || !imgs) { std::memset(counts, 0, sizeof(int) * (size_t)nframes); return ORBX_OK; }
     if (!kps || !desc) return ORBX_E_INVALID;
     if (width > ex->max_w || height > ex->max_h || nframes > ex->max_batch) return ORBX_E_CAPACITY;
-    if (row_pitch < (size_t)width) return ORBX_E_INVALID;
+    const size_t C = (size_t)ex->in_channels;
+    if (row_pitch < (size_t)width * C) return ORBX_E_INVALID;
     CK(cudaSetDevice(ex->device));
     const size_t cap = (size_t)ex->full.capacity;
+    uint8_t *staging = ex->buf.staging;
+    if (C != 1) {                                   // colour input needs C x the gray staging: allocated on first use
+        const size_t need = (size_t)ex->max_batch * ex->max_w * ex->max_h * C;
+        if (ex->staging_color_bytes < need) {
+            if (ex->staging_color) CK(cudaFree(ex->staging_color));
+            ex->staging_color = nullptr; ex->staging_color_bytes = 0;
+            if (cudaMalloc(&ex->staging_color, need) != cudaSuccess) { cuda_fail(cudaGetLastError(), "cudaMalloc"); return ORBX_E_NOMEM; }
+            ex->staging_color_bytes = need;
+        }
+        staging = ex->staging_color;
+    }
     int rc = ensure_geometry(ex, width, height);
     if (rc) return rc;
     // Chunked three-stream pipeline: the H2D copy of chunk c+1 and the D2H copy of chunk c-1 overlap
     // the kernels of chunk c (PCIe is full duplex; frames are independent).
     int nchunks = nframes >= 64 ? 4 : (nframes >= 8 ? 2 : 1);
     if (const char *e = std::getenv("ORBX_HOST_CHUNKS")) { const int v = std::atoi(e); if (v >= 1 && v <= orbx_extractor::kMaxChunks && v <= nframes) nchunks = v; }
-    const size_t fbytes = (size_t)width * height;
+    const size_t rbytes = (size_t)width * C;           // bytes per tight row
+    const size_t fbytes = rbytes * height;
     for (int c = 0; c < nchunks; ++c) {
         const int f0 = (int)((long long)nframes * c / nchunks), f1 = (int)((long long)nframes * (c + 1) / nchunks);
         const int n = f1 - f0;
         if (n <= 0) continue;
-        if (row_pitch == (size_t)width && (frame_stride == fbytes || n == 1)) {
+        if (row_pitch == rbytes && (frame_stride == fbytes || n == 1)) {
             // fully contiguous frames: one linear copy (a 2-D copy of 640-byte rows is slower on the DMA engine)
-            CK(cudaMemcpyAsync(ex->buf.staging + f0 * fbytes, imgs + (size_t)f0 * frame_stride, (size_t)n * fbytes,
+            CK(cudaMemcpyAsync(staging + f0 * fbytes, imgs + (size_t)f0 * frame_stride, (size_t)n * fbytes,
                                cudaMemcpyHostToDevice, ex->s_h2d));
         } else if (frame_stride == row_pitch * (size_t)height || n == 1) {
-            CK(cudaMemcpy2DAsync(ex->buf.staging + f0 * fbytes, (size_t)width, imgs + (size_t)f0 * frame_stride, row_pitch,
-                                 (size_t)width, (size_t)height * n, cudaMemcpyHostToDevice, ex->s_h2d));
+            CK(cudaMemcpy2DAsync(staging + f0 * fbytes, rbytes, imgs + (size_t)f0 * frame_stride, row_pitch,
+                                 rbytes, (size_t)height * n, cudaMemcpyHostToDevice, ex->s_h2d));
         } else {
             for (int f = f0; f < f1; ++f)
-                CK(cudaMemcpy2DAsync(ex->buf.staging + f * fbytes, (size_t)width, imgs + (size_t)f * frame_stride, row_pitch,
-                                     (size_t)width, (size_t)height, cudaMemcpyHostToDevice, ex->s_h2d));
+                CK(cudaMemcpy2DAsync(staging + f * fbytes, rbytes, imgs + (size_t)f * frame_stride, row_pitch,
+                                     rbytes, (size_t)height, cudaMemcpyHostToDevice, ex->s_h2d));
         }
         CK(cudaEventRecord(ex->ev_h2d[c], ex->s_h2d));
         // chunks alternate between two compute streams so one chunk's kernels fill the launch gaps
         // and tail waves of the other (per-frame buffers are disjoint)
         cudaStream_t cs = (c & 1) ? ex->stream2 : ex->stream;
         CK(cudaStreamWaitEvent(cs, ex->ev_h2d[c], 0));
-        rc = run_pipeline(ex, ex->buf.staging, (size_t)width, fbytes, width, height, f0, n,
+        rc = run_pipeline(ex, staging, rbytes, fbytes, width, height, f0, n,
                           ex->buf.out_kps, ex->buf.out_desc, ex->buf.out_counts, cs);
         if (rc) return rc;
         CK(cudaEventRecord(ex->ev_done[c], cs));

@@ -51,6 +51,7 @@ struct LevelGeom {
 struct Geo {
     int nlevels, ini_th, min_th, border_on;
     int frame0;               // first frame handled by this launch (chunked host pipeline)
+    int in_channels, in_rgb;  // input pixel format: 1 / 3 / 4 interleaved channels, RGB(A) or BGR(A) order
     int total_cells;          // cells per frame, all levels
     int capacity;             // output keypoint slots per frame
     int kept_total;           // kept slots per frame (= capacity)

@@ -140,3 +140,20 @@ def test_stereo_left_right_matching(orbx, oracle):
     assert np.array_equal(d1, o1) and np.array_equal(i1, oi) and np.array_equal(d2, o2)
     match = oracle.ratio_select(d1, i1, d2, 50, 0.7)
     assert (match >= 0).sum() > nl // 4
+
+
+@pytest.mark.parametrize("channels,rgb", [(3, False), (3, True), (4, False)])
+def test_colour_input_fused_gray_conversion(orbx, oracle, channels, rgb):
+    """cvtColor(..2GRAY) (src/Tracking.cpp:57-70) fused into the level-0 kernel."""
+    rng = np.random.default_rng(channels)
+    base = synth_batch([3, 4])
+    col = np.repeat(base[..., None], channels, axis=3).astype(np.int32) + rng.integers(-20, 21, base.shape + (channels,))
+    col = np.clip(col, 0, 255).astype(np.uint8)
+    ex = orbx.Extractor(max_width=640, max_height=480, max_batch=2)
+    ex.set_input_format(channels, rgb)
+    kps, desc, counts = ex.extract_host(col)
+    oex = oracle.OracleExtractor()
+    for f in range(2):
+        gray = oracle.cvt_gray(col[f], rgb)
+        assert np.array_equal(ex.level(f, 0), gray), "level 0 is not the OpenCV fixed-point gray image"
+        _compare_frame(oracle, ex, oex, gray, f, kps, desc, counts, check_stages=False)

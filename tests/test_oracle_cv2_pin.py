@@ -61,3 +61,11 @@ def test_full_extractor_matches_cv2_tier_a(oracle, case):
     assert rep["pyramid_px"] == 0 and rep["blur_px"] == 0 and rep["cand_mismatch"] == 0 and rep["kept_mismatch"] == 0
     assert rep["n_tier_a"] == rep["n_oracle"] and rep.get("xy_equal", True)
     assert rep["angle_max_abs_deg"] <= 1e-4 and rep["desc_bits_diff"] <= 1e-3 * max(rep["desc_bits"], 1)
+
+
+@pytest.mark.parametrize("code,channels,rgb", [("COLOR_BGR2GRAY", 3, False), ("COLOR_RGB2GRAY", 3, True),
+                                               ("COLOR_BGRA2GRAY", 4, False), ("COLOR_RGBA2GRAY", 4, True)])
+def test_cvt_gray_matches_cv2(oracle, code, channels, rgb):
+    """The conversion in front of the extractor (src/Tracking.cpp:57-70), SURVEY.md 8f-2."""
+    img = np.random.default_rng(channels + rgb).integers(0, 256, (97, 131, channels), dtype=np.uint8)
+    assert np.array_equal(oracle.cvt_gray(img, rgb), cv2.cvtColor(img, getattr(cv2, code)))
