@@ -10,6 +10,7 @@
  *                                    GetLevels/GetScaleFactor(s)/...   include/ORBextractor.h:47-69
  *   orbx_extract_host/_device        ORBextractor::operator()          include/ORBextractor.h:43-45, src/ORBextractor.cpp:1001-1065
  *   orbx_set_input_format            cv::cvtColor(..2GRAY) before the extractor   src/Tracking.cpp:57-70
+ *   orbx_undistort_keypoints_device  Frame::UndistortedKeyPoints   src/Frame.cpp:80-109
  *   orbx_download_level              mvImagePyramid (public member)    include/ORBextractor.h:71, src/ORBextractor.cpp:1071-1096
  *   orbm_hamming_pairs_host          ORBmatcher::DescriptorDistance    include/ORBmatcher.h:19, src/ORBmatcher.cpp:128-144
  *   orbm_knn2_* / orbm_ratio_select  best-2 scan + acceptance          src/ORBmatcher.cpp:37-67
@@ -133,6 +134,13 @@ long long orbx_launch_count(const orbx_extractor *ex);
 #define ORBX_NUM_STAGES 6
 int orbx_set_profiling(orbx_extractor *ex, int enabled);
 int orbx_stage_times(orbx_extractor *ex, float *ms);
+
+/* Frame::UndistortedKeyPoints (src/Frame.cpp:80-109): cv::undistortPoints(pts, K, dist, R = I, P = K) applied to
+ * pt.x / pt.y of n keypoints (device pointers; in may equal out; all other fields are copied).
+ * cam = {fx, fy, cx, cy}, dist = {k1, k2, p1, p2, k3} (host pointers).  dist[0] == 0 -> plain copy (:82-86).
+ * literal_bug != 0 reproduces :106 as written (the undistorted x is stored into y as well). */
+int orbx_undistort_keypoints_device(orbx_extractor *ex, const orbx_keypoint *d_in, orbx_keypoint *d_out, int n,
+                                    const float *cam, const float *dist, int literal_bug, void *stream);
 
 /* ---------------- matcher ---------------- */
 int orbm_create(int max_queries, int max_db, int device, orbm_matcher **out);

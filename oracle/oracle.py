@@ -72,6 +72,7 @@ def lib():
     L.orbo_ic_angle.restype = f32
     L.orbo_ic_angle.argtypes = [vp, sz, i32, i32, vp, C.POINTER(i32), C.POINTER(i32)]
     L.orbo_orb_descriptor.argtypes = [vp, sz, i32, i32, f32, vp]
+    L.orbo_undistort_keypoints.argtypes = [vp, vp, i32, vp, vp, i32]
     L.orbo_cvt_gray_u8.argtypes = [vp, i32, i32, sz, i32, i32, vp, sz]
     L.orbo_descriptor_distance.restype = i32
     L.orbo_descriptor_distance.argtypes = [vp, vp]
@@ -226,6 +227,14 @@ def orb_descriptor(blurred, x, y, angle_deg):
     d = np.zeros(32, np.uint8)
     lib().orbo_orb_descriptor(_p(blurred), blurred.strides[0], x, y, float(angle_deg), _p(d))
     return d
+
+
+def undistort_keypoints(kps, cam, dist, literal_bug=False):
+    kps = np.ascontiguousarray(kps, KEYPOINT_DTYPE)
+    out = np.zeros_like(kps)
+    cam = np.ascontiguousarray(cam, np.float32); dist = np.ascontiguousarray(dist, np.float32)
+    lib().orbo_undistort_keypoints(_p(kps), _p(out), len(kps), _p(cam), _p(dist), int(literal_bug))
+    return out
 
 
 def cvt_gray(img, rgb_order=False):

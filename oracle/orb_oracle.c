@@ -766,6 +766,28 @@ int orbo_level_candidates(const orbo_extractor *ex, int level, const orbo_cand *
 int orbo_level_kept(const orbo_extractor *ex, int level, const orbo_cand **c) { *c = ex->kept[level]; return ex->nkept[level]; }
 int orbo_level_retries(const orbo_extractor *ex, int level) { return ex->retries[level]; }
 
+void orbo_undistort_keypoints(const orbo_keypoint *in, orbo_keypoint *out, int n, const float *cam, const float *dist, int literal_bug)
+{
+    const double fx = cam[0], fy = cam[1], cx = cam[2], cy = cam[3];
+    const double k1 = dist[0], k2 = dist[1], p1 = dist[2], p2 = dist[3], k3 = dist[4];
+    for (int i = 0; i < n; ++i) {
+        out[i] = in[i];
+        if (dist[0] == 0.0f) continue;                       /* Frame.cpp:82-86 */
+        double x = ((double)in[i].x - cx) / fx, y = ((double)in[i].y - cy) / fy;
+        const double x0 = x, y0 = y;
+        for (int it = 0; it < 5; ++it) {                     /* cvUndistortPointsInternal, TermCriteria(MAX_ITER, 5) */
+            const double r2 = x * x + y * y;
+            const double icdist = 1.0 / (1 + ((k3 * r2 + k2) * r2 + k1) * r2);
+            if (icdist < 0) { x = x0; y = y0; break; }
+            const double dX = 2 * p1 * x * y + p2 * (r2 + 2 * x * x);
+            const double dY = p1 * (r2 + 2 * y * y) + 2 * p2 * x * y;
+            x = (x0 - dX) * icdist; y = (y0 - dY) * icdist;
+        }
+        const float ux = (float)(x * fx + cx), uy = (float)(y * fy + cy);
+        out[i].x = ux; out[i].y = literal_bug ? ux : uy;      /* Frame.cpp:105-106 */
+    }
+}
+
 void orbo_cvt_gray_u8(const uint8_t *src, int w, int h, size_t spitch, int channels, int rgb_order, uint8_t *dst, size_t dpitch)
 {
     for (int y = 0; y < h; ++y) {

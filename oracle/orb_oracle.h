@@ -94,6 +94,12 @@ void orbo_orb_descriptor(const uint8_t *blurred, size_t pitch, int x, int y, flo
  * OpenCV 4.13.0 fixed point: (R*9798 + G*19235 + B*3735 + 16384) >> 15 (pinned against cv2; the 2.4/3.x era used 14 bits). */
 void orbo_cvt_gray_u8(const uint8_t *src, int w, int h, size_t spitch, int channels, int rgb_order, uint8_t *dst, size_t dpitch);
 
+/* Frame::UndistortedKeyPoints (src/Frame.cpp:80-109): cv::undistortPoints(pts, K, dist, R = I, P = K) on the keypoint
+ * coordinates, restated from OpenCV 4.13.0 (5 fixed iterations in double; pinned against cv2).  cam = {fx, fy, cx, cy},
+ * dist = {k1, k2, p1, p2, k3} as floats (the reference stores them in CV_32F Mats, Frame.cpp:46-55).  dist[0] == 0 -> copy
+ * (:82-86).  literal_bug != 0 reproduces :106 (the undistorted x is also written to y). */
+void orbo_undistort_keypoints(const orbo_keypoint *in, orbo_keypoint *out, int n, const float *cam, const float *dist, int literal_bug);
+
 /* ---- matcher ---- */
 /* ORBmatcher::DescriptorDistance, ORBmatcher.cpp:128-144 (SWAR popcount on 8 x int32) */
 int orbo_descriptor_distance(const uint8_t *a, const uint8_t *b);

@@ -605,6 +605,17 @@ extern "C" int orbx_download_kept(orbx_extractor *ex, int frame, int level, orbx
     return download_keys(ex, ex->buf.kept + (size_t)frame * g.kept_total + L.kept_base, ex->buf.nkept + (size_t)frame * g.nlevels + level, L.kept_cap, out, cap, n);
 }
 
+extern "C" int orbx_undistort_keypoints_device(orbx_extractor *ex, const orbx_keypoint *d_in, orbx_keypoint *d_out, int n,
+                                               const float *cam, const float *dist, int literal_bug, void *stream)
+{
+    if (!ex || n < 0 || !cam || !dist || (n && (!d_in || !d_out))) return ORBX_E_INVALID;
+    CK(cudaSetDevice(ex->device));
+    launch_undistort(d_in, d_out, n, cam, dist, literal_bug, stream ? (cudaStream_t)stream : ex->stream);
+    ex->launches += n > 0;
+    CK(cudaGetLastError());
+    return ORBX_OK;
+}
+
 extern "C" long long orbx_launch_count(const orbx_extractor *ex) { return ex ? ex->launches : 0; }
 
 extern "C" int orbx_set_profiling(orbx_extractor *ex, int enabled)

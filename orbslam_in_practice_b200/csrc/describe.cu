@@ -268,4 +268,41 @@ void launch_describe(const Geo &g, const DevBuffers &b, int nframes, orbx_keypoi
     k_describe<<<grd, kDescWarps * 32, 0, s>>>(g, b.pyr, b.blur, b.kept, b.nkept, d_kps, d_desc, d_counts, g_pattern_dev[dev]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Frame::UndistortedKeyPoints (src/Frame.cpp:80-109) = cv::undistortPoints with R = I, P = K: five fixed
+// iterations of the inverse Brown model in double precision (OpenCV 4.13.0 cvUndistortPointsInternal).
+// Explicit round-to-nearest intrinsics keep the operation order of the scalar C++ code (no FMA contraction).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_undistort(const orbx_keypoint *__restrict__ in, orbx_keypoint *__restrict__ out, int n,
+                            double fx, double fy, double cx, double cy, double k1, double k2, double p1, double p2, double k3,
+                            int passthrough, int literal_bug)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    orbx_keypoint k = in[i];
+    if (!passthrough) {
+        double x = __ddiv_rn(__dsub_rn((double)k.x, cx), fx), y = __ddiv_rn(__dsub_rn((double)k.y, cy), fy);
+        const double x0 = x, y0 = y;
+        for (int it = 0; it < 5; ++it) {
+            const double r2 = __dadd_rn(__dmul_rn(x, x), __dmul_rn(y, y));
+            const double den = __dadd_rn(1.0, __dmul_rn(__dadd_rn(__dmul_rn(__dadd_rn(__dmul_rn(k3, r2), k2), r2), k1), r2));
+            const double icdist = __ddiv_rn(1.0, den);
+            if (icdist < 0) { x = x0; y = y0; break; }
+            const double dX = __dadd_rn(__dmul_rn(__dmul_rn(__dmul_rn(2.0, p1), x), y), __dmul_rn(p2, __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, x), x))));
+            const double dY = __dadd_rn(__dmul_rn(p1, __dadd_rn(r2, __dmul_rn(__dmul_rn(2.0, y), y))), __dmul_rn(__dmul_rn(__dmul_rn(2.0, p2), x), y));
+            x = __dmul_rn(__dsub_rn(x0, dX), icdist); y = __dmul_rn(__dsub_rn(y0, dY), icdist);
+        }
+        const float ux = (float)__dadd_rn(__dmul_rn(x, fx), cx), uy = (float)__dadd_rn(__dmul_rn(y, fy), cy);
+        k.x = ux; k.y = literal_bug ? ux : uy;
+    }
+    out[i] = k;
+}
+
+void launch_undistort(const orbx_keypoint *in, orbx_keypoint *out, int n, const float *cam, const float *dist, int literal_bug, cudaStream_t s)
+{
+    if (n <= 0) return;
+    k_undistort<<<(n + 255) / 256, 256, 0, s>>>(in, out, n, cam[0], cam[1], cam[2], cam[3], dist[0], dist[1], dist[2], dist[3], dist[4],
+                                               dist[0] == 0.0f, literal_bug);
+}
+
 } // namespace orbx

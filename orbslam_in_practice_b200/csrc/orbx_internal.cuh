@@ -85,6 +85,7 @@ void launch_fast(const Geo &g, const DevBuffers &b, int nframes, cudaStream_t s)
 void launch_octree(const Geo &g, const DevBuffers &b, int nframes, int smem_bytes, cudaStream_t s);
 void launch_blur(const Geo &g, const DevBuffers &b, int nframes, cudaStream_t s);
 void launch_describe(const Geo &g, const DevBuffers &b, int nframes, orbx_keypoint *d_kps, uint8_t *d_desc, int *d_counts, cudaStream_t s);
+void launch_undistort(const orbx_keypoint *in, orbx_keypoint *out, int n, const float *cam, const float *dist, int literal_bug, cudaStream_t s);
 int octree_smem_bytes(const Geo &g);
 int octree_configure(int smem_bytes);
 

@@ -157,3 +157,25 @@ def test_colour_input_fused_gray_conversion(orbx, oracle, channels, rgb):
         gray = oracle.cvt_gray(col[f], rgb)
         assert np.array_equal(ex.level(f, 0), gray), "level 0 is not the OpenCV fixed-point gray image"
         _compare_frame(oracle, ex, oex, gray, f, kps, desc, counts, check_stages=False)
+
+
+def test_undistort_keypoints(orbx, oracle):
+    """SURVEY.md 8f-3: Frame::UndistortedKeyPoints on the device vs the oracle (pinned against cv2.undistortPoints)."""
+    import torch
+    img = synth_frame(9)
+    ex = orbx.Extractor(max_width=640, max_height=480, max_batch=1)
+    kps, desc, counts = ex.extract_host(img)
+    n = int(counts[0])
+    cam = [517.3, 516.5, 318.6, 255.3]; dist = [0.2624, -0.9531, -0.0054, 0.0026, 1.1633]
+    d_in = torch.from_numpy(kps[0, :n].view(np.uint8).reshape(n, 28)).cuda()
+    d_out = torch.zeros_like(d_in)
+    ex.undistort_keypoints_device(d_in.data_ptr(), d_out.data_ptr(), n, cam, dist, False, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy().view(oracle.KEYPOINT_DTYPE).reshape(n)
+    want = oracle.undistort_keypoints(kps[0, :n].astype(oracle.KEYPOINT_DTYPE), cam, dist)
+    assert np.abs(got["x"] - want["x"]).max() <= 1e-3 and np.abs(got["y"] - want["y"]).max() <= 1e-3   # px; observed: identical
+    for fld in ("size", "angle", "response", "octave", "class_id"):
+        assert np.array_equal(got[fld], want[fld])
+    ex.undistort_keypoints_device(d_in.data_ptr(), d_out.data_ptr(), n, cam, [0, 0, 0, 0, 0])
+    torch.cuda.synchronize()
+    assert torch.equal(d_in, d_out)

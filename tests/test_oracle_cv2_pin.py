@@ -69,3 +69,20 @@ def test_cvt_gray_matches_cv2(oracle, code, channels, rgb):
     """The conversion in front of the extractor (src/Tracking.cpp:57-70), SURVEY.md 8f-2."""
     img = np.random.default_rng(channels + rgb).integers(0, 256, (97, 131, channels), dtype=np.uint8)
     assert np.array_equal(oracle.cvt_gray(img, rgb), cv2.cvtColor(img, getattr(cv2, code)))
+
+
+def test_undistort_keypoints_matches_cv2(oracle):
+    """Frame::UndistortedKeyPoints (src/Frame.cpp:80-109), SURVEY.md 8f-3: cv::undistortPoints(pts, K, dist, Mat(), K)."""
+    rng = np.random.default_rng(0)
+    K = np.array([[517.3, 0, 318.6], [0, 516.5, 255.3], [0, 0, 1]], np.float32)
+    dist = np.array([0.2624, -0.9531, -0.0054, 0.0026, 1.1633], np.float32)          # TUM fr1-like
+    kps = np.zeros(2000, oracle.KEYPOINT_DTYPE)
+    kps["x"] = rng.random(2000) * 640; kps["y"] = rng.random(2000) * 480; kps["octave"] = 3
+    want = cv2.undistortPoints(np.stack([kps["x"], kps["y"]], 1).reshape(-1, 1, 2), K, dist, None, K).reshape(-1, 2)
+    got = oracle.undistort_keypoints(kps, [K[0, 0], K[1, 1], K[0, 2], K[1, 2]], dist)
+    assert np.array_equal(got["x"], want[:, 0]) and np.array_equal(got["y"], want[:, 1])
+    assert (got["octave"] == 3).all()
+    bug = oracle.undistort_keypoints(kps, [K[0, 0], K[1, 1], K[0, 2], K[1, 2]], dist, literal_bug=True)
+    assert np.array_equal(bug["y"], want[:, 0])                                        # Frame.cpp:106 as written
+    same = oracle.undistort_keypoints(kps, [K[0, 0], K[1, 1], K[0, 2], K[1, 2]], [0, 0.1, 0, 0, 0])
+    assert np.array_equal(same["x"], kps["x"]) and np.array_equal(same["y"], kps["y"])  # Frame.cpp:82-86
