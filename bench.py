@@ -395,7 +395,7 @@ def run_match(args, _lib, torch, dist, dev, world, rank, local, stream, K, barri
     tri = torch.empty((3, KNN_NQ), dtype=torch.int32, device=dev)
     out = torch.empty((4, KNN_NQ), dtype=torch.int32, device=dev)
 
-    def knn_step():
+    def knn_step_nccl():
         m.knn2_device(t_q.data_ptr(), KNN_NQ, t_db.data_ptr(), hi - lo, lo, tri[0].data_ptr(), tri[1].data_ptr(),
                       tri[2].data_ptr(), stream)
         src, stride = sharding.gather_triples(tri, world), 3 * KNN_NQ     # NCCL all-gather over NVLink when world > 1
@@ -403,6 +403,27 @@ def run_match(args, _lib, torch, dist, dev, world, rank, local, stream, K, barri
                               out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), stream, shard_stride=stride)
         m.ratio_select_device(out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), KNN_NQ, 50, 0.7,
                               out[3].data_ptr(), stream)
+
+    def knn_step_p2p():
+        # scan + publish + ONE fused kernel (wait for the peers' shards, NVLink peer loads, merge, ratio test)
+        m.knn2_sharded_device(t_q.data_ptr(), KNN_NQ, t_db.data_ptr(), hi - lo, lo, out[0].data_ptr(), out[1].data_ptr(),
+                              out[2].data_ptr(), 50, 0.7, out[3].data_ptr(), stream)
+
+    exchange = "single GPU (no exchange)"
+    knn_step = knn_step_nccl
+    if world > 1:
+        exchange = "nccl all_gather + merge kernel"
+        try:
+            m.exchange_open(sharding.exchange_handles(m, KNN_NQ, rank, world))
+            knn_step_nccl(); torch.cuda.synchronize(); want = out.clone()
+            knn_step_p2p(); torch.cuda.synchronize(); m.exchange_status()
+            okt = torch.tensor([int(torch.equal(out, want))], device=dev)
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+            if int(okt.item()) == 1:
+                knn_step = knn_step_p2p
+                exchange = "fused peer-memory kernel (CUDA IPC + NVLink P2P loads), verified equal to the NCCL path"
+        except Exception as e:                       # e.g. IPC not permitted in this container: stay on the NCCL path
+            sys.stderr.write("peer exchange unavailable, using NCCL all_gather: %s\n" % e)
 
     ksteps = max(1, min(K, 5))
     for _ in range(2):
@@ -430,7 +451,7 @@ def run_match(args, _lib, torch, dist, dev, world, rank, local, stream, K, barri
                           "peak": popc_peak / 1e12, "unit": "TPOPC/s", "frac": scan_pairs * 8 / (scan_ms * 1e-3) / popc_peak,
                           "peak_source": "measured in this run (orbm_popc_peak microbenchmark, 32-bit POPC results/s)",
                           "scan_ms": scan_ms, "merge_ms": merge_ms},
-             "matched_queries": matched, "gpu_launches": int(knn_launches)}
+             "matched_queries": matched, "gpu_launches": int(knn_launches), "exchange": exchange}
 
     if rank == 0 and world == 1 and not args.skip_cpu:
         match["cpu_baseline"] = cpu_knn_baseline(db, q)

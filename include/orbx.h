@@ -172,6 +172,22 @@ int orbm_merge_shards_device(orbm_matcher *m, const int32_t *d_d1, const int32_t
 int orbm_set_profiling(orbm_matcher *m, int enabled);
 int orbm_knn2_times(orbm_matcher *m, float *scan_ms, float *merge_ms);
 
+/* --- database-sharded search with a peer-memory exchange (one process per GPU on one NVLink/NVSwitch box) ---
+ * Setup: every rank calls orbm_exchange_create and publishes the returned 64-byte IPC handle (e.g. with
+ * torch.distributed.all_gather); every rank then calls orbm_exchange_open with all handles in rank order.
+ * Per search: orbm_knn2_sharded_device scans this rank's shard (rows index_base .. index_base + ndb_shard - 1 of the
+ * global database; ranks own ascending ranges), publishes the result to the peers, and runs ONE fused kernel that waits for
+ * all shards, reads their (d1, idx1, d2) over NVLink peer loads and writes the merged best-2 and the ratio-test matches
+ * (d_match may be NULL).  Results are identical on every rank and identical to an unsharded scan.
+ * orbm_exchange_status returns ORBX_E_CUDA if a previous fused kernel timed out waiting for a peer. */
+#define ORBM_IPC_HANDLE_BYTES 64
+int orbm_exchange_create(orbm_matcher *m, int max_queries, int rank, int world, unsigned char *handle_out);
+int orbm_exchange_open(orbm_matcher *m, const unsigned char *handles /* world x ORBM_IPC_HANDLE_BYTES */);
+int orbm_knn2_sharded_device(orbm_matcher *m, const uint8_t *d_query, int nq, const uint8_t *d_db_shard, int ndb_shard,
+                             int index_base, int32_t *d_d1, int32_t *d_idx1, int32_t *d_d2,
+                             int th_low, float ratio, int32_t *d_match, void *stream);
+int orbm_exchange_status(orbm_matcher *m);
+
 /* ORBmatcher::SearchForInitialization (src/ORBmatcher.cpp:9-126) on extractor outputs, including the Frame grid
  * it queries (Frame::AssignFeaturesToGrid / GetFeaturesInArea, src/Frame.cpp:144-168, 219-271): windowed best-2
  * with the sequential one-to-one gate, TH_LOW / ratio acceptance, rotation-histogram filter, prev-matched update.

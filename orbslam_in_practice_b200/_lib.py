@@ -28,6 +28,7 @@ ABI_SYMBOLS = [
     "orbm_create", "orbm_destroy", "orbm_launch_count", "orbm_hamming_pairs_host",
     "orbm_knn2_device", "orbm_knn2_host", "orbm_ratio_select_device", "orbm_merge_shards_device",
     "orbm_popc_peak", "orbm_search_init_workspace_bytes", "orbm_search_init_device", "orbm_search_init_host",
+    "orbm_exchange_create", "orbm_exchange_open", "orbm_knn2_sharded_device", "orbm_exchange_status",
 ]
 
 
@@ -90,6 +91,10 @@ def load():
     L.orbm_popc_peak.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.orbm_search_init_workspace_bytes.restype = sz
     L.orbm_search_init_workspace_bytes.argtypes = [i32, i32]
+    L.orbm_exchange_create.argtypes = [vp, i32, i32, i32, vp]
+    L.orbm_exchange_open.argtypes = [vp, vp]
+    L.orbm_knn2_sharded_device.argtypes = [vp, vp, i32, vp, i32, i32, vp, vp, vp, i32, f32, vp, vp]
+    L.orbm_exchange_status.argtypes = [vp]
     L.orbm_search_init_host.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, vp, C.POINTER(i32), i32, f32, i32, i32, i32, i32]
     L.orbm_search_init_device.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, vp, i32, f32, i32, i32, i32, i32, vp, sz, vp]
     _lib = L
@@ -251,6 +256,23 @@ class Matcher:
         check(load().orbm_search_init_device(self.h, kps_ptr, desc_ptr, counts_ptr, capacity, pair_a_ptr, pair_b_ptr, npairs,
                                              prev_ptr, matches_ptr, nmatches_ptr, window, nnratio, int(check_ori), width,
                                              height, int(literal_bug), ws_ptr, ws_bytes, stream))
+
+    # ---- peer-memory exchange for the database-sharded search ----
+    def exchange_create(self, max_queries, rank, world):
+        h = (C.c_ubyte * 64)()
+        check(load().orbm_exchange_create(self.h, max_queries, rank, world, h))
+        return bytes(h)
+
+    def exchange_open(self, handles):
+        buf = (C.c_ubyte * (64 * len(handles))).from_buffer_copy(b"".join(handles))
+        check(load().orbm_exchange_open(self.h, buf))
+
+    def knn2_sharded_device(self, q_ptr, nq, db_ptr, ndb, index_base, d1_ptr, idx1_ptr, d2_ptr, th_low, ratio, match_ptr, stream=0):
+        check(load().orbm_knn2_sharded_device(self.h, q_ptr, nq, db_ptr, ndb, index_base, d1_ptr, idx1_ptr, d2_ptr, th_low, ratio,
+                                              match_ptr, stream))
+
+    def exchange_status(self):
+        check(load().orbm_exchange_status(self.h))
 
     def search_init_host(self, kp1, desc1, kp2, desc2, prev_matched, window=100, nnratio=0.9, check_ori=True,
                          width=640, height=480, literal_bug=False):

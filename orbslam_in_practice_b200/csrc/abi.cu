@@ -20,6 +20,9 @@ void launch_hamming_pairs(const uint8_t *a, const uint8_t *b, int n, int *dist, 
 void launch_ratio_select(const int *d1, const int *idx1, const int *d2, int nq, int th, float ratio, int *match, cudaStream_t s);
 void launch_merge_shards(const int *d1, const int *idx1, const int *d2, int nshards, int nq, size_t stride, int *od1, int *oidx1, int *od2, cudaStream_t s);
 int run_popc_bench(int mode, int sm_count, double *ops_per_second);
+void launch_exchange_signal(uint32_t *const *peer_flags, int rank, int world, uint32_t epoch, cudaStream_t s);
+void launch_merge_peers(const int *const *peer_tri, const uint32_t *my_flags, int world, int nq, size_t arr_stride, uint32_t epoch,
+                        int *od1, int *oidx1, int *od2, int th_low, float ratio, int *match, int *err, cudaStream_t s);
 // search_init.cu
 struct SearchInitArgs {
     const orbx_keypoint *kps; const uint8_t *desc; const int *counts; int cap;
@@ -657,6 +660,10 @@ struct orbm_matcher {
     uint2 *partial; size_t partial_elems;
     uint8_t *d_q, *d_db; int *d_out;   // device staging for the host-pointer entry points
     void *si_buf; size_t si_bytes;     // scratch of orbm_search_init_host
+    // peer-memory exchange (sharded search): own buffer = [2 parities][3][xq_max] int32 + flags[64] + err
+    unsigned char *x_buf; int x_qmax, x_rank, x_world; uint32_t x_epoch;
+    void *x_peer[64];                  // opened peer mappings (own entry = x_buf)
+    int **x_tri_tab; uint32_t **x_flag_tab;   // device tables: [2][world] triple pointers, [world] flag pointers
     long long launches;
     int profiling; bool ev_valid;
     cudaEvent_t ev[3];
@@ -691,6 +698,8 @@ extern "C" int orbm_destroy(orbm_matcher *m)
     cudaSetDevice(m->device);
     if (m->stream) { cudaStreamSynchronize(m->stream); cudaStreamDestroy(m->stream); }
     cudaFree(m->partial); cudaFree(m->d_q); cudaFree(m->d_db); cudaFree(m->d_out); cudaFree(m->si_buf);
+    for (int r = 0; r < m->x_world; ++r) if (m->x_peer[r] && r != m->x_rank) cudaIpcCloseMemHandle(m->x_peer[r]);
+    cudaFree(m->x_buf); cudaFree(m->x_tri_tab); cudaFree(m->x_flag_tab);
     for (auto &e : m->ev) if (e) cudaEventDestroy(e);
     delete m;
     return ORBX_OK;
@@ -805,6 +814,79 @@ extern "C" int orbm_merge_shards_device(orbm_matcher *m, const int32_t *d_d1, co
     launch_merge_shards(d_d1, d_idx1, d_d2, nshards, nq, shard_stride, d_od1, d_oidx1, d_od2, stream ? (cudaStream_t)stream : m->stream);
     m->launches += nq > 0;
     CK(cudaGetLastError());
+    return ORBX_OK;
+}
+
+static size_t x_tri_bytes(const orbm_matcher *m) { return (size_t)2 * 3 * m->x_qmax * sizeof(int); }
+
+extern "C" int orbm_exchange_create(orbm_matcher *m, int max_queries, int rank, int world, unsigned char *handle_out)
+{
+    if (!m || !handle_out || max_queries < 1 || world < 1 || world > 64 || rank < 0 || rank >= world || m->x_buf) return ORBX_E_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == ORBM_IPC_HANDLE_BYTES, "IPC handle size");
+    CK(cudaSetDevice(m->device));
+    m->x_qmax = max_queries; m->x_rank = rank; m->x_world = world; m->x_epoch = 0;
+    const size_t bytes = x_tri_bytes(m) + 64 * sizeof(uint32_t) + 64;
+    if (cudaMalloc(&m->x_buf, bytes) != cudaSuccess) { cuda_fail(cudaGetLastError(), "cudaMalloc"); return ORBX_E_NOMEM; }
+    CK(cudaMemset(m->x_buf, 0, bytes));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, m->x_buf));
+    std::memcpy(handle_out, &h, sizeof(h));
+    return ORBX_OK;
+}
+
+extern "C" int orbm_exchange_open(orbm_matcher *m, const unsigned char *handles)
+{
+    if (!m || !handles || !m->x_buf || m->x_tri_tab) return ORBX_E_INVALID;
+    CK(cudaSetDevice(m->device));
+    const int W = m->x_world;
+    for (int r = 0; r < W; ++r) {
+        if (r == m->x_rank) { m->x_peer[r] = m->x_buf; continue; }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handles + (size_t)r * ORBM_IPC_HANDLE_BYTES, sizeof(h));
+        CK(cudaIpcOpenMemHandle(&m->x_peer[r], h, cudaIpcMemLazyEnablePeerAccess));
+    }
+    std::vector<int *> tri((size_t)2 * W);
+    std::vector<uint32_t *> flg((size_t)W);
+    for (int r = 0; r < W; ++r) {
+        unsigned char *b = (unsigned char *)m->x_peer[r];
+        tri[r] = (int *)b; tri[W + r] = (int *)b + (size_t)3 * m->x_qmax;
+        flg[r] = (uint32_t *)(b + x_tri_bytes(m));
+    }
+    CK(cudaMalloc(&m->x_tri_tab, tri.size() * sizeof(int *)));
+    CK(cudaMalloc(&m->x_flag_tab, flg.size() * sizeof(uint32_t *)));
+    CK(cudaMemcpy(m->x_tri_tab, tri.data(), tri.size() * sizeof(int *), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(m->x_flag_tab, flg.data(), flg.size() * sizeof(uint32_t *), cudaMemcpyHostToDevice));
+    return ORBX_OK;
+}
+
+extern "C" int orbm_knn2_sharded_device(orbm_matcher *m, const uint8_t *d_query, int nq, const uint8_t *d_db_shard, int ndb_shard,
+                                        int index_base, int32_t *d_d1, int32_t *d_idx1, int32_t *d_d2,
+                                        int th_low, float ratio, int32_t *d_match, void *stream)
+{
+    if (!m || !m->x_tri_tab || nq < 1 || nq > m->x_qmax || !d_d1 || !d_idx1 || !d_d2) return ORBX_E_INVALID;
+    CK(cudaSetDevice(m->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : m->stream;
+    const uint32_t epoch = ++m->x_epoch;
+    const int par = (int)(epoch & 1u), W = m->x_world;
+    int *mine = (int *)m->x_buf + (size_t)par * 3 * m->x_qmax;       // this epoch's triple, arrays strided by x_qmax
+    int rc = orbm_knn2_device(m, d_query, nq, d_db_shard, ndb_shard, index_base, mine, mine + m->x_qmax, mine + 2 * (size_t)m->x_qmax, s);
+    if (rc) return rc;
+    launch_exchange_signal(m->x_flag_tab, m->x_rank, W, epoch, s);
+    unsigned char *own = m->x_buf;
+    launch_merge_peers((const int *const *)(m->x_tri_tab + (size_t)par * W), (const uint32_t *)(own + x_tri_bytes(m)), W, nq, (size_t)m->x_qmax,
+                       epoch, d_d1, d_idx1, d_d2, th_low, ratio, d_match, (int *)(own + x_tri_bytes(m) + 64 * sizeof(uint32_t)), s);
+    m->launches += 2;
+    CK(cudaGetLastError());
+    return ORBX_OK;
+}
+
+extern "C" int orbm_exchange_status(orbm_matcher *m)
+{
+    if (!m || !m->x_buf) return ORBX_E_INVALID;
+    CK(cudaSetDevice(m->device));
+    int err = 0;
+    CK(cudaMemcpy(&err, m->x_buf + x_tri_bytes(m) + 64 * sizeof(uint32_t), sizeof(int), cudaMemcpyDeviceToHost));
+    if (err) { std::snprintf(g_cuda_err, sizeof(g_cuda_err), "peer exchange timed out waiting for a shard"); return ORBX_E_CUDA; }
     return ORBX_OK;
 }
 

@@ -166,6 +166,65 @@ __global__ void k_merge_shards(const int *__restrict__ d1, const int *__restrict
     od1[i] = best; oidx1[i] = bidx; od2[i] = best2;
 }
 
+// ---- peer-memory exchange for the database-sharded search ----
+// Every rank scans its shard into its own exchange buffer, then stores the call's epoch into a flag word in
+// EVERY peer's buffer (NVLink P2P store).  The fused kernel below waits until all shards of this epoch are
+// published, then reads the world's (d1, idx1, d2) triples straight from peer memory over NVLink and folds
+// them (same rule as k_merge_shards) together with the TH_LOW / ratio acceptance: gather + merge + select in
+// one kernel, no NCCL call and no staging copy on the data path.
+__global__ void k_exchange_signal(uint32_t *const *__restrict__ peer_flags, int rank, int world, uint32_t epoch)
+{
+    const int p = threadIdx.x;
+    if (p < world) {
+        __threadfence_system();                                   // the triples of this epoch are written (earlier kernels, same stream)
+        *reinterpret_cast<volatile uint32_t *>(peer_flags[p] + rank) = epoch;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_merge_peers(const int *const *__restrict__ peer_tri, const volatile uint32_t *my_flags, int world, int nq, size_t arr_stride,
+              uint32_t epoch, int *__restrict__ od1, int *__restrict__ oidx1, int *__restrict__ od2,
+              int th_low, float ratio, int *__restrict__ match, int *__restrict__ err)
+{
+    __shared__ int s_ok;
+    if (threadIdx.x == 0) {
+        int ok = 1;
+        const long long t0 = clock64();
+        for (int r = 0; r < world && ok; ++r)
+            while ((int)(my_flags[r] - epoch) < 0) {              // peer r has not published this epoch yet
+                if (clock64() - t0 > 4000000000ll) { ok = 0; break; }   // ~2 s: report instead of hanging the GPU
+                __nanosleep(200);
+            }
+        __threadfence_system();
+        s_ok = ok;
+        if (!ok) *err = 1;
+    }
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq || !s_ok) return;
+    int best = INT_MAX, best2 = INT_MAX, bidx = -1;
+    for (int r = 0; r < world; ++r) {                             // ranks own ascending index ranges
+        const int *t = peer_tri[r];
+        const int id = __ldcv(t + arr_stride + i);                // peer memory: bypass L1
+        if (id < 0) continue;
+        const int a = __ldcv(t + i), b = __ldcv(t + 2 * arr_stride + i);
+        if (a < best) { best2 = best; best = a; bidx = id; } else if (a < best2) best2 = a;
+        if (b < best2) best2 = b;
+    }
+    od1[i] = best; oidx1[i] = bidx; od2[i] = best2;
+    if (match) match[i] = (bidx >= 0 && best <= th_low && (float)best < __fmul_rn((float)best2, ratio)) ? bidx : -1;
+}
+
+void launch_exchange_signal(uint32_t *const *peer_flags, int rank, int world, uint32_t epoch, cudaStream_t s)
+{
+    k_exchange_signal<<<1, 32, 0, s>>>(peer_flags, rank, world, epoch);
+}
+void launch_merge_peers(const int *const *peer_tri, const uint32_t *my_flags, int world, int nq, size_t arr_stride, uint32_t epoch,
+                        int *od1, int *oidx1, int *od2, int th_low, float ratio, int *match, int *err, cudaStream_t s)
+{
+    if (nq > 0) k_merge_peers<<<(nq + 255) / 256, 256, 0, s>>>(peer_tri, my_flags, world, nq, arr_stride, epoch, od1, oidx1, od2, th_low, ratio, match, err);
+}
+
 // ---- integer-pipe microbenchmarks (roofline denominators for k_knn2) ----
 template <int MODE>
 __global__ void __launch_bounds__(256)

@@ -34,3 +34,17 @@ def gather_triples(tri, world):
     # concatenated-along-dim-0 view: the layout both NCCL and gloo accept for _allgather_base
     dist.all_gather_into_tensor(out.view((world * tri.shape[0],) + tuple(tri.shape[1:])), tri.contiguous())
     return out
+
+
+def exchange_handles(matcher, max_queries, rank, world):
+    """Create this rank's peer-exchange buffer (orbm_exchange_create) and all-gather the 64-byte CUDA IPC handles.
+    Returns the handles in rank order, ready for matcher.exchange_open()."""
+    h = matcher.exchange_create(max_queries, rank, world)
+    if world == 1:
+        return [h]
+    mine = torch.tensor(list(h), dtype=torch.uint8)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    mine = mine.to(dev)
+    allh = torch.empty((world, 64), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(allh.view(world * 64), mine)
+    return [bytes(allh[r].cpu().tolist()) for r in range(world)]

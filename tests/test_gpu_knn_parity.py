@@ -73,3 +73,26 @@ def test_sharded_merge_and_ratio_select_equal_unsharded(orbx, oracle):
     p = parts.cpu().numpy()
     om = oracle.merge_shards(p[0], p[1], p[2])
     assert np.array_equal(om[0], o1) and np.array_equal(om[1], oi) and np.array_equal(om[2], o2)
+
+
+def test_peer_exchange_single_rank_equals_plain_knn(orbx, oracle):
+    """The fused wait + peer-read + merge + ratio kernel with world = 1 (own buffer only); N > 1 is exercised by
+    tools/sharded_knn_check.py under torchrun (needs several GPUs)."""
+    import torch
+    ndb, nq = 6000, 1500
+    db = synth_descriptor_db(ndb, dup_frac=0.03); q = synth_queries(db, nq)
+    m = orbx.Matcher(nq, ndb)
+    m.exchange_open([m.exchange_create(nq, 0, 1)])
+    dev = torch.device("cuda:0")
+    tq, tdb = torch.from_numpy(q).to(dev), torch.from_numpy(db).to(dev)
+    out = torch.empty((4, nq), dtype=torch.int32, device=dev)
+    s = torch.cuda.current_stream().cuda_stream
+    for _ in range(3):                               # several epochs: both parities of the double buffer
+        m.knn2_sharded_device(tq.data_ptr(), nq, tdb.data_ptr(), ndb, 0, out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(),
+                              50, 0.7, out[3].data_ptr(), s)
+    torch.cuda.synchronize()
+    m.exchange_status()
+    o1, oi, o2 = oracle.knn2(q, db, 0, 8)
+    got = out.cpu().numpy()
+    assert np.array_equal(got[0], o1) and np.array_equal(got[1], oi) and np.array_equal(got[2], o2)
+    assert np.array_equal(got[3], oracle.ratio_select(o1, oi, o2, 50, 0.7))
