@@ -311,7 +311,7 @@ def run_ours(args):
     algo = stage_algo_bytes()
     dom = int(np.argmax(stage_ms))
     dom_name = STAGES[dom]
-    nlaunch = {"level0": 1, "resize": NLEVELS - 1, "fast": 1, "octree": 1, "blur": NLEVELS, "describe": 1}[dom_name]
+    nlaunch = {"level0": 1, "resize": NLEVELS - 1, "fast": 1, "octree": 1, "blur": 1, "describe": 1}[dom_name]
     achieved = algo[dom_name] * BATCH / (stage_ms[dom] * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")

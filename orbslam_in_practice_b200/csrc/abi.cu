@@ -422,7 +422,7 @@ static int run_pipeline(orbx_extractor *ex, const uint8_t *d_imgs, size_t pitch,
     STAGE_EVENT(6);
 #undef STAGE_EVENT
     if (prof) ex->prof_calls++;
-    ex->launches += 1 + (g.nlevels - 1) + (g.total_cells > 0) + 1 + g.nlevels + 1;
+    ex->launches += 1 + (g.nlevels - 1) + (g.total_cells > 0) + 1 + 1 + 1;   // level0, resize chain, FAST, octree, blur, describe
     ex->last_frames = frame0 + nframes;
     CK(cudaGetLastError());
     return ORBX_OK;

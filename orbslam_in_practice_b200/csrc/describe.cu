@@ -29,16 +29,21 @@ __device__ __forceinline__ int reflect101d(int i, int n)
 // ---------------------------------------------------------------------------------------------
 constexpr int kBlurRows = 32;
 constexpr int kBlurWarps = 4;
+struct BlurRows { int first[ORBX_MAX_LEVELS + 1]; };   // first blockIdx.y of every level
 
 __device__ __forceinline__ uint32_t dp2(uint32_t a, uint32_t wts, uint32_t c) { return __dp2a_lo(a, wts, c); }
 
 __global__ void __launch_bounds__(32 * kBlurWarps)
-k_blur(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, uint8_t *__restrict__ blur, int level)
+k_blur(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, uint8_t *__restrict__ blur, const BlurRows rows)
 {
+    // one launch covers every level: blockIdx.y walks the concatenated row groups of all levels
+    int level = 0;
+#pragma unroll 1
+    for (int l = 1; l < g.nlevels; ++l) if ((int)blockIdx.y >= rows.first[l]) level = l;
     const LevelGeom &L = g.lv[level];
     const int lane = threadIdx.x, f = blockIdx.z + g.frame0;
-    const int y0 = (blockIdx.y * kBlurWarps + threadIdx.y) * kBlurRows;
-    if (y0 >= L.h) return;
+    const int y0 = (((int)blockIdx.y - rows.first[level]) * kBlurWarps + threadIdx.y) * kBlurRows;
+    if (y0 >= L.h || (int)blockIdx.x * 120 >= L.w) return;
     const int y1 = min(y0 + kBlurRows, L.h);
     const int wc_raw = (int)blockIdx.x * 30 + lane - 1;                 // word column (4 px) in the level, -1 = left halo
     const int wc_max = ((L.pitch - kPadX) >> 2) - 1;
@@ -95,11 +100,17 @@ k_blur(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, uint8_t *
 
 void launch_blur(const Geo &g, const DevBuffers &b, int nframes, cudaStream_t s)
 {
+    BlurRows rows;
+    int total = 0, strips = 1;
     for (int l = 0; l < g.nlevels; ++l) {
+        rows.first[l] = total;
+        total += (g.lv[l].h + kBlurRows * kBlurWarps - 1) / (kBlurRows * kBlurWarps);
         const int words = (g.lv[l].w + 3) / 4;
-        dim3 grd((words + 29) / 30, (g.lv[l].h + kBlurRows * kBlurWarps - 1) / (kBlurRows * kBlurWarps), nframes);
-        k_blur<<<grd, dim3(32, kBlurWarps), 0, s>>>(g, b.pyr, b.blur, l);
+        strips = strips > (words + 29) / 30 ? strips : (words + 29) / 30;
     }
+    for (int l = g.nlevels; l <= ORBX_MAX_LEVELS; ++l) rows.first[l] = total;
+    dim3 grd(strips, total, nframes);
+    k_blur<<<grd, dim3(32, kBlurWarps), 0, s>>>(g, b.pyr, b.blur, rows);
 }
 
 // ---------------------------------------------------------------------------------------------
