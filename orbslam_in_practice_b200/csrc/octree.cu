@@ -93,7 +93,7 @@ __device__ __forceinline__ int quadrant(uint32_t key, const Node &nd)
 __device__ __forceinline__ uint32_t comp(const uint4 &v, int q) { return q == 0 ? v.x : q == 1 ? v.y : q == 2 ? v.z : v.w; }
 
 template <int kOctThreads>
-__global__ void __launch_bounds__(kOctThreads)
+__global__ void __launch_bounds__(kOctThreads, kOctThreads == 256 ? 6 : 1)   // latency-bound: favour resident blocks over registers
 k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, const uint32_t *__restrict__ cell_slots,
          uint32_t *keysA_all, uint32_t *keysB_all, uint16_t *nodeA_all, uint16_t *nodeB_all, uint4 *scanE_all,
          int *__restrict__ ncand_out, uint32_t *__restrict__ kept_out, int *__restrict__ nkept_out)
@@ -110,7 +110,8 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
     Node *nodesN = nodes + NC;
     int *childCnt = reinterpret_cast<int *>(nodesN + NC);   // [4*NC]
     int *newIdx = childCnt + 4 * NC;                        // [4*NC]
-    int *rank = newIdx + 4 * NC;                            // [NC]
+    uint4 *nodeFirst = reinterpret_cast<uint4 *>(newIdx + 4 * NC);   // [NC] quadrant counters in front of a node's first key (16-B aligned)
+    int *rank = reinterpret_cast<int *>(nodeFirst + NC);   // [NC]
     int *arr = rank + NC;                                   // [NC] processing-order scratch
     int *ubase = arr + NC;                                  // [NC]
     unsigned char *nonEmpty = reinterpret_cast<unsigned char *>(ubase + NC); // [NC]
@@ -120,8 +121,12 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
     uint32_t *kB = keysB_all + (size_t)f * g.keys_per_frame + L.key_base;
     uint16_t *nA = nodeA_all + (size_t)f * g.keys_per_frame + L.key_base;
     uint16_t *nB = nodeB_all + (size_t)f * g.keys_per_frame + L.key_base;
-    uint4 *E = scanE_all + (size_t)f * (g.keys_per_frame + g.nlevels) + L.key_base + level;
-    int *celloff = reinterpret_cast<int *>(E);              // reused before the first scan
+    // per-key scratch carved from the 16 B/key scan region: own-quadrant rank (u32) and quadrant (u8)
+    uint32_t *E32 = reinterpret_cast<uint32_t *>(scanE_all + (size_t)f * (g.keys_per_frame + g.nlevels) + L.key_base + level);
+    unsigned char *qbuf = reinterpret_cast<unsigned char *>(E32 + L.max_cand + 1);
+    int *celloff = reinterpret_cast<int *>(E32);            // reused before the first scan
+    const int lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
 
     const int N = L.N;
     const int nCells = L.nCols * L.nRows;
@@ -141,7 +146,6 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
         }
         if (tid == 0) { S.n = carry; ncand_out[f * g.nlevels + level] = carry; }
         __syncthreads();
-        const int lane = tid & 31, warp = tid >> 5;
         for (int c = warp; c < nCells; c += kOctWarps) {
             const int cnt = ccount[c], off = celloff[c];
             for (int i = lane; i < cnt; i += 32) kB[off + i] = cslots[(size_t)c * L.cell_cap + i];
@@ -153,36 +157,56 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
     // ---- roots (:493-535): stable partition of kB by root index into kA ----
     const int nIni = L.nIni;
     if (nIni <= 0 || n == 0) { if (tid == 0) nkept_out[f * g.nlevels + level] = 0; return; }
+    // every warp streams one contiguous segment of the key array; ranks come from ballots + running warp-uniform
+    // counters, so a sweep over all keys costs two block barriers instead of two per 256 keys
+    const int seg = (((n + kOctWarps - 1) / kOctWarps) + 31) & ~31;
+    const int s0 = min(n, warp * seg), s1 = min(n, s0 + seg);
     {
         const float hX = L.hX;
         int placed = 0, nroots = 0;
-        for (int r = 0; r < nIni; ++r) {
-            int carry = 0;
-            for (int base = 0; base < n; base += kOctThreads) {
-                const int p = base + tid;
-                uint32_t key = 0; int flag = 0;
-                if (p < n) {
-                    key = kB[p];
-                    int ri = (int)((float)cand_x(key) / hX);      // :519
-                    ri = min(ri, nIni - 1);
-                    flag = (ri == r);
-                }
-                int tot;
-                const int ex = block_excl_scan<kOctWarps>(flag, S, tot);
-                if (flag) { kA[placed + carry + ex] = key; nA[placed + carry + ex] = (uint16_t)nroots; }
-                carry += tot;
+        for (int r0 = 0; r0 < nIni; r0 += 4) {                            // four roots per sweep
+            uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+            for (int p0 = s0; p0 < s1; p0 += 32) {
+                const int p = p0 + lane;
+                int q = 4;
+                if (p < s1) { const int ri = min((int)((float)cand_x(kB[p]) / hX), nIni - 1) - r0; if (ri >= 0 && ri < 4) q = ri; }   // :519
+                c0 += __popc(__ballot_sync(0xffffffffu, q == 0)); c1 += __popc(__ballot_sync(0xffffffffu, q == 1));
+                c2 += __popc(__ballot_sync(0xffffffffu, q == 2)); c3 += __popc(__ballot_sync(0xffffffffu, q == 3));
             }
-            if (carry > 0) {
-                if (tid == 0) {
-                    Node nd;
-                    nd.x0 = (short)(int)(hX * (float)r); nd.x1 = (short)(int)(hX * (float)(r + 1));  // :505-506
-                    nd.y0 = 0; nd.y1 = (short)L.regionH;
-                    nd.begin = placed; nd.count = carry;
-                    nodes[nroots] = nd;
+            if (lane == 0) S.warp_v[warp] = make_uint4(c0, c1, c2, c3);
+            __syncthreads();
+            uint4 run = make_uint4(0, 0, 0, 0), tot = run;
+            for (int w = 0; w < kOctWarps; ++w) { const uint4 t = S.warp_v[w]; if (w < warp) run = add4(run, t); tot = add4(tot, t); }
+            const int off0 = placed, off1 = off0 + tot.x, off2 = off1 + tot.y, off3 = off2 + tot.z;
+            const int id0 = nroots, id1 = id0 + (tot.x > 0), id2 = id1 + (tot.y > 0), id3 = id2 + (tot.z > 0);
+            for (int p0 = s0; p0 < s1; p0 += 32) {
+                const int p = p0 + lane;
+                int q = 4; uint32_t key = 0;
+                if (p < s1) { key = kB[p]; const int ri = min((int)((float)cand_x(key) / hX), nIni - 1) - r0; if (ri >= 0 && ri < 4) q = ri; }
+                const uint32_t b0 = __ballot_sync(0xffffffffu, q == 0), b1 = __ballot_sync(0xffffffffu, q == 1);
+                const uint32_t b2 = __ballot_sync(0xffffffffu, q == 2), b3 = __ballot_sync(0xffffffffu, q == 3);
+                if (q < 4) {
+                    const int dst = q == 0 ? off0 + run.x + __popc(b0 & lt) : q == 1 ? off1 + run.y + __popc(b1 & lt)
+                                  : q == 2 ? off2 + run.z + __popc(b2 & lt) : off3 + run.w + __popc(b3 & lt);
+                    kA[dst] = key; nA[dst] = (uint16_t)(q == 0 ? id0 : q == 1 ? id1 : q == 2 ? id2 : id3);
                 }
-                ++nroots;
-                placed += carry;
+                run.x += __popc(b0); run.y += __popc(b1); run.z += __popc(b2); run.w += __popc(b3);
             }
+            if (tid == 0) {
+                const int cnts[4] = { (int)tot.x, (int)tot.y, (int)tot.z, (int)tot.w }, offs[4] = { off0, off1, off2, off3 };
+                int id = nroots;
+                for (int k = 0; k < 4 && r0 + k < nIni; ++k)
+                    if (cnts[k] > 0) {
+                        Node nd;
+                        nd.x0 = (short)(int)(hX * (float)(r0 + k)); nd.x1 = (short)(int)(hX * (float)(r0 + k + 1));   // :505-506
+                        nd.y0 = 0; nd.y1 = (short)L.regionH;
+                        nd.begin = offs[k]; nd.count = cnts[k];
+                        nodes[id++] = nd;
+                    }
+            }
+            nroots = id3 + (tot.w > 0);
+            placed = off3 + tot.w;
+            __syncthreads();
         }
         if (tid == 0) S.size = nroots;
         __syncthreads();
@@ -194,25 +218,41 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
         const int size = S.size;
         const int prevSize = size;
 
-        // ---- A: stable ranks of every key inside its future child ----
+        // ---- A: stable rank of every key inside its future child (warp-streaming scan, see above) ----
         {
-            uint4 carry = make_uint4(0, 0, 0, 0);
-            for (int base = 0; base < n; base += kOctThreads) {
-                const int p = base + tid;
-                uint4 c = make_uint4(0, 0, 0, 0);
-                if (p < n) {
+            uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+            for (int p0 = s0; p0 < s1; p0 += 32) {
+                const int p = p0 + lane;
+                int q = 4;
+                if (p < s1) {
                     const Node nd = nodes[nA[p]];
-                    if (nd.count > 1) {
-                        const int q = quadrant(kA[p], nd);
-                        c.x = q == 0; c.y = q == 1; c.z = q == 2; c.w = q == 3;
-                    }
+                    if (nd.count > 1) q = quadrant(kA[p], nd);
+                    qbuf[p] = (unsigned char)q;
                 }
-                uint4 tot;
-                const uint4 ex = block_excl_scan4<kOctWarps>(c, S, tot);
-                if (p < n) E[p] = add4(carry, ex);
-                carry = add4(carry, tot);
+                c0 += __popc(__ballot_sync(0xffffffffu, q == 0)); c1 += __popc(__ballot_sync(0xffffffffu, q == 1));
+                c2 += __popc(__ballot_sync(0xffffffffu, q == 2)); c3 += __popc(__ballot_sync(0xffffffffu, q == 3));
             }
-            if (tid == 0) { E[n] = carry; S.nToExpand = 0; S.J = 0x7fffffff; S.pending = 0; }
+            if (lane == 0) S.warp_v[warp] = make_uint4(c0, c1, c2, c3);
+            if (tid == 0) { S.nToExpand = 0; S.J = 0x7fffffff; S.pending = 0; }
+            __syncthreads();
+            uint4 run = make_uint4(0, 0, 0, 0);
+            for (int w = 0; w < warp; ++w) run = add4(run, S.warp_v[w]);
+            for (int p0 = s0; p0 < s1; p0 += 32) {
+                const int p = p0 + lane;
+                const int q = p < s1 ? (int)qbuf[p] : 4;
+                const uint32_t b0 = __ballot_sync(0xffffffffu, q == 0), b1 = __ballot_sync(0xffffffffu, q == 1);
+                const uint32_t b2 = __ballot_sync(0xffffffffu, q == 2), b3 = __ballot_sync(0xffffffffu, q == 3);
+                if (q < 4) {
+                    const uint4 ex = make_uint4(run.x + __popc(b0 & lt), run.y + __popc(b1 & lt), run.z + __popc(b2 & lt), run.w + __popc(b3 & lt));
+                    E32[p] = comp(ex, q);
+                    const int gi = nA[p];
+                    const Node nd = nodes[gi];
+                    if (p == nd.begin) nodeFirst[gi] = ex;
+                    if (p == nd.begin + nd.count - 1)             // counters just behind the node's last key
+                        *reinterpret_cast<uint4 *>(childCnt + 4 * gi) = make_uint4(ex.x + (q == 0), ex.y + (q == 1), ex.z + (q == 2), ex.w + (q == 3));
+                }
+                run.x += __popc(b0); run.y += __popc(b1); run.z += __popc(b2); run.w += __popc(b3);
+            }
             __syncthreads();
         }
         // ---- B: child sizes ----
@@ -220,7 +260,7 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
             const Node nd = nodes[gi];
             int ne = 0;
             if (nd.count > 1) {
-                const uint4 e0 = E[nd.begin], e1 = E[nd.begin + nd.count];
+                const uint4 e0 = nodeFirst[gi], e1 = *reinterpret_cast<const uint4 *>(childCnt + 4 * gi);
                 const int c0 = e1.x - e0.x, c1 = e1.y - e0.y, c2 = e1.z - e0.z, c3 = e1.w - e0.w;
                 childCnt[4 * gi] = c0; childCnt[4 * gi + 1] = c1; childCnt[4 * gi + 2] = c2; childCnt[4 * gi + 3] = c3;
                 ne = (c0 > 0) + (c1 > 0) + (c2 > 0) + (c3 > 0);
@@ -343,11 +383,11 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
             const uint32_t key = kA[p];
             if (split[gi]) {
                 const Node nd = nodes[gi];
-                const int q = quadrant(key, nd);
+                const int q = qbuf[p];
                 int off = 0;
 #pragma unroll
                 for (int qq = 0; qq < 3; ++qq) if (qq < q) off += childCnt[4 * gi + qq];
-                const int np = nd.begin + off + (int)(comp(E[p], q) - comp(E[nd.begin], q));
+                const int np = nd.begin + off + (int)(E32[p] - comp(nodeFirst[gi], q));
                 kB[np] = key; nB[np] = (uint16_t)newIdx[4 * gi + q];
             } else {
                 kB[p] = key; nB[p] = (uint16_t)newIdx[4 * gi];
@@ -384,7 +424,7 @@ int octree_smem_bytes(const Geo &g)
     int nc = 0;
     for (int l = 0; l < g.nlevels; ++l) nc = nc > g.lv[l].node_cap ? nc : g.lv[l].node_cap;
     // 2 node tables + childCnt + newIdx (4 ints each) + rank + arr + ubase + 2 byte flags
-    return nc * (2 * (int)sizeof(Node) + 4 * 4 * 2 + 3 * 4 + 2) + 64;
+    return nc * (2 * (int)sizeof(Node) + 4 * 4 * 2 + 3 * 4 + 16 + 2) + 64;
 }
 
 int octree_configure(int smem_bytes)
