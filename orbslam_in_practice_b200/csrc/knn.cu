@@ -11,9 +11,11 @@
 #include "orbx_internal.cuh"
 
 #include <climits>
+#include <cstdlib>
 
 namespace orbx {
 
+constexpr int kDefaultCsa = 2;                // carry-save stages in front of the POPCs (see hamming_row)
 constexpr int kKnnThreads = 256;
 constexpr int kQPT = 4;                       // queries per thread
 constexpr int kQPB = kKnnThreads * kQPT;      // queries per block
@@ -29,7 +31,30 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-__global__ void __launch_bounds__(kKnnThreads)
+// Hamming distance of two 256-bit rows.  CSA = number of carry-save adder stages folded in front of the POPCs
+// (Harley-Seal): a CSA turns three words of equal weight into a sum word (a^b^c, one LOP3) and a carry word of
+// twice the weight (maj(a,b,c), one LOP3), trading one POPC (4 lanes/clk/SMSP) for two LOP3 (16 lanes/clk/SMSP).
+//   CSA 0: 8 POPC   CSA 2: 6 POPC + 4 LOP3   CSA 3: 5 POPC + 6 LOP3   CSA 4: 4 POPC + 8 LOP3
+template <int CSA>
+__device__ __forceinline__ int hamming_row(const uint32_t (&q)[8], const uint4 d0, const uint4 d1)
+{
+    const uint32_t x0 = q[0] ^ d0.x, x1 = q[1] ^ d0.y, x2 = q[2] ^ d0.z, x3 = q[3] ^ d0.w;
+    const uint32_t x4 = q[4] ^ d1.x, x5 = q[5] ^ d1.y, x6 = q[6] ^ d1.z, x7 = q[7] ^ d1.w;
+    if (CSA == 0)
+        return __popc(x0) + __popc(x1) + __popc(x2) + __popc(x3) + __popc(x4) + __popc(x5) + __popc(x6) + __popc(x7);
+    const uint32_t s0 = x0 ^ x1 ^ x2, c0 = (x0 & x1) | (x2 & (x0 | x1));
+    const uint32_t s1 = x3 ^ x4 ^ x5, c1 = (x3 & x4) | (x5 & (x3 | x4));
+    if (CSA == 2)
+        return __popc(s0) + __popc(s1) + __popc(x6) + __popc(x7) + 2 * (__popc(c0) + __popc(c1));
+    const uint32_t s2 = s0 ^ s1 ^ x6, c2 = (s0 & s1) | (x6 & (s0 | s1));
+    if (CSA == 3)
+        return __popc(s2) + __popc(x7) + 2 * (__popc(c0) + __popc(c1) + __popc(c2));
+    const uint32_t s3 = c0 ^ c1 ^ c2, c3 = (c0 & c1) | (c2 & (c0 | c1));
+    return __popc(s2) + __popc(x7) + 2 * __popc(s3) + 4 * __popc(c3);
+}
+
+template <int CSA>
+__global__ void __launch_bounds__(kKnnThreads, 4)
 k_knn2(const uint4 *__restrict__ query, int nq, const uint4 *__restrict__ db, int ndb, int seg_rows,
        uint2 *__restrict__ partial)
 {
@@ -78,8 +103,7 @@ k_knn2(const uint4 *__restrict__ query, int nq, const uint4 *__restrict__ db, in
             const uint4 d0 = tile[cur][2 * r], d1 = tile[cur][2 * r + 1];
 #pragma unroll
             for (int i = 0; i < kQPT; ++i) {
-                const int dist = __popc(q[i][0] ^ d0.x) + __popc(q[i][1] ^ d0.y) + __popc(q[i][2] ^ d0.z) + __popc(q[i][3] ^ d0.w) +
-                                 __popc(q[i][4] ^ d1.x) + __popc(q[i][5] ^ d1.y) + __popc(q[i][6] ^ d1.z) + __popc(q[i][7] ^ d1.w);
+                const int dist = hamming_row<CSA>(q[i], d0, d1);
                 const uint32_t key = ((uint32_t)dist << kIdxBits) | (rbase + (uint32_t)r);
                 const uint32_t hi = max(k1[i], key);
                 k1[i] = min(k1[i], key);
@@ -238,7 +262,7 @@ k_popc_bench(uint32_t *out, int iters, uint32_t seed)
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-            if (MODE == 0) a[i] = __popc(a[i]) + 0x01010101u * 0;          // POPC only (dependent per chain, 16 chains)
+            if (MODE == 0) a[i] = __popc(a[i]);                             // POPC only (dependent per chain, 16 chains)
             if (MODE == 1) a[i] = __popc(a[i] ^ k);                         // LOP3 + POPC
             if (MODE == 2) a[i] = (a[i] ^ k) + (a[i] >> 1);                 // ALU only (LOP3/SHF/IADD)
         }
@@ -276,7 +300,12 @@ void launch_knn2(const uint8_t *d_query, int nq, const uint8_t *d_db, int ndb, i
     if (ndb <= 0) { k_knn2_empty<<<(nq + 255) / 256, 256, 0, s>>>(nq, d1, idx1, d2); return; }
     dim3 grd((nq + kQPB - 1) / kQPB, nseg);
     if (ev) cudaEventRecord(ev[0], s);
-    k_knn2<<<grd, kKnnThreads, 0, s>>>((const uint4 *)d_query, nq, (const uint4 *)d_db, ndb, seg_rows, partial);
+    static int csa = -1;
+    if (csa < 0) { const char *e = getenv("ORBX_KNN_CSA"); csa = e ? atoi(e) : kDefaultCsa; }
+    if (csa == 0) k_knn2<0><<<grd, kKnnThreads, 0, s>>>((const uint4 *)d_query, nq, (const uint4 *)d_db, ndb, seg_rows, partial);
+    else if (csa == 2) k_knn2<2><<<grd, kKnnThreads, 0, s>>>((const uint4 *)d_query, nq, (const uint4 *)d_db, ndb, seg_rows, partial);
+    else if (csa == 3) k_knn2<3><<<grd, kKnnThreads, 0, s>>>((const uint4 *)d_query, nq, (const uint4 *)d_db, ndb, seg_rows, partial);
+    else k_knn2<4><<<grd, kKnnThreads, 0, s>>>((const uint4 *)d_query, nq, (const uint4 *)d_db, ndb, seg_rows, partial);
     if (ev) cudaEventRecord(ev[1], s);
     k_knn2_merge<<<(nq + 255) / 256, 256, 0, s>>>(partial, nq, nseg, seg_rows, index_base, d1, idx1, d2);
     if (ev) cudaEventRecord(ev[2], s);
