@@ -1,21 +1,21 @@
 // fast.cu -- the per-cell FAST-9 loop of ComputeKeyPointsOctTree (ORBextractor.cpp:745-786).
 //
-// One WARP per (cell, frame); eight cells per block, each warp with a private shared-memory
-// region, so there are no block barriers and no idle warps (ncu history, round 1: thread-per-pixel
-// = 406 lane-instructions/pixel, ALU bound; block-per-cell with work queues = 224; this = ~50).
-// The warp stages the cell's (wCell+6) x (hCell+6) u8 tile with aligned word loads, then:
-//   A  every interior pixel, lane = column: compass pre-test.  Every 9-arc of the 16-ring holds one
-//      pixel of each opposite pair, so a corner needs min(max(N,S),max(E,W)) > v+t (bright) or
-//      max(min(N,S),min(E,W)) < v-t (dark).  Survivors (~9 %) go to a queue with their polarity.
-//   B  queue, all lanes busy: the cornerScore of the candidate polarity as a sliding-window
-//      min over the circular ring with 3-input min/max (VIMNMX3).  A 9-arc of each polarity cannot
-//      coexist (18 > 16 ring pixels), so score0 = max_arcs(min_arc(s*d)) - 1 and the pixel is a
-//      corner at threshold t iff score0 >= t (SURVEY.md A3 identity: one score serves both
-//      iniThFAST and minThFAST).
-//   C  corners only: strict 3x3 non-max suppression *inside the cell* at iniTh and at minTh
-//      (neighbours below the threshold or outside the cell read 0) -> two bitmaps
-//   D  the reference's retry: use the iniTh bitmap unless it is empty (vKeysCell.empty()), then
-//      emit set bits in row-major order into the cell's slot array.
+// One WARP per (cell, frame); eight cells per block, each warp with a private shared-memory region, so
+// there are no block barriers and no idle warps.  ncu history, round 1 (lane-instructions per pixel):
+// thread-per-pixel 406 (ALU pipe 79 %), block-per-cell with work queues 224, warp-per-cell ~100, this ~80.
+// The warp stages the cell's (wCell+6) x (hCell+6) u8 tile with aligned 16-byte loads, then runs the
+// reference's two attempts literally -- cv::FAST(cell, iniThFAST) and, only if that returned nothing,
+// cv::FAST(cell, minThFAST) (:766-773).  One attempt at threshold t:
+//   A  every interior pixel, lane = column, verdicts collected in per-lane bitmasks: compass pre-test.
+//      Every 9-arc of the 16-ring holds one pixel of each opposite pair, so a corner needs
+//      min(max(N,S),max(E,W)) > v+t (bright) or max(min(N,S),min(E,W)) < v-t (dark).  Survivors are
+//      compacted into a queue with their polarity.
+//   B  queue, all lanes busy: the cornerScore of the candidate polarity as a sliding-window min over the
+//      circular ring with 3-input min/max (VIMNMX3).  A 9-arc of each polarity cannot coexist (18 > 16
+//      ring pixels), so score = max_arcs(min_arc(s*d)) - 1, and the pixel is a corner iff that max > t.
+//   C  corners only: strict 3x3 non-max suppression *inside the cell* (non-corners and pixels outside the
+//      cell read 0) -> bitmap
+//   D  emit set bits in row-major order into the cell's slot array.
 // The octree kernel concatenates cells in row-major cell order = the order of vToDistributeKeys.
 #include "orbx_internal.cuh"
 
@@ -24,7 +24,7 @@ namespace orbx {
 constexpr int kFastWarps = 8;
 constexpr int kFastThreads = kFastWarps * 32;
 // per-warp shared-memory layout, sized at launch from the largest cell of the geometry
-struct FastSmem { int tp, sp, tile_rows, npix_max, off_score, off_queue, off_corner, off_bm, per_warp; };
+struct FastSmem { int tp, sp, tile_rows, npix_max, off_score, off_queue, off_bm, per_warp; };
 
 __device__ __forceinline__ int min3(int a, int b, int c) { return __vimin3_s32(a, b, c); }
 __device__ __forceinline__ int max3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
@@ -226,7 +226,6 @@ void launch_fast(const Geo &g, const DevBuffers &b, int nframes, cudaStream_t s)
     sm.npix_max = (mw * mh + 1) / 2 * 2;
     sm.off_score = up16(sm.tile_rows * sm.tp);
     sm.off_queue = sm.off_score + up16((mh + 2) * sm.sp);
-    sm.off_corner = 0;
     sm.off_bm = sm.off_queue + up16(sm.npix_max * 2);
     sm.per_warp = sm.off_bm + up16(((sm.npix_max + 31) / 32) * 4);
     const size_t bytes = (size_t)sm.per_warp * kFastWarps;

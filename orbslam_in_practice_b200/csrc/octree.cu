@@ -5,8 +5,11 @@
 // where every node owns a contiguous range whose internal order is the candidate order, so a
 // DivideNode is a *stable 4-way partition inside the parent's range*.  The std::list is a node
 // table in list order.  One pass =
-//   A  block-wide exclusive scan over all keys of the one-hot quadrant vector (stable ranks)
-//   B  per node: child sizes from the scan at the range ends
+//   A  exclusive scan over all keys of the one-hot quadrant vector (stable ranks): every warp streams a
+//      contiguous segment, ranks come from ballots + running warp-uniform counters (two block barriers per
+//      sweep); per key only the rank in its own quadrant (u32) and the quadrant (u8) are stored, the full
+//      counter vectors only at the first and last key of every node
+//   B  per node: child sizes = counters behind the last key - counters in front of the first key
 //   C  choose the nodes to split and their processing rank
 //        phase 1 (:558-617): every >1-key node, in list order
 //        phase 2 (:629-691): >1-key nodes sorted by (size desc, later-created first = smaller
@@ -59,28 +62,6 @@ __device__ __forceinline__ int block_excl_scan(int v, OctShared &S, int &total)
 }
 
 __device__ __forceinline__ uint4 add4(uint4 a, uint4 b) { return make_uint4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
-
-template <int NW>
-__device__ __forceinline__ uint4 block_excl_scan4(uint4 v, OctShared &S, uint4 &total)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint4 inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        uint4 t;
-        t.x = __shfl_up_sync(0xffffffffu, inc.x, o); t.y = __shfl_up_sync(0xffffffffu, inc.y, o);
-        t.z = __shfl_up_sync(0xffffffffu, inc.z, o); t.w = __shfl_up_sync(0xffffffffu, inc.w, o);
-        if (lane >= o) inc = add4(inc, t);
-    }
-    if (lane == 31) S.warp_v[warp] = inc;
-    __syncthreads();
-    uint4 off = make_uint4(0, 0, 0, 0), tot = off;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) { const uint4 t = S.warp_v[w]; if (w < warp) off = add4(off, t); tot = add4(tot, t); }
-    __syncthreads();
-    total = tot;
-    return make_uint4(off.x + inc.x - v.x, off.y + inc.y - v.y, off.z + inc.z - v.z, off.w + inc.w - v.w);
-}
 
 __device__ __forceinline__ int quadrant(uint32_t key, const Node &nd)
 {

@@ -55,7 +55,7 @@ struct Geo {
     int total_cells;          // cells per frame, all levels
     int capacity;             // output keypoint slots per frame
     int kept_total;           // kept slots per frame (= capacity)
-    unsigned long long pyr_frame_total, blur_frame_total; // unused when per-level strides are used
+    unsigned long long pyr_frame_total, blur_frame_total; // allocation sizes (bytes, all frames) of the pyramid / blur buffers
     unsigned long long slots_per_frame, keys_per_frame;
     LevelGeom lv[ORBX_MAX_LEVELS];
     int umax[16];
@@ -69,7 +69,7 @@ struct DevBuffers {
     uint32_t *cell_slots;// [F][slots_per_frame]
     uint32_t *keysA, *keysB;   // [F][keys_per_frame]
     uint16_t *nodeA, *nodeB;   // [F][keys_per_frame]
-    uint4 *scanE;        // [F][keys_per_frame + nlevels]
+    uint4 *scanE;        // [F][keys_per_frame + nlevels] octree per-key scratch (16 B/key: u32 rank + u8 quadrant are carved from it)
     int *ncand;          // [F][nlevels]
     uint32_t *kept;      // [F][kept_total]
     int *nkept;          // [F][nlevels]
