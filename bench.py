@@ -194,7 +194,8 @@ def run_reference(args):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * BATCH / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": "256x 640x480 frames, nfeatures=1000, scale 1.2, 8 levels, FAST 20/7 (bounded sample per step)"},
+            "config": {"workload": WORKLOAD_DESC, "frames_per_gpu": BATCH,
+                       "note": "each step is a bounded sample of this workload on the host cores (see cpu_baseline.sample)"},
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
