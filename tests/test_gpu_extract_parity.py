@@ -179,3 +179,35 @@ def test_undistort_keypoints(orbx, oracle):
     ex.undistort_keypoints_device(d_in.data_ptr(), d_out.data_ptr(), n, cam, [0, 0, 0, 0, 0])
     torch.cuda.synchronize()
     assert torch.equal(d_in, d_out)
+
+
+@pytest.mark.parametrize("w,h,nf", [(333, 257, 600), (801, 603, 1500), (1023, 767, 1000), (752, 480, 1200), (97, 65, 100)])
+def test_odd_frame_sizes(orbx, oracle, w, h, nf):
+    img = synth_frame(w + h, w, h)
+    ex = orbx.Extractor(nfeatures=nf, max_width=w, max_height=h, max_batch=1)
+    oex = oracle.OracleExtractor(nfeatures=nf)
+    kps, desc, counts = ex.extract_host(img)
+    _compare_frame(oracle, ex, oex, img, 0, kps, desc, counts)
+
+
+def test_strided_host_input_and_two_handles(orbx, oracle):
+    """Row pitch > width and a frame stride that is not rows * pitch; two extractors alive at once
+    (the reference keeps an nFeatures and a 2*nFeatures extractor, src/Tracking.cpp:47-48)."""
+    big = np.zeros((3, 500, 700), np.uint8)
+    frames = synth_batch([40, 41, 42])
+    big[:, 10:490, 30:670] = frames
+    view = big[::2, 10:490, 30:670]                                  # frames 0 and 2, pitch 700, stride 2*500*700
+    ex1 = orbx.Extractor(nfeatures=1000, max_width=640, max_height=480, max_batch=2)
+    ex2 = orbx.Extractor(nfeatures=2000, max_width=640, max_height=480, max_batch=2)
+    k1, d1, c1 = ex1.extract_host(view)
+    k2, d2, c2 = ex2.extract_host(view)
+    o1, o2 = oracle.OracleExtractor(1000), oracle.OracleExtractor(2000)
+    for slot, f in enumerate((0, 2)):
+        _compare_frame(oracle, ex1, o1, frames[f], slot, k1, d1, c1, check_stages=False)
+        _compare_frame(oracle, ex2, o2, frames[f], slot, k2, d2, c2, check_stages=False)
+    # eager 19-px border mode gives the same keypoints and a device-resident border
+    ex1.set_pyramid_border(True)
+    k3, d3, c3 = ex1.extract_host(view)
+    assert np.array_equal(c1, c3) and np.array_equal(d1, d3)
+    oex = oracle.OracleExtractor(1000); oex(frames[0])
+    assert np.array_equal(ex1.level(0, 3, border=19), oracle.reflect101_border(oex.level(3), 19))
