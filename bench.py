@@ -315,18 +315,27 @@ def run_ours(args):
     nlaunch = {"level0": 1, "resize": NLEVELS - 1, "fast": 1, "octree": 1, "blur": 1, "describe": 1}[dom_name]
     achieved = algo[dom_name] * BATCH / (stage_ms[dom] * 1e-3) / 1e9
     traffic = None
+    issue = None
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.exists(tpath) and args.workload == "vga" and BATCH == 256:          # dram bytes of this stage from the committed ncu --set full capture (same workload)
         tj = json.load(open(tpath))
         if dom_name in tj["bytes_per_step"]:
             traffic = tj["bytes_per_step"][dom_name] / max(1, tj["launches"][dom_name])
+            winst = tj.get("warp_instructions_per_step", {}).get(dom_name)
+            if winst:       # instruction-issue view of the same kernel: what actually bounds it
+                sm_hz = (clocks.get("sm_mhz") or 1965.0) * 1e6
+                peak_issue = torch.cuda.get_device_properties(dev).multi_processor_count * 4 * sm_hz
+                issue = {"warp_instructions_per_step": winst, "source": "smsp__inst_executed.sum, same ncu capture",
+                         "achieved_gwarpinst_s": winst / (stage_ms[dom] * 1e-3) / 1e9, "peak_gwarpinst_s": peak_issue / 1e9,
+                         "frac": winst / (stage_ms[dom] * 1e-3) / peak_issue,
+                         "peak": "SMs x 4 schedulers x SM clock (1 warp instruction per scheduler per clock)"}
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / peaks["hbm_gbs"], "traffic": traffic,
                 "traffic_source": "profiles/r01_traffic.json (ncu dram__bytes_read+write per launch)" if traffic else None,
                 "algorithmic_bytes_per_launch": algo[dom_name] * BATCH / nlaunch, "peak_source": peak_src,
                 "note": "extraction is integer-issue bound, not HBM bound (DESIGN.md section 4): the HBM fraction is reported for completeness; ncu instruction counts are in profiles/",
                 "launches_in_stage": nlaunch, "stage_ms": {n: float(m) for n, m in zip(STAGES, stage_ms)},
-                "whole_pipeline_frac": value / world * ALGO_BYTES_PER_FRAME / 1e9 / peaks["hbm_gbs"]}
+                "whole_pipeline_frac": value / world * ALGO_BYTES_PER_FRAME / 1e9 / peaks["hbm_gbs"], "issue": issue}
 
     # ---------------- SearchForInitialization on consecutive frame pairs ----------------
     search_init = None
