@@ -22,6 +22,14 @@ __device__ __forceinline__ int reflect101(int i, int n)
     return i;
 }
 
+// reflect-101 with at most one reflection per side in the common case (border <= 19 < level size)
+__device__ __forceinline__ int reflect_fast(int i, int n)
+{
+    i = i < 0 ? -i : i;
+    i = i >= n ? 2 * (n - 1) - i : i;
+    return (unsigned)i < (unsigned)n ? i : reflect101(i, n);
+}
+
 // ---------------------------------------------------------------------------------------------
 // level 0: input frames -> bordered level-0 buffers.  One thread = one aligned 16-byte chunk of a
 // padded destination row (the interior starts at byte kPadX = 32 of a 64-byte aligned pitch).
@@ -108,7 +116,7 @@ k_resize(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr_src, uin
     const int X0 = chunk * 4 - kPadX;
     if (chunk * 4 >= D.pitch || X0 + 3 < -B || X0 >= D.w + B) return;
     const int2 *tabx = tables + D.tabx;
-    int o0[4], o1[4], c0[4], c1[4];
+    int o0[4], c0[4], c1[4];
     if (X0 >= 0 && X0 + 3 < D.w) {
         // interior chunk: the four table entries are one aligned 32-byte run
         const int4 t01 = __ldg(reinterpret_cast<const int4 *>(tabx + X0));
@@ -121,56 +129,62 @@ k_resize(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr_src, uin
             o0[k] = t.x; c0[k] = t.y;
         }
     }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        o1[k] = min(o0[k] + 1, S.w - 1);
-        c1[k] = c0[k] >> 16; c0[k] = (short)(c0[k] & 0xffff);
-    }
     // source and destination levels live in the same allocation but never overlap: separate restrict
     // pointers let the compiler hoist the next row's loads above this row's store
     const uint8_t *__restrict__ src = pyr_src + S.base + (size_t)f * S.frame_stride + (size_t)kPadY * S.pitch + kPadX;
     uint8_t *__restrict__ dst = pyr_dst + D.base + (size_t)f * D.frame_stride + (size_t)chunk * 4;
+    // per-pixel column pointers.  The second tap reads the byte after the first: where OpenCV clamps the
+    // offset at the right edge the table has fraction 0 (c1 == 0), so the byte behind the row (padding
+    // inside the pitch) is multiplied by zero instead of being clamped away.
+    const uint8_t *col[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        col[k] = src + o0[k];
+        c1[k] = c0[k] >> 16; c0[k] = (short)(c0[k] & 0xffff);
+    }
     const int2 *taby = tables + D.taby;
     const int Ybase = (int)blockIdx.y * kResizeRows - B;
+    const int spitch = S.pitch;
     // the y-table entry of the NEXT row is fetched one iteration ahead: otherwise every row pays two dependent
-    // global-load latencies (table entry -> source row pointer -> pixels); ncu showed 50 % of the stall samples
-    // on the pixel loads
-    int2 ty_next = __ldg(taby + reflect101(min(Ybase, D.h + B - 1), D.h));
+    // global-load latencies (table entry -> source row pointer -> pixels)
+    int2 ty_next = __ldg(taby + reflect_fast(min(Ybase, D.h + B - 1), D.h));
     int prev_sy1 = -0x7fffffff;
-    int hp[4] = { 0, 0, 0, 0 };
+    int hp[4] = { 0, 0, 0, 0 };                           // horizontally interpolated lower source row, already >> 4
+    uint8_t *drow = dst + (size_t)(Ybase + kPadY) * D.pitch;
 #pragma unroll 2
-    for (int r = 0; r < kResizeRows; ++r) {
+    for (int r = 0; r < kResizeRows; ++r, drow += D.pitch) {
         const int Y = Ybase + r;
         if (Y >= D.h + B) break;
         const int2 ty = ty_next;
-        ty_next = __ldg(taby + reflect101(min(Y + 1, D.h + B - 1), D.h));
+        ty_next = __ldg(taby + reflect_fast(min(Y + 1, D.h + B - 1), D.h));
         const int sy0 = min(max(ty.x, 0), S.h - 1), sy1 = min(max(ty.x + 1, 0), S.h - 1);
         const int cy0 = (short)(ty.y & 0xffff), cy1 = ty.y >> 16;
-        const uint8_t *r0 = src + (size_t)sy0 * S.pitch, *r1 = src + (size_t)sy1 * S.pitch;
         int h0[4], h1[4];
         if (sy0 == prev_sy1) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) h0[k] = hp[k];
         } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) h0[k] = r0[o0[k]] * c0[k] + r0[o1[k]] * c1[k];
+            for (int k = 0; k < 4; ++k) { const uint8_t *p = col[k] + (size_t)(unsigned)(sy0 * spitch); h0[k] = (p[0] * c0[k] + p[1] * c1[k]) >> 4; }
         }
         if (sy1 == sy0) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) h1[k] = h0[k];
         } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) h1[k] = r1[o0[k]] * c0[k] + r1[o1[k]] * c1[k];
+            for (int k = 0; k < 4; ++k) { const uint8_t *p = col[k] + (size_t)(unsigned)(sy1 * spitch); h1[k] = (p[0] * c0[k] + p[1] * c1[k]) >> 4; }
         }
+        // ((b0 * (H0 >> 4)) >> 16) + ((b1 * (H1 >> 4)) >> 16) + 2) >> 2 never leaves [0, 255]: H <= 255 * 2049 and b0 + b1 <= 2049
+        // give at most 1020 + 2 before the last shift, so OpenCV's saturate_cast is the identity here
         uint32_t out = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int v = (((cy0 * (h0[k] >> 4)) >> 16) + ((cy1 * (h1[k] >> 4)) >> 16) + 2) >> 2;
-            out |= (uint32_t)min(max(v, 0), 255) << (8 * k);
+            const uint32_t v = (uint32_t)(((cy0 * h0[k]) >> 16) + ((cy1 * h1[k]) >> 16) + 2) >> 2;
+            out |= v << (8 * k);
             hp[k] = h1[k];
         }
         prev_sy1 = sy1;
-        *reinterpret_cast<uint32_t *>(dst + (size_t)(Y + kPadY) * D.pitch) = out;
+        *reinterpret_cast<uint32_t *>(drow) = out;
     }
 }
 

@@ -7,7 +7,7 @@ base=synth_batch(range(32)); fr=np.ascontiguousarray(np.concatenate([base]*8))
 ex=_lib.Extractor(1000,1.2,8,20,7,W,H,B,0); cap=ex.capacity
 hf=torch.from_numpy(fr).pin_memory(); hk=torch.empty((B,cap,7)).pin_memory(); hd=torch.empty((B,cap,32),dtype=torch.uint8).pin_memory(); hc=torch.empty(B,dtype=torch.int32).pin_memory()
 def run(): ex.extract_host_ptr(hf.data_ptr(),W,W*H,W,H,B,hk.data_ptr(),hd.data_ptr(),hc.data_ptr())
-for ch in (2,4,8):
+for ch in (3,4,5,6,8):
     os.environ['ORBX_HOST_CHUNKS']=str(ch)
     for _ in range(3): run()
     t=time.perf_counter()
