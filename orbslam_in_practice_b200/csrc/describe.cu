@@ -2,6 +2,8 @@
 // (:27-54, :422-429), computeOrbDescriptor (:57-97) and the operator() epilogue (:1036-1064).
 #include "orbx_internal.cuh"
 
+#include <mutex>
+
 namespace orbx {
 
 __device__ __forceinline__ int reflect101d(int i, int n)
@@ -30,11 +32,15 @@ __device__ __forceinline__ int reflect101d(int i, int n)
 constexpr int kBlurRows = 32;
 constexpr int kBlurWarps = 4;
 struct BlurRows { int first[ORBX_MAX_LEVELS + 1]; };   // first blockIdx.y of every level
+// DP2A weight words (low byte x low 16-bit lane, next byte x high lane).  Passed as a kernel parameter so that they
+// are constant-bank operands; as literals the compiler re-materialised all of them in registers in every row iteration.
+struct BlurWeights { uint32_t k0k2, z_k1, k3k1, k2k0, z_k0, k2k2, k0_z, k1k3, k1_z, half; };
 
 __device__ __forceinline__ uint32_t dp2(uint32_t a, uint32_t wts, uint32_t c) { return __dp2a_lo(a, wts, c); }
 
 __global__ void __launch_bounds__(32 * kBlurWarps)
-k_blur(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, uint8_t *__restrict__ blur, const BlurRows rows)
+k_blur(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, uint8_t *__restrict__ blur, const BlurRows rows,
+       const __grid_constant__ BlurWeights W)
 {
     // one launch covers every level: blockIdx.y walks the concatenated row groups of all levels
     int level = 0;
@@ -52,9 +58,7 @@ k_blur(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, uint8_t *
     uint8_t *dst = blur + L.blur_base + (size_t)f * L.blur_frame_stride + 4 * wc;
     const bool writer = lane >= 1 && lane <= 30 && 4 * wc_raw < L.w;
 
-    // weights packed for DP2A: low byte multiplies the low 16-bit lane, next byte the high lane
     constexpr uint32_t K0 = 18, K1 = 34, K2 = 48, K3 = 56;             // k4 = k2, k5 = k1, k6 = k0
-#define W2(a, b) ((uint32_t)(a) | ((uint32_t)(b) << 8))
     uint32_t lo[7], hi[7];                                             // sliding window of split source rows
     const uint8_t *rp = src + (ptrdiff_t)(y0 - 3) * L.pitch;           // walks down the source rows
 #pragma unroll
@@ -71,7 +75,9 @@ k_blur(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, uint8_t *
 #pragma unroll
         for (int j = 0; j < 7; ++j) {
             const int y = yb + j;
-            if (y < y1) {
+            // no branch around the body: rows past y1 are computed from valid (allocated) memory and simply not
+            // stored, which keeps the shuffles convergent (the compiler bracketed them with WARPSYNC otherwise)
+            {
                 // window slot (j + 6) % 7 receives source row y + 3; rows y-3 .. y+3 are slots j .. j+6 (mod 7)
                 const uint32_t w = wn0;
                 wn0 = wn1;
@@ -85,17 +91,16 @@ k_blur(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, uint8_t *
                 const uint32_t plo = __shfl_up_sync(0xffffffffu, vlo, 1), phi = __shfl_up_sync(0xffffffffu, vhi, 1);     // column c-1
                 const uint32_t nlo = __shfl_down_sync(0xffffffffu, vlo, 1), nhi = __shfl_down_sync(0xffffffffu, vhi, 1); // column c+1
                 // horizontal 7-tap on 16-bit values with 32-bit sums (+ rounding), SURVEY.md A2
-                uint32_t o0 = dp2(phi, W2(K0, K2), 32768u); o0 = dp2(plo, W2(0, K1), o0); o0 = dp2(vlo, W2(K3, K1), o0); o0 = dp2(vhi, W2(K2, K0), o0);
-                uint32_t o1 = dp2(plo, W2(0, K0), 32768u);  o1 = dp2(phi, W2(0, K1), o1); o1 = dp2(vlo, W2(K2, K2), o1); o1 = dp2(vhi, W2(K3, K1), o1); o1 = dp2(nlo, W2(K0, 0), o1);
-                uint32_t o2 = dp2(phi, W2(0, K0), 32768u);  o2 = dp2(vlo, W2(K1, K3), o2); o2 = dp2(vhi, W2(K2, K2), o2); o2 = dp2(nlo, W2(K1, 0), o2); o2 = dp2(nhi, W2(K0, 0), o2);
-                uint32_t o3 = dp2(vlo, W2(K0, K2), 32768u); o3 = dp2(vhi, W2(K1, K3), o3); o3 = dp2(nlo, W2(K2, K0), o3); o3 = dp2(nhi, W2(K1, 0), o3);
+                uint32_t o0 = dp2(phi, W.k0k2, W.half); o0 = dp2(plo, W.z_k1, o0); o0 = dp2(vlo, W.k3k1, o0); o0 = dp2(vhi, W.k2k0, o0);
+                uint32_t o1 = dp2(plo, W.z_k0, W.half); o1 = dp2(phi, W.z_k1, o1); o1 = dp2(vlo, W.k2k2, o1); o1 = dp2(vhi, W.k3k1, o1); o1 = dp2(nlo, W.k0_z, o1);
+                uint32_t o2 = dp2(phi, W.z_k0, W.half); o2 = dp2(vlo, W.k1k3, o2); o2 = dp2(vhi, W.k2k2, o2); o2 = dp2(nlo, W.k1_z, o2); o2 = dp2(nhi, W.k0_z, o2);
+                uint32_t o3 = dp2(vlo, W.k0k2, W.half); o3 = dp2(vhi, W.k1k3, o3); o3 = dp2(nlo, W.k2k0, o3); o3 = dp2(nhi, W.k1_z, o3);
                 const uint32_t out = __byte_perm(__byte_perm(o0, o1, 0x0062), __byte_perm(o2, o3, 0x0062), 0x5410);
-                if (writer) *reinterpret_cast<uint32_t *>(dp) = out;
+                if (writer && y < y1) *reinterpret_cast<uint32_t *>(dp) = out;
                 dp += L.blur_pitch;
             }
         }
     }
-#undef W2
 }
 
 void launch_blur(const Geo &g, const DevBuffers &b, int nframes, cudaStream_t s)
@@ -110,7 +115,10 @@ void launch_blur(const Geo &g, const DevBuffers &b, int nframes, cudaStream_t s)
     }
     for (int l = g.nlevels; l <= ORBX_MAX_LEVELS; ++l) rows.first[l] = total;
     dim3 grd(strips, total, nframes);
-    k_blur<<<grd, dim3(32, kBlurWarps), 0, s>>>(g, b.pyr, b.blur, rows);
+    auto W2 = [](uint32_t a, uint32_t b) { return a | (b << 8); };
+    const uint32_t K0 = 18, K1 = 34, K2 = 48, K3 = 56;
+    const BlurWeights W = { W2(K0, K2), W2(0, K1), W2(K3, K1), W2(K2, K0), W2(0, K0), W2(K2, K2), W2(K0, 0), W2(K1, K3), W2(K1, 0), 32768u };
+    k_blur<<<grd, dim3(32, kBlurWarps), 0, s>>>(g, b.pyr, b.blur, rows, W);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -265,6 +273,8 @@ void launch_describe(const Geo &g, const DevBuffers &b, int nframes, orbx_keypoi
 {
     int dev = 0;
     cudaGetDevice(&dev);
+    static std::mutex pattern_mutex;                      // handles are per-thread objects; this table is process-wide
+    std::lock_guard<std::mutex> lock(pattern_mutex);
     if (dev < 64 && !g_pattern_dev[dev]) {
         static const signed char h_pattern[1024] = {
 #include "orb_pattern_31.inc"

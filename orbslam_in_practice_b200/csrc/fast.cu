@@ -229,11 +229,8 @@ void launch_fast(const Geo &g, const DevBuffers &b, int nframes, cudaStream_t s)
     sm.off_bm = sm.off_queue + up16(sm.npix_max * 2);
     sm.per_warp = sm.off_bm + up16(((sm.npix_max + 31) / 32) * 4);
     const size_t bytes = (size_t)sm.per_warp * kFastWarps;
-    static size_t configured = 0;
-    if (bytes > 48 * 1024 && bytes > configured) {
-        cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        configured = bytes;
-    }
+    // per-device function attribute; a handful of nanoseconds, so no process-wide caching (one handle per device each)
+    if (bytes > 48 * 1024) cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     dim3 grd((g.total_cells + kFastWarps - 1) / kFastWarps, nframes);
     k_fast_cells<<<grd, kFastThreads, bytes, s>>>(g, b.pyr, b.cell_count, b.cell_slots, sm);
 }

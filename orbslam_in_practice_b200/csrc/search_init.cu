@@ -236,11 +236,8 @@ size_t search_init_smem_bytes(int cap, int sort_n)
 int launch_search_init(const SearchInitArgs &a, cudaStream_t s)
 {
     const size_t smem = search_init_smem_bytes(a.cap, a.sort_n);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        if (cudaFuncSetAttribute(k_search_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-        configured = smem;
-    }
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(k_search_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     k_search_init<<<a.npairs, kSiThreads, smem, s>>>(a);
     return 0;
 }
