@@ -211,3 +211,35 @@ def test_strided_host_input_and_two_handles(orbx, oracle):
     assert np.array_equal(c1, c3) and np.array_equal(d1, d3)
     oex = oracle.OracleExtractor(1000); oex(frames[0])
     assert np.array_equal(ex1.level(0, 3, border=19), oracle.reflect101_border(oex.level(3), 19))
+
+
+@pytest.mark.parametrize("params", [dict(nfeatures=50, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7),
+                                    dict(nfeatures=3000, scale_factor=1.1, nlevels=12, ini_th=12, min_th=5),
+                                    dict(nfeatures=700, scale_factor=2.0, nlevels=3, ini_th=40, min_th=40),
+                                    dict(nfeatures=400, scale_factor=1.2, nlevels=1, ini_th=7, min_th=20)])
+def test_parameter_corners(orbx, oracle, params):
+    """Tiny and huge quotas (phase-2-only and never-phase-2 octrees), many / one level, iniTh < minTh."""
+    img = synth_frame(77)
+    ex = orbx.Extractor(max_width=640, max_height=480, max_batch=1, **params)
+    oex = oracle.OracleExtractor(**params)
+    kps, desc, counts = ex.extract_host(img)
+    _compare_frame(oracle, ex, oex, img, 0, kps, desc, counts)
+
+
+def test_wide_panorama_many_octree_roots(orbx, oracle):
+    """Aspect ratio 8:1 -> nIni = 8 root nodes (ORBextractor.cpp:493): two sweeps of the 4-roots-per-sweep partition."""
+    img = synth_frame(5, 1600, 200)
+    ex = orbx.Extractor(nfeatures=1500, max_width=1600, max_height=200, max_batch=1)
+    oex = oracle.OracleExtractor(nfeatures=1500)
+    kps, desc, counts = ex.extract_host(img)
+    _compare_frame(oracle, ex, oex, img, 0, kps, desc, counts)
+
+
+def test_portrait_frame_without_octree_roots(orbx, oracle):
+    """width/height < 0.5 -> nIni = round(...) = 0: the reference divides by zero there; oracle and device both
+    return no keypoints for such levels (documented deviation)."""
+    img = synth_frame(6, 200, 640)
+    ex = orbx.Extractor(nfeatures=500, max_width=200, max_height=640, max_batch=1)
+    oex = oracle.OracleExtractor(nfeatures=500)
+    kps, desc, counts = ex.extract_host(img)
+    _compare_frame(oracle, ex, oex, img, 0, kps, desc, counts)
