@@ -299,11 +299,44 @@ def run_ours(args):
     for _ in range(K):
         step_host()                                   # synchronous: returns after the D2H completed
     torch.cuda.synchronize()
+    e2e_sync_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    barrier()
+    assert int(h_cnt.sum()) == kp_total, "host path and device path disagree"
+
+    # Same steps through the split call (orbx_extract_host_begin / _end) on two handles: step k+1's upload is in flight
+    # while step k's kernels run.  Every step still uploads its own 256 frames and downloads its own results.
+    ex_b = _lib.Extractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, W, H, BATCH, local)
+    slots = []
+    for e in (ex, ex_b):
+        slots.append((e, torch.from_numpy(frames_np).pin_memory(), torch.empty((BATCH, cap, 7), dtype=torch.float32).pin_memory(),
+                      torch.empty((BATCH, cap, 32), dtype=torch.uint8).pin_memory(), torch.empty(BATCH, dtype=torch.int32).pin_memory()))
+
+    def begin(i):
+        e, hf, hk, hd, hc = slots[i & 1]
+        e.extract_host_begin(hf.data_ptr(), W, W * H, W, H, BATCH, hk.data_ptr(), hd.data_ptr(), hc.data_ptr())
+
+    def end(i):
+        slots[i & 1][0].extract_host_end()
+
+    def run_pipelined(n):
+        begin(0)
+        for i in range(n):
+            if i + 1 < n:
+                begin(i + 1)
+            end(i)
+
+    run_pipelined(Wm + 1)
+    barrier()
+    t0 = time.perf_counter()
+    run_pipelined(K)
+    torch.cuda.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
     barrier()
+    assert int(slots[0][4].sum()) == kp_total and int(slots[1][4].sum()) == kp_total, "pipelined host path disagrees"
+    del ex_b
     clocks = sampler.stop()
     e2e_value = world * BATCH * K / (e2e_ms * 1e-3)
-    assert int(h_cnt.sum()) == kp_total, "host path and device path disagree"
+    e2e_sync_value = world * BATCH * K / (e2e_sync_ms * 1e-3)
     h2d = BATCH * W * H
     d2h = BATCH * cap * (28 + 32) + BATCH * 4
 
@@ -380,7 +413,10 @@ def run_ours(args):
                            "l2": "per-step working set (inputs 79 MB + pyramid/blur 0.6 GB) exceeds the 126 MB L2; no flush needed",
                            "parallelism": "frames batch-sharded, no collective"},
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": e2e_ms / K, "api": "orbx_extract_host (C ABI), pinned host buffers"},
+                        "ms_per_step": e2e_ms / K,
+                        "api": "orbx_extract_host_begin/_end (C ABI) on two handles, pinned host buffers: consecutive steps overlap "
+                               "(upload of step k+1 during the kernels of step k); every step uploads its frames and downloads its results",
+                        "single_blocking_call": {"value": e2e_sync_value, "ms_per_step": e2e_sync_ms / K, "api": "orbx_extract_host"}},
                 "gpu_launches": int(launches),
                 "roofline": roofline, "clocks": clocks}
         if match is not None:

@@ -92,6 +92,16 @@ int orbx_extract_host(orbx_extractor *ex, const uint8_t *imgs, size_t row_pitch,
                       int width, int height, int nframes,
                       orbx_keypoint *kps, uint8_t *desc, int32_t *counts);
 
+/* Split form of orbx_extract_host for pipelining across handles: _begin enqueues the uploads, kernels and downloads
+ * of the batch and returns at once; _end waits for them (the output buffers are valid after _end).  With two handles,
+ * begin(A, batch k+1) can be issued before end(B, batch k), so A's PCIe upload overlaps B's kernels.  The host
+ * buffers must stay alive and unmodified between _begin and _end, and should be pinned (pageable memory makes the
+ * copies synchronous).  One batch in flight per handle. */
+int orbx_extract_host_begin(orbx_extractor *ex, const uint8_t *imgs, size_t row_pitch, size_t frame_stride,
+                            int width, int height, int nframes,
+                            orbx_keypoint *kps, uint8_t *desc, int32_t *counts);
+int orbx_extract_host_end(orbx_extractor *ex);
+
 /* Same with DEVICE pointers; asynchronous on `stream` (a cudaStream_t; NULL = the handle's stream). */
 int orbx_extract_device(orbx_extractor *ex, const uint8_t *d_imgs, size_t row_pitch, size_t frame_stride,
                         int width, int height, int nframes,

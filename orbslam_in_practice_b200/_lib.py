@@ -21,7 +21,7 @@ CAND_DTYPE = np.dtype([("x", "<i2"), ("y", "<i2"), ("score", "<i4")])
 ABI_SYMBOLS = [
     "orbx_strerror", "orbx_last_cuda_error", "orbx_version", "orbx_device_count",
     "orbx_create", "orbx_destroy", "orbx_nlevels", "orbx_capacity", "orbx_tables",
-    "orbx_extract_host", "orbx_extract_device", "orbx_set_pyramid_border", "orbx_set_input_format", "orbx_undistort_keypoints_device",
+    "orbx_extract_host", "orbx_extract_host_begin", "orbx_extract_host_end", "orbx_extract_device", "orbx_set_pyramid_border", "orbx_set_input_format", "orbx_undistort_keypoints_device",
     "orbx_level_dims", "orbx_download_level", "orbx_level_device_ptr",
     "orbx_download_candidates", "orbx_download_kept", "orbx_max_candidates", "orbx_launch_count",
     "orbx_set_profiling", "orbx_stage_times", "orbm_set_profiling", "orbm_knn2_times",
@@ -63,6 +63,8 @@ def load():
     L.orbx_capacity.argtypes = [vp]
     L.orbx_tables.argtypes = [vp] * 7
     L.orbx_extract_host.argtypes = [vp, vp, sz, sz, i32, i32, i32, vp, vp, vp]
+    L.orbx_extract_host_begin.argtypes = [vp, vp, sz, sz, i32, i32, i32, vp, vp, vp]
+    L.orbx_extract_host_end.argtypes = [vp]
     L.orbx_extract_device.argtypes = [vp, vp, sz, sz, i32, i32, i32, vp, vp, vp, vp]
     L.orbx_set_pyramid_border.argtypes = [vp, i32]
     L.orbx_set_input_format.argtypes = [vp, i32, i32]
@@ -169,6 +171,12 @@ class Extractor:
 
     def extract_host_ptr(self, img_ptr, row_pitch, frame_stride, W, H, F, kps_ptr, desc_ptr, counts_ptr):
         check(load().orbx_extract_host(self.h, img_ptr, row_pitch, frame_stride, W, H, F, kps_ptr, desc_ptr, counts_ptr))
+
+    def extract_host_begin(self, img_ptr, row_pitch, frame_stride, W, H, F, kps_ptr, desc_ptr, counts_ptr):
+        check(load().orbx_extract_host_begin(self.h, img_ptr, row_pitch, frame_stride, W, H, F, kps_ptr, desc_ptr, counts_ptr))
+
+    def extract_host_end(self):
+        check(load().orbx_extract_host_end(self.h))
 
     def extract_device(self, img_ptr, row_pitch, frame_stride, W, H, F, kps_ptr, desc_ptr, counts_ptr, stream=0):
         check(load().orbx_extract_device(self.h, img_ptr, row_pitch, frame_stride, W, H, F, kps_ptr, desc_ptr,

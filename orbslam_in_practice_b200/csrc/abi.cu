@@ -445,9 +445,28 @@ extern "C" int orbx_extract_device(orbx_extractor *ex, const uint8_t *d_imgs, si
     return run_pipeline(ex, d_imgs, row_pitch, frame_stride, width, height, 0, nframes, d_kps, d_desc, d_counts, s);
 }
 
+extern "C" int orbx_extract_host_end(orbx_extractor *ex)
+{
+    if (!ex) return ORBX_E_INVALID;
+    CK(cudaSetDevice(ex->device));
+    CK(cudaStreamSynchronize(ex->s_d2h));
+    CK(cudaStreamSynchronize(ex->stream));
+    CK(cudaStreamSynchronize(ex->stream2));
+    return ORBX_OK;
+}
+
 extern "C" int orbx_extract_host(orbx_extractor *ex, const uint8_t *imgs, size_t row_pitch, size_t frame_stride,
                                  int width, int height, int nframes,
                                  orbx_keypoint *kps, uint8_t *desc, int32_t *counts)
+{
+    int rc = orbx_extract_host_begin(ex, imgs, row_pitch, frame_stride, width, height, nframes, kps, desc, counts);
+    if (rc) return rc;
+    return orbx_extract_host_end(ex);
+}
+
+extern "C" int orbx_extract_host_begin(orbx_extractor *ex, const uint8_t *imgs, size_t row_pitch, size_t frame_stride,
+                                       int width, int height, int nframes,
+                                       orbx_keypoint *kps, uint8_t *desc, int32_t *counts)
 {
     if (!ex || nframes < 0 || !counts) return ORBX_E_INVALID;
     if (nframes == 0) return ORBX_OK;
@@ -507,10 +526,7 @@ extern "C" int orbx_extract_host(orbx_extractor *ex, const uint8_t *imgs, size_t
         CK(cudaMemcpyAsync(desc + f0 * cap * 32, ex->buf.out_desc + f0 * cap * 32, (size_t)n * cap * 32, cudaMemcpyDeviceToHost, ex->s_d2h));
         CK(cudaMemcpyAsync(counts + f0, ex->buf.out_counts + f0, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost, ex->s_d2h));
     }
-    CK(cudaStreamSynchronize(ex->s_d2h));
-    CK(cudaStreamSynchronize(ex->stream));
-    CK(cudaStreamSynchronize(ex->stream2));
-    return ORBX_OK;
+    return ORBX_OK;                                  // copies and kernels are in flight: orbx_extract_host_end waits
 }
 
 extern "C" int orbx_level_dims(const orbx_extractor *ex, int level, int *width, int *height)

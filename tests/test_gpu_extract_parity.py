@@ -243,3 +243,30 @@ def test_portrait_frame_without_octree_roots(orbx, oracle):
     oex = oracle.OracleExtractor(nfeatures=500)
     kps, desc, counts = ex.extract_host(img)
     _compare_frame(oracle, ex, oex, img, 0, kps, desc, counts)
+
+
+def test_begin_end_pipelining_across_two_handles(orbx, oracle):
+    """orbx_extract_host_begin/_end: two batches in flight on two handles give the same results as blocking calls."""
+    import torch
+    batches = [synth_batch([50, 51, 52]), synth_batch([53, 54, 55])]
+    exs = [orbx.Extractor(max_width=640, max_height=480, max_batch=3) for _ in range(2)]
+    cap = exs[0].capacity
+    bufs = []
+    for b in batches:
+        hf = torch.from_numpy(b).pin_memory()
+        bufs.append((hf, torch.zeros((3, cap, 7)).pin_memory(), torch.zeros((3, cap, 32), dtype=torch.uint8).pin_memory(),
+                     torch.zeros(3, dtype=torch.int32).pin_memory()))
+    for rep in range(3):
+        for e, (hf, hk, hd, hc) in zip(exs, bufs):
+            e.extract_host_begin(hf.data_ptr(), 640, 640 * 480, 640, 480, 3, hk.data_ptr(), hd.data_ptr(), hc.data_ptr())
+        for e in exs:
+            e.extract_host_end()
+    oex = oracle.OracleExtractor()
+    for b, e, (hf, hk, hd, hc) in zip(batches, exs, bufs):
+        kps = hk.numpy().view(np.float32).reshape(3, cap, 7)
+        ks = np.zeros((3, cap), orbx.KEYPOINT_DTYPE)
+        for i, fld in enumerate(("x", "y", "size", "angle", "response")):
+            ks[fld] = kps[:, :, i]
+        ks["octave"] = kps[:, :, 5].view(np.int32); ks["class_id"] = kps[:, :, 6].view(np.int32)
+        for f in range(3):
+            _compare_frame(oracle, e, oex, b[f], f, ks, hd.numpy(), hc.numpy(), check_stages=False)
