@@ -8,7 +8,7 @@ CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "liborbx.so")
 SOURCES = ["abi.cu", "pyramid.cu", "fast.cu", "octree.cu", "describe.cu", "knn.cu", "search_init.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--fmad=true", "-shared", "-cudart", "static"]
+              "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--fmad=true", "-shared", "-cudart", "static", "-ldl"]
 
 
 def needs_build():

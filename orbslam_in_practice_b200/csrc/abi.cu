@@ -11,6 +11,15 @@
 #include <new>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: named ranges for Nsight timelines, no-ops without a tool attached
+
+namespace {
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+} // namespace
+
 namespace orbx {
 // knn.cu
 int knn_segments(int nq, int ndb, int sm_count, int *seg_rows_out);
@@ -385,6 +394,7 @@ static int ensure_geometry(orbx_extractor *ex, int w, int h)
 static int run_pipeline(orbx_extractor *ex, const uint8_t *d_imgs, size_t pitch, size_t fstride, int w, int h, int frame0, int nframes,
                         orbx_keypoint *d_kps, uint8_t *d_desc, int *d_counts, cudaStream_t s)
 {
+    NvtxRange range("orbx::extract (level0, resize x7, FAST, octree, blur, describe)");
     int rc = ensure_geometry(ex, w, h);
     if (rc) return rc;
     Geo g = ex->geo;
@@ -749,6 +759,7 @@ extern "C" int orbm_knn2_device(orbm_matcher *m, const uint8_t *d_query, int nq,
     if (nq > m->max_q || ndb > m->max_db) return ORBX_E_CAPACITY;
     if (((uintptr_t)d_query | (uintptr_t)d_db) & 15) return ORBX_E_INVALID;   // 16-byte vector loads
     if (nq == 0) return ORBX_OK;
+    NvtxRange range("orbm::knn2 (scan + segment merge)");
     CK(cudaSetDevice(m->device));
     cudaStream_t s = stream ? (cudaStream_t)stream : m->stream;
     int seg_rows = 0;

@@ -85,7 +85,10 @@ k_fast_cells(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr,
             for (int r = rr; r < ch; r += 4)
                 *reinterpret_cast<uint4 *>(tile + r * kTP + sub * 16) = __ldg(reinterpret_cast<const uint4 *>(img + (size_t)r * L.pitch) + sub);
     }
-    const int nbm = (iw * ih + 31) >> 5;
+    // NMS bitmap: one 32- or 64-bit row of bits per pixel row (bit = column), so bit order is row-major and the
+    // emission needs no division
+    const int bsh = iw <= 32 ? 5 : 6;
+    const int nbm = ih << (bsh - 5);
     const int minTh = g.min_th, iniTh = g.ini_th;
     uint32_t *bm = reinterpret_cast<uint32_t *>(mine + sm.off_bm);
 
@@ -181,7 +184,7 @@ k_fast_cells(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr,
             const int nmax = max3(max3((int)q[-kSP - 1], (int)q[-kSP], (int)q[-kSP + 1]), max3((int)q[-1], (int)q[1], (int)q[kSP - 1]),
                                   max((int)q[kSP], (int)q[kSP + 1]));
             if (s > nmax) {
-                const int idx = y * iw + x;
+                const int idx = (y << bsh) + x;
                 atomicOr(&bm[idx >> 5], 1u << (idx & 31));
                 mine_any = true;
             }
@@ -206,7 +209,7 @@ k_fast_cells(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr,
                 const int b = __ffs(bits) - 1;
                 bits &= bits - 1;
                 const int idx = wi * 32 + b;
-                const int y = idx / iw, x = idx - y * iw;
+                const int y = idx >> bsh, x = idx & ((1 << bsh) - 1);
                 // keypoint in level coordinates relative to (16,16): cell pixel (x+3, y+3) + (j*wCell, i*hCell)
                 slots[pos++] = pack_cand(x + 3 + cj * L.wCell, y + 3 + ci * L.hCell, score[(y + 1) * kSP + (x + 1)]);
             }
@@ -227,7 +230,7 @@ void launch_fast(const Geo &g, const DevBuffers &b, int nframes, cudaStream_t s)
     sm.off_score = up16(sm.tile_rows * sm.tp);
     sm.off_queue = sm.off_score + up16((mh + 2) * sm.sp);
     sm.off_bm = sm.off_queue + up16(sm.npix_max * 2);
-    sm.per_warp = sm.off_bm + up16(((sm.npix_max + 31) / 32) * 4);
+    sm.per_warp = sm.off_bm + up16(mh * 2 * 4);
     const size_t bytes = (size_t)sm.per_warp * kFastWarps;
     // per-device function attribute; a handful of nanoseconds, so no process-wide caching (one handle per device each)
     if (bytes > 48 * 1024) cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
