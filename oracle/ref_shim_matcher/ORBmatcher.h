@@ -1,7 +1,14 @@
 /*
- * ORBmatcher.h (shim) -- same class declaration as the reference's include/ORBmatcher.h:8-32 minus the two
- * KeyFrame/MapPoint-typed stubs with empty bodies (:22,:24), on top of the Frame shim.  Lets the reference's
- * src/ORBmatcher.cpp compile unmodified.  TEST INFRASTRUCTURE ONLY.
+ * Declaration shim for the matcher translation unit.  TEST INFRASTRUCTURE ONLY.
+ *
+ * oracle/Makefile compiles the reference's src/ORBmatcher.cpp where it lies; that file defines four members
+ * of ORBSlam::ORBmatcher (constructor inline in the header, SearchForInitialization, DescriptorDistance,
+ * ComputeThreeMaxima) and two static constants.  This header declares exactly those so the definitions have
+ * something to attach to.  The KeyFrame / MapPoint entry points of the reference header (include/ORBmatcher.h:22,24)
+ * have empty bodies there and are not on the measured path, so they are not declared.
+ *
+ * Member order and the two data members' types must match what the .cpp's definitions use; nothing else here
+ * is taken from the reference header.
  */
 #ifndef ORBMATCHER_H
 #define ORBMATCHER_H
@@ -9,18 +16,35 @@
 #include "Frame.h"
 
 namespace ORBSlam {
-class ORBmatcher {
-public:
-    ORBmatcher(float nnratio = 0.6, bool checkOri = true) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
-    int SearchForInitialization(Frame &F1, Frame &F2, std::vector<cv::Point2f> &vbPrevMatched, std::vector<int> &vnMatches12, int windowSize);
-    int DescriptorDistance(const cv::Mat &a, const cv::Mat &b);
-    void ComputeThreeMaxima(std::vector<int> *histo, const int L, int &ind1, int &ind2, int &ind3);
 
-private:
-    static const int HISTO_LENGTH;
-    static const int TH_LOW;
+class ORBmatcher {
+    /* state the definitions read: ratio of the best-2 test and the rotation-histogram switch */
     float mfNNratio;
     bool mbCheckOrientation;
+
+    /* defined at the top of the .cpp */
+    static const int TH_LOW;
+    static const int HISTO_LENGTH;
+
+public:
+    typedef std::vector<int> IntVec;
+    typedef std::vector<cv::Point2f> PointVec;
+
+    explicit ORBmatcher(float ratio = 0.6, bool useOrientation = true)
+    {
+        mfNNratio = ratio;
+        mbCheckOrientation = useOrientation;
+    }
+
+    /* 32-byte Hamming distance */
+    int DescriptorDistance(const cv::Mat &lhs, const cv::Mat &rhs);
+
+    /* three largest bins of a rotation histogram with `bins` entries */
+    void ComputeThreeMaxima(IntVec *histogram, const int bins, int &first, int &second, int &third);
+
+    /* windowed best-2 search between the initial and the current frame */
+    int SearchForInitialization(Frame &initial, Frame &current, PointVec &prevMatched, IntVec &matches12, int window);
 };
+
 } // namespace ORBSlam
 #endif
