@@ -224,6 +224,44 @@ int orbm_search_init_host(orbm_matcher *m, const orbx_keypoint *kp1, const uint8
                           float *prev_matched, int32_t *matches12, int32_t *nmatches,
                           int window, float nnratio, int check_orientation, int width, int height, int literal_gridid_bug);
 
+/* Windowed search with per-query windows: the generalisation of the kernel above that the reference's two empty
+ * matcher entry points need (SearchByProjection include/ORBmatcher.h:24, SearchByBoW :22).
+ * The window query is Frame::GetFeaturesInArea(x, y, r, minLevel, maxLevel) as the reference wrote it
+ * (src/Frame.cpp:219-271, level filter :245-258); the loop around it follows upstream ORB-SLAM2's frame-to-frame
+ * SearchByProjection, because the reference's body is empty -- parity for that loop is pinned only through the
+ * SearchForInitialization instance of the same kernel.
+ *   query q of frame F1 searches F2 around d_centers[q] (the projected position; a NaN x skips the query) with
+ *   r = radius * level_scale[octave(q)], candidate octaves in [octave(q) - level_below, octave(q) + level_above]
+ *   (level_below < 0: from level 0; level_above < 0: no upper bound), queries with an octave outside
+ *   [query_level_min, query_level_max] are skipped.
+ *   gate 0: SearchForInitialization's rule (a candidate already matched at distance <= dist is skipped; a better
+ *           match displaces the earlier one, src/ORBmatcher.cpp:49-50,69-77)
+ *   gate 1: first come, first served (a matched F2 keypoint is skipped by later queries; upstream SearchByProjection)
+ *   accept: best <= th_dist, and best < (float)best2 * nnratio unless nnratio <= 0
+ *   check_orientation: rotation-histogram filter (src/ORBmatcher.cpp:79-118);  update_centers: write the matched
+ *   keypoint's position back into d_centers (:121-124). */
+typedef struct {
+    float radius;
+    float level_scale[16];
+    int32_t query_level_min, query_level_max;
+    int32_t level_below, level_above;
+    int32_t gate;
+    int32_t th_dist;
+    float nnratio;
+    int32_t check_orientation;
+    int32_t update_centers;
+    int32_t width, height;
+    int32_t literal_gridid_bug;
+} orbm_window_params;
+
+int orbm_search_window_device(orbm_matcher *m, const orbx_keypoint *d_kps, const uint8_t *d_desc, const int32_t *d_counts,
+                              int capacity, const int32_t *d_pair_a, const int32_t *d_pair_b, int npairs,
+                              float *d_centers, int32_t *d_matches12, int32_t *d_nmatches,
+                              const orbm_window_params *params, void *d_workspace, size_t workspace_bytes, void *stream);
+int orbm_search_window_host(orbm_matcher *m, const orbx_keypoint *kp1, const uint8_t *desc1, int n1,
+                            const orbx_keypoint *kp2, const uint8_t *desc2, int n2,
+                            float *centers, int32_t *matches12, int32_t *nmatches, const orbm_window_params *params);
+
 /* Integer-pipe microbenchmark used for the kNN roofline: runs a dependent-free POPC loop on every
  * SM and returns measured 32-bit POPC results per second (device-event timed). */
 int orbm_popc_peak(int device, double *popc_per_second, double *lop3_per_second);

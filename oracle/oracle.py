@@ -80,6 +80,8 @@ def lib():
     L.orbo_knn2_mt.argtypes = [vp, i32, vp, i32, i32, vp, vp, vp, i32]
     L.orbo_ratio_select.argtypes = [vp, vp, vp, i32, i32, f32, vp]
     L.orbo_merge_shards.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp]
+    L.orbo_search_window.restype = i32
+    L.orbo_search_window.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp, vp]
     L.orbo_search_for_initialization.restype = i32
     L.orbo_search_for_initialization.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp, i32, f32, i32, i32, i32, i32]
     L.orbo_extract_many.restype = i32
@@ -285,6 +287,39 @@ def search_for_initialization(kp1, desc1, kp2, desc2, prev_matched, window=100, 
                                              _p(prev), _p(m12), window, nnratio, int(check_orientation),
                                              width, height, int(literal_bug))
     return n, m12, prev
+
+
+class WindowParams(C.Structure):
+    """orbo_window_params (same layout as orbm_window_params in include/orbx.h)."""
+    _fields_ = [("radius", C.c_float), ("level_scale", C.c_float * 16),
+                ("query_level_min", C.c_int32), ("query_level_max", C.c_int32),
+                ("level_below", C.c_int32), ("level_above", C.c_int32), ("gate", C.c_int32), ("th_dist", C.c_int32),
+                ("nnratio", C.c_float), ("check_orientation", C.c_int32), ("update_centers", C.c_int32),
+                ("width", C.c_int32), ("height", C.c_int32), ("literal_gridid_bug", C.c_int32)]
+
+
+def window_params(radius, level_scale=None, query_levels=(0, 15), level_below=1, level_above=1, gate=1, th_dist=100,
+                  nnratio=0.0, check_orientation=True, update_centers=False, width=640, height=480, literal_bug=False):
+    p = WindowParams()
+    p.radius = radius
+    ls = list(level_scale) if level_scale is not None else []
+    for i in range(16):
+        p.level_scale[i] = ls[i] if i < len(ls) else 1.0
+    p.query_level_min, p.query_level_max = query_levels
+    p.level_below, p.level_above, p.gate, p.th_dist, p.nnratio = level_below, level_above, gate, th_dist, nnratio
+    p.check_orientation, p.update_centers = int(check_orientation), int(update_centers)
+    p.width, p.height, p.literal_gridid_bug = width, height, int(literal_bug)
+    return p
+
+
+def search_window(kp1, desc1, kp2, desc2, centers, params):
+    kp1 = np.ascontiguousarray(kp1, KEYPOINT_DTYPE)
+    kp2 = np.ascontiguousarray(kp2, KEYPOINT_DTYPE)
+    desc1, desc2 = _u8(desc1), _u8(desc2)
+    cen = np.ascontiguousarray(centers, np.float32).copy()
+    m12 = np.zeros(len(kp1), np.int32)
+    n = lib().orbo_search_window(_p(kp1), _p(desc1), len(kp1), _p(kp2), _p(desc2), len(kp2), _p(cen), _p(m12), C.byref(params))
+    return n, m12, cen
 
 
 def extract_many(imgs, nthreads, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):

@@ -1017,6 +1017,114 @@ int orbo_search_for_initialization(const orbo_keypoint *kp1, const uint8_t *desc
     return nmatches;
 }
 
+/* Windowed search with per-query windows.  The window query is the reference's
+ * Frame::GetFeaturesInArea(x, y, r, minLevel, maxLevel) (Frame.cpp:219-271, level filter :245-258); the loop around it is
+ * SearchForInitialization's (ORBmatcher.cpp:9-126) with the gate / acceptance made parameters, which also covers upstream
+ * ORB-SLAM2's frame-to-frame SearchByProjection (the reference's own body is empty, include/ORBmatcher.h:24 -- PARITY
+ * UNPINNED for gate 1; gate 0 with the SearchForInitialization parameters must equal orbo_search_for_initialization,
+ * which is pinned against the reference TU). */
+int orbo_search_window(const orbo_keypoint *kp1, const uint8_t *desc1, int n1,
+                       const orbo_keypoint *kp2, const uint8_t *desc2, int n2,
+                       float *centers, int32_t *m12, const orbo_window_params *P)
+{
+    const float minX = 0, maxX = (float)P->width, minY = 0, maxY = (float)P->height;
+    const float wInv = (float)FRAME_GRID_COLS / (maxX - minX), hInv = (float)FRAME_GRID_ROWS / (maxY - minY);
+    gcell *grid = (gcell *)calloc(FRAME_GRID_COLS * FRAME_GRID_ROWS, sizeof(gcell));
+    for (int i = 0; i < n2; ++i) {
+        double x = kp2[i].x, y = kp2[i].y;
+        int ix = (int)round((x - minX) * wInv);
+        int iy = (int)round((y - (P->literal_gridid_bug ? maxY : minY)) * hInv);
+        if (ix < 0 || ix >= FRAME_GRID_COLS || iy < 0 || iy >= FRAME_GRID_ROWS) continue;
+        gcell *c = &grid[ix * FRAME_GRID_ROWS + iy];
+        if (c->n == c->cap) { c->cap = c->cap ? c->cap * 2 : 8; c->idx = (int *)realloc(c->idx, sizeof(int) * (size_t)c->cap); }
+        c->idx[c->n++] = i;
+    }
+    int nmatches = 0;
+    for (int i = 0; i < n1; ++i) m12[i] = -1;
+    int *rot[HISTO_LENGTH]; int rotn[HISTO_LENGTH];
+    for (int i = 0; i < HISTO_LENGTH; ++i) { rot[i] = (int *)malloc(sizeof(int) * (size_t)(n1 + 1)); rotn[i] = 0; }
+    const float factor = HISTO_LENGTH / 360.0f;
+    int *matchedDist = (int *)malloc(sizeof(int) * (size_t)(n2 + 1));
+    int *m21 = (int *)malloc(sizeof(int) * (size_t)(n2 + 1));
+    for (int i = 0; i < n2; ++i) { matchedDist[i] = INT_MAX; m21[i] = -1; }
+    int *vind = (int *)malloc(sizeof(int) * (size_t)(n2 + 1));
+
+    for (int i1 = 0; i1 < n1; ++i1) {
+        const int level1 = kp1[i1].octave;
+        if (level1 < P->query_level_min || level1 > P->query_level_max) continue;
+        const float x = centers[2 * i1], y = centers[2 * i1 + 1];
+        if (x != x) continue;                                       /* no projection for this query */
+        const float r = P->radius * P->level_scale[level1 & 15];
+        const int minLevel = P->level_below < 0 ? 0 : level1 - P->level_below;
+        const int maxLevel = P->level_above < 0 ? -1 : level1 + P->level_above;
+        int nv = 0;
+        do {
+            int cx0 = (int)floorf((x - minX - r) * wInv); if (cx0 < 0) cx0 = 0;
+            if (cx0 >= FRAME_GRID_COLS) break;
+            int cx1 = (int)ceilf((x - minX + r) * wInv); if (cx1 > FRAME_GRID_COLS - 1) cx1 = FRAME_GRID_COLS - 1;
+            if (cx1 < 0) break;
+            int cy0 = (int)floorf((y - minY - r) * hInv); if (cy0 < 0) cy0 = 0;
+            if (cy0 >= FRAME_GRID_ROWS) break;
+            int cy1 = (int)ceilf((y - minY + r) * hInv); if (cy1 > FRAME_GRID_ROWS - 1) cy1 = FRAME_GRID_ROWS - 1;
+            if (cy1 < 0) break;
+            const int bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+            for (int ix = cx0; ix <= cx1; ++ix)
+                for (int iy = cy0; iy <= cy1; ++iy) {
+                    const gcell *c = &grid[ix * FRAME_GRID_ROWS + iy];
+                    for (int j = 0; j < c->n; ++j) {
+                        const orbo_keypoint *k = &kp2[c->idx[j]];
+                        if (bCheckLevels) {
+                            if (k->octave < minLevel) continue;
+                            if (maxLevel >= 0 && k->octave > maxLevel) continue;
+                        }
+                        const float dx = k->x - x, dy = k->y - y;
+                        if (fabsf(dx) < r && fabsf(dy) < r) vind[nv++] = c->idx[j];
+                    }
+                }
+        } while (0);
+        if (nv == 0) continue;
+        const uint8_t *d1 = desc1 + (size_t)i1 * 32;
+        int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+        for (int t = 0; t < nv; ++t) {
+            const int i2 = vind[t];
+            const int dist = orbo_descriptor_distance(d1, desc2 + (size_t)i2 * 32);
+            if (P->gate == 0 ? matchedDist[i2] <= dist : m21[i2] >= 0) continue;
+            if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+            else if (dist < bestDist2) bestDist2 = dist;
+        }
+        if (bestIdx2 < 0 || bestDist > P->th_dist) continue;
+        if (P->nnratio > 0.f && !(bestDist < (float)bestDist2 * P->nnratio)) continue;
+        if (m21[bestIdx2] >= 0) { m12[m21[bestIdx2]] = -1; nmatches--; }
+        m12[i1] = bestIdx2; m21[bestIdx2] = i1; matchedDist[bestIdx2] = bestDist; nmatches++;
+        if (P->check_orientation) {
+            float rotv = kp1[i1].angle - kp2[bestIdx2].angle;
+            if (rotv < 0.0) rotv += 360.0f;
+            int bin = (int)roundf(rotv * factor);
+            if (bin == HISTO_LENGTH) bin = 0;
+            rot[bin][rotn[bin]++] = i1;
+        }
+    }
+    if (P->check_orientation) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        compute_three_maxima(rotn, HISTO_LENGTH, &ind1, &ind2, &ind3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int j = 0; j < rotn[i]; ++j) {
+                const int idx1 = rot[i][j];
+                if (m12[idx1] >= 0) { m12[idx1] = -1; nmatches--; }
+            }
+        }
+    }
+    if (P->update_centers)
+        for (int i1 = 0; i1 < n1; ++i1)
+            if (m12[i1] >= 0) { centers[2 * i1] = kp2[m12[i1]].x; centers[2 * i1 + 1] = kp2[m12[i1]].y; }
+    for (int i = 0; i < FRAME_GRID_COLS * FRAME_GRID_ROWS; ++i) free(grid[i].idx);
+    free(grid);
+    for (int i = 0; i < HISTO_LENGTH; ++i) free(rot[i]);
+    free(matchedDist); free(m21); free(vind);
+    return nmatches;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* multi-thread extraction helper for the CPU baseline                                        */
 /* ------------------------------------------------------------------------------------------ */

@@ -127,6 +127,27 @@ int orbo_search_for_initialization(const orbo_keypoint *kp1, const uint8_t *desc
                                    int window, float nnratio, int check_orientation,
                                    int width, int height, int literal_bug);
 
+/* Windowed search with per-query windows: SearchForInitialization's loop with the gate and acceptance as parameters
+ * (same field meaning as orbm_window_params in include/orbx.h).  Gate 0 + SearchForInitialization parameters must equal
+ * orbo_search_for_initialization; gate 1 follows upstream ORB-SLAM2's SearchByProjection (reference body empty,
+ * include/ORBmatcher.h:24 -> parity unpinned for that instance). */
+typedef struct {
+    float radius;
+    float level_scale[16];
+    int32_t query_level_min, query_level_max;
+    int32_t level_below, level_above;
+    int32_t gate;
+    int32_t th_dist;
+    float nnratio;
+    int32_t check_orientation;
+    int32_t update_centers;
+    int32_t width, height;
+    int32_t literal_gridid_bug;
+} orbo_window_params;
+int orbo_search_window(const orbo_keypoint *kp1, const uint8_t *desc1, int n1,
+                       const orbo_keypoint *kp2, const uint8_t *desc2, int n2,
+                       float *centers /* n1 x 2, NaN x = skip */, int32_t *matches12 /* n1 */, const orbo_window_params *params);
+
 /* multi-thread helper for the CPU baseline: extract `nframes` frames with `nthreads` pthreads,
  * one extractor per thread.  counts[nframes] receives keypoint counts. */
 int orbo_extract_many(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST,

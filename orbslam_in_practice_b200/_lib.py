@@ -28,6 +28,7 @@ ABI_SYMBOLS = [
     "orbm_create", "orbm_destroy", "orbm_launch_count", "orbm_hamming_pairs_host",
     "orbm_knn2_device", "orbm_knn2_host", "orbm_ratio_select_device", "orbm_merge_shards_device",
     "orbm_popc_peak", "orbm_search_init_workspace_bytes", "orbm_search_init_device", "orbm_search_init_host",
+    "orbm_search_window_device", "orbm_search_window_host",
     "orbm_exchange_create", "orbm_exchange_open", "orbm_knn2_sharded_device", "orbm_exchange_status",
 ]
 
@@ -42,6 +43,28 @@ class Params(C.Structure):
 
 
 _lib = None
+
+
+class WindowParams(C.Structure):
+    """orbm_window_params (include/orbx.h): per-query windowed search (SearchByProjection-style)."""
+    _fields_ = [("radius", C.c_float), ("level_scale", C.c_float * 16),
+                ("query_level_min", C.c_int32), ("query_level_max", C.c_int32),
+                ("level_below", C.c_int32), ("level_above", C.c_int32), ("gate", C.c_int32), ("th_dist", C.c_int32),
+                ("nnratio", C.c_float), ("check_orientation", C.c_int32), ("update_centers", C.c_int32),
+                ("width", C.c_int32), ("height", C.c_int32), ("literal_gridid_bug", C.c_int32)]
+
+    @classmethod
+    def projection(cls, th, scale_factors, width, height, th_dist=100, check_orientation=True, level_below=1, level_above=1):
+        """Upstream ORB-SLAM2 frame-to-frame SearchByProjection: r = th * scaleFactor[octave], octaves +-1, best <= TH_HIGH."""
+        p = cls()
+        p.radius = th
+        for i in range(16):
+            p.level_scale[i] = scale_factors[i] if i < len(scale_factors) else 1.0
+        p.query_level_min, p.query_level_max = 0, 15
+        p.level_below, p.level_above, p.gate, p.th_dist, p.nnratio = level_below, level_above, 1, th_dist, 0.0
+        p.check_orientation, p.update_centers = int(check_orientation), 0
+        p.width, p.height, p.literal_gridid_bug = width, height, 0
+        return p
 
 
 def load():
@@ -91,6 +114,8 @@ def load():
     L.orbm_set_profiling.argtypes = [vp, i32]
     L.orbm_knn2_times.argtypes = [vp, C.POINTER(f32), C.POINTER(f32)]
     L.orbm_popc_peak.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.orbm_search_window_device.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, vp, vp, vp, sz, vp]
+    L.orbm_search_window_host.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, vp, C.POINTER(i32), vp]
     L.orbm_search_init_workspace_bytes.restype = sz
     L.orbm_search_init_workspace_bytes.argtypes = [i32, i32]
     L.orbm_exchange_create.argtypes = [vp, i32, i32, i32, vp]
@@ -291,6 +316,21 @@ class Matcher:
         check(load().orbm_search_init_host(self.h, _p(kp1), _p(desc1), len(kp1), _p(kp2), _p(desc2), len(kp2), _p(prev), _p(m12),
                                            C.byref(n), window, nnratio, int(check_ori), width, height, int(literal_bug)))
         return n.value, m12, prev
+
+    def search_window_host(self, kp1, desc1, kp2, desc2, centers, params):
+        """params: a WindowParams (orbm_window_params).  Returns (nmatches, matches12, centers)."""
+        kp1 = np.ascontiguousarray(kp1, KEYPOINT_DTYPE); kp2 = np.ascontiguousarray(kp2, KEYPOINT_DTYPE)
+        desc1 = np.ascontiguousarray(desc1, np.uint8); desc2 = np.ascontiguousarray(desc2, np.uint8)
+        cen = np.ascontiguousarray(centers, np.float32).copy()
+        m12 = np.zeros(len(kp1), np.int32); n = C.c_int()
+        check(load().orbm_search_window_host(self.h, _p(kp1), _p(desc1), len(kp1), _p(kp2), _p(desc2), len(kp2), _p(cen), _p(m12),
+                                             C.byref(n), C.byref(params)))
+        return n.value, m12, cen
+
+    def search_window_device(self, kps_ptr, desc_ptr, counts_ptr, capacity, pair_a_ptr, pair_b_ptr, npairs, centers_ptr,
+                             matches_ptr, nmatches_ptr, params, ws_ptr, ws_bytes, stream=0):
+        check(load().orbm_search_window_device(self.h, kps_ptr, desc_ptr, counts_ptr, capacity, pair_a_ptr, pair_b_ptr, npairs,
+                                               centers_ptr, matches_ptr, nmatches_ptr, C.byref(params), ws_ptr, ws_bytes, stream))
 
     def set_profiling(self, on):
         check(load().orbm_set_profiling(self.h, int(on)))

@@ -11,6 +11,7 @@
 namespace ORBSlam {
 
 const int ORBmatcher::TH_LOW = 50;          // src/ORBmatcher.cpp:7
+const int ORBmatcher::TH_HIGH = 100;        // upstream ORB-SLAM2 (the reference defines TH_LOW only)
 const int ORBmatcher::HISTO_LENGTH = 30;    // src/ORBmatcher.cpp:6
 
 static void check(int rc, const char *what)
@@ -76,6 +77,33 @@ int ORBmatcher::SearchForInitialization(const std::vector<cv::KeyPoint> &vKeys1,
                                 (const orbx_keypoint *)vKeys2.data(), d2.data(), n2, (float *)vbPrevMatched.data(),
                                 vnMatches12.data(), &nmatches, windowSize, mfNNratio, mbCheckOrientation ? 1 : 0,
                                 imageWidth, imageHeight, 0), "search_init");
+    if (nmatches < 0) throw std::runtime_error("ORBmatcher: search workspace too small");
+    return nmatches;
+}
+
+int ORBmatcher::SearchByProjection(const std::vector<cv::KeyPoint> &vLastKeys, const cv::Mat &LastDescriptors,
+                                   const std::vector<cv::Point2f> &vProjected,
+                                   const std::vector<cv::KeyPoint> &vCurrentKeys, const cv::Mat &CurrentDescriptors,
+                                   const std::vector<float> &vScaleFactors, std::vector<int> &vnMatches, float th,
+                                   int imageWidth, int imageHeight)
+{
+    const int n1 = (int)vLastKeys.size(), n2 = (int)vCurrentKeys.size();
+    vnMatches.assign((size_t)n1, -1);
+    if (n1 == 0) return 0;
+    if ((int)vProjected.size() != n1) throw std::runtime_error("ORBmatcher: vProjected must have one entry per last-frame keypoint");
+    Ensure(n1 > n2 ? n1 : n2, n1 > n2 ? n1 : n2);
+    const std::vector<unsigned char> d1 = pack_rows(LastDescriptors), d2 = n2 ? pack_rows(CurrentDescriptors) : std::vector<unsigned char>();
+    orbm_window_params p = orbm_window_params();
+    p.radius = th;
+    for (int i = 0; i < 16; ++i) p.level_scale[i] = i < (int)vScaleFactors.size() ? vScaleFactors[(size_t)i] : 1.0f;
+    p.query_level_min = 0; p.query_level_max = 15; p.level_below = 1; p.level_above = 1;
+    p.gate = 1; p.th_dist = TH_HIGH; p.nnratio = 0.0f; p.check_orientation = mbCheckOrientation ? 1 : 0; p.update_centers = 0;
+    p.width = imageWidth; p.height = imageHeight; p.literal_gridid_bug = 0;
+    std::vector<cv::Point2f> centers(vProjected);
+    int nmatches = 0;
+    check(orbm_search_window_host(mHandle, (const orbx_keypoint *)vLastKeys.data(), d1.data(), n1,
+                                  (const orbx_keypoint *)vCurrentKeys.data(), d2.data(), n2, (float *)centers.data(),
+                                  vnMatches.data(), &nmatches, &p), "search_window");
     if (nmatches < 0) throw std::runtime_error("ORBmatcher: search workspace too small");
     return nmatches;
 }

@@ -42,7 +42,20 @@ public:
                                 std::vector<cv::Point2f> &vbPrevMatched, std::vector<int> &vnMatches12, int windowSize,
                                 int imageWidth, int imageHeight);
 
+    // SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, float th, bool bMono) (include/ORBmatcher.h:24) on
+    // plain containers.  The reference's body is empty, so the loop follows upstream ORB-SLAM2's frame-to-frame variant
+    // (SURVEY.md 8f row 4): last-frame point i, projected to vProjected[i] in the current frame (x = NaN: not visible),
+    // searches r = th * vScaleFactors[octave] around it among current keypoints of octave +-1 with the reference's
+    // GetFeaturesInArea (src/Frame.cpp:219-271); best distance <= TH_HIGH wins, an already matched current keypoint is
+    // skipped, then the rotation-histogram filter.  vnMatches[i] = current keypoint index or -1; returns #matches.
+    int SearchByProjection(const std::vector<cv::KeyPoint> &vLastKeys, const cv::Mat &LastDescriptors,
+                           const std::vector<cv::Point2f> &vProjected,
+                           const std::vector<cv::KeyPoint> &vCurrentKeys, const cv::Mat &CurrentDescriptors,
+                           const std::vector<float> &vScaleFactors, std::vector<int> &vnMatches, float th,
+                           int imageWidth, int imageHeight);
+
     static const int TH_LOW;
+    static const int TH_HIGH;
     static const int HISTO_LENGTH;
 
 private:

@@ -32,16 +32,6 @@ int run_popc_bench(int mode, int sm_count, double *ops_per_second);
 void launch_exchange_signal(uint32_t *const *peer_flags, int rank, int world, uint32_t epoch, cudaStream_t s);
 void launch_merge_peers(const int *const *peer_tri, const uint32_t *my_flags, int world, int nq, size_t arr_stride, uint32_t epoch,
                         int *od1, int *oidx1, int *od2, int th_low, float ratio, int *match, int *err, cudaStream_t s);
-// search_init.cu
-struct SearchInitArgs {
-    const orbx_keypoint *kps; const uint8_t *desc; const int *counts; int cap;
-    const int *pair_a, *pair_b; int npairs;
-    float *prev_matched; int *matches12; int *nmatches;
-    int window; float nnratio; int check_ori; float max_x, max_y; int literal_bug;
-    uint32_t *workspace; unsigned long long ws_words_per_pair;
-    int sort_n;
-};
-int launch_search_init(const SearchInitArgs &a, cudaStream_t s);
 } // namespace orbx
 
 using namespace orbx;
@@ -923,24 +913,31 @@ extern "C" size_t orbm_search_init_workspace_bytes(int capacity, int npairs)
     return (size_t)capacity * ((size_t)capacity + 1) * sizeof(uint32_t) * (size_t)npairs;
 }
 
-extern "C" int orbm_search_init_device(orbm_matcher *m, const orbx_keypoint *d_kps, const uint8_t *d_desc, const int32_t *d_counts,
-                                       int capacity, const int32_t *d_pair_a, const int32_t *d_pair_b, int npairs,
-                                       float *d_prev_matched, int32_t *d_matches12, int32_t *d_nmatches,
-                                       int window, float nnratio, int check_orientation, int width, int height,
-                                       int literal_gridid_bug, void *d_workspace, size_t workspace_bytes, void *stream)
+static int window_params_ok(const orbm_window_params *p)
 {
-    if (!m || npairs < 0 || capacity < 1 || capacity >= 65536 || width < 1 || height < 1 || window < 0) return ORBX_E_INVALID;
+    return p && p->width >= 1 && p->height >= 1 && p->radius >= 0.f && (p->gate == 0 || p->gate == 1) &&
+           p->query_level_min >= 0 && p->query_level_max < 16 && p->query_level_min <= p->query_level_max;
+}
+
+extern "C" int orbm_search_window_device(orbm_matcher *m, const orbx_keypoint *d_kps, const uint8_t *d_desc, const int32_t *d_counts,
+                                         int capacity, const int32_t *d_pair_a, const int32_t *d_pair_b, int npairs,
+                                         float *d_centers, int32_t *d_matches12, int32_t *d_nmatches,
+                                         const orbm_window_params *params, void *d_workspace, size_t workspace_bytes, void *stream)
+{
+    if (!m || npairs < 0 || capacity < 1 || capacity >= 65536 || !window_params_ok(params)) return ORBX_E_INVALID;
     if (npairs == 0) return ORBX_OK;
-    if (!d_kps || !d_desc || !d_counts || !d_pair_a || !d_pair_b || !d_prev_matched || !d_matches12 || !d_nmatches || !d_workspace)
+    if (!d_kps || !d_desc || !d_counts || !d_pair_a || !d_pair_b || !d_centers || !d_matches12 || !d_nmatches || !d_workspace)
         return ORBX_E_INVALID;
     if (((uintptr_t)d_desc & 15) || ((uintptr_t)d_workspace & 3)) return ORBX_E_INVALID;
     CK(cudaSetDevice(m->device));
     SearchInitArgs a;
     a.kps = d_kps; a.desc = d_desc; a.counts = d_counts; a.cap = capacity;
     a.pair_a = d_pair_a; a.pair_b = d_pair_b; a.npairs = npairs;
-    a.prev_matched = d_prev_matched; a.matches12 = d_matches12; a.nmatches = d_nmatches;
-    a.window = window; a.nnratio = nnratio; a.check_ori = check_orientation ? 1 : 0;
-    a.max_x = (float)width; a.max_y = (float)height; a.literal_bug = literal_gridid_bug ? 1 : 0;
+    a.prev_matched = d_centers; a.matches12 = d_matches12; a.nmatches = d_nmatches;
+    a.w = *params;
+    // octaves of F2 any query can reach; the grid (and the sort) only holds those
+    a.grid_level_min = params->level_below < 0 ? 0 : params->query_level_min - params->level_below;
+    a.grid_level_max = params->level_above < 0 ? INT_MAX : params->query_level_max + params->level_above;
     a.workspace = (uint32_t *)d_workspace; a.ws_words_per_pair = workspace_bytes / sizeof(uint32_t) / (size_t)npairs;
     int sn = 32; while (sn < capacity) sn <<= 1;
     a.sort_n = sn;
@@ -950,19 +947,44 @@ extern "C" int orbm_search_init_device(orbm_matcher *m, const orbx_keypoint *d_k
     return ORBX_OK;
 }
 
-extern "C" int orbm_search_init_host(orbm_matcher *m, const orbx_keypoint *kp1, const uint8_t *desc1, int n1,
-                                     const orbx_keypoint *kp2, const uint8_t *desc2, int n2,
-                                     float *prev_matched, int32_t *matches12, int32_t *nmatches,
-                                     int window, float nnratio, int check_orientation, int width, int height, int literal_gridid_bug)
+// SearchForInitialization as an instance of the windowed search: octave-0 queries, octave-0 candidates, fixed window,
+// TH_LOW = 50 (src/ORBmatcher.cpp:7), displacement gate, centres updated
+static orbm_window_params search_init_params(int window, float nnratio, int check_orientation, int width, int height, int literal_gridid_bug)
 {
-    if (!m || n1 < 0 || n2 < 0 || n1 >= 65536 || n2 >= 65536 || !nmatches) return ORBX_E_INVALID;
+    orbm_window_params p;
+    std::memset(&p, 0, sizeof(p));
+    p.radius = (float)window;
+    for (int i = 0; i < 16; ++i) p.level_scale[i] = 1.0f;
+    p.query_level_min = 0; p.query_level_max = 0; p.level_below = 0; p.level_above = 0;
+    p.gate = 0; p.th_dist = 50; p.nnratio = nnratio; p.check_orientation = check_orientation ? 1 : 0; p.update_centers = 1;
+    p.width = width; p.height = height; p.literal_gridid_bug = literal_gridid_bug ? 1 : 0;
+    return p;
+}
+
+extern "C" int orbm_search_init_device(orbm_matcher *m, const orbx_keypoint *d_kps, const uint8_t *d_desc, const int32_t *d_counts,
+                                       int capacity, const int32_t *d_pair_a, const int32_t *d_pair_b, int npairs,
+                                       float *d_prev_matched, int32_t *d_matches12, int32_t *d_nmatches,
+                                       int window, float nnratio, int check_orientation, int width, int height,
+                                       int literal_gridid_bug, void *d_workspace, size_t workspace_bytes, void *stream)
+{
+    if (width < 1 || height < 1 || window < 0) return ORBX_E_INVALID;
+    const orbm_window_params p = search_init_params(window, nnratio, check_orientation, width, height, literal_gridid_bug);
+    return orbm_search_window_device(m, d_kps, d_desc, d_counts, capacity, d_pair_a, d_pair_b, npairs, d_prev_matched, d_matches12,
+                                     d_nmatches, &p, d_workspace, workspace_bytes, stream);
+}
+
+extern "C" int orbm_search_window_host(orbm_matcher *m, const orbx_keypoint *kp1, const uint8_t *desc1, int n1,
+                                       const orbx_keypoint *kp2, const uint8_t *desc2, int n2,
+                                       float *centers, int32_t *matches12, int32_t *nmatches, const orbm_window_params *params)
+{
+    if (!m || n1 < 0 || n2 < 0 || n1 >= 65536 || n2 >= 65536 || !nmatches || !window_params_ok(params)) return ORBX_E_INVALID;
     if (n1 == 0) { *nmatches = 0; return ORBX_OK; }
-    if (!kp1 || !desc1 || !prev_matched || !matches12 || (n2 && (!kp2 || !desc2))) return ORBX_E_INVALID;
+    if (!kp1 || !desc1 || !centers || !matches12 || (n2 && (!kp2 || !desc2))) return ORBX_E_INVALID;
     CK(cudaSetDevice(m->device));
     cudaStream_t s = m->stream;
     const int cap = (n1 > n2 ? n1 : n2) < 1 ? 1 : (n1 > n2 ? n1 : n2);
     const size_t wsb = orbm_search_init_workspace_bytes(cap, 1);
-    // one scratch allocation laid out as [kps 2][desc 2][counts 2][pairs 2][prev][m12][nm][workspace]
+    // one scratch allocation laid out as [kps 2][desc 2][counts 2][pairs 2][centres][m12][nm][workspace]
     const size_t o_kps = 0, o_desc = (o_kps + 2 * (size_t)cap * sizeof(orbx_keypoint) + 15) & ~(size_t)15, o_cnt = (o_desc + 2 * (size_t)cap * 32 + 15) & ~(size_t)15,
                  o_prev = o_cnt + 64, o_m12 = o_prev + (size_t)cap * 8, o_nm = o_m12 + (size_t)cap * 4, o_ws = (o_nm + 16 + 15) & ~(size_t)15;
     const size_t need = o_ws + wsb;
@@ -981,17 +1003,26 @@ extern "C" int orbm_search_init_host(orbm_matcher *m, const orbx_keypoint *kp1, 
         CK(cudaMemcpyAsync(b + o_desc + (size_t)cap * 32, desc2, (size_t)n2 * 32, cudaMemcpyHostToDevice, s));
     }
     CK(cudaMemcpyAsync(b + o_cnt, meta, sizeof(meta), cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(b + o_prev, prev_matched, (size_t)n1 * 8, cudaMemcpyHostToDevice, s));
-    int rc = orbm_search_init_device(m, (const orbx_keypoint *)(b + o_kps), b + o_desc, (const int *)(b + o_cnt), cap,
-                                     (const int *)(b + o_cnt) + 2, (const int *)(b + o_cnt) + 3, 1,
-                                     (float *)(b + o_prev), (int *)(b + o_m12), (int *)(b + o_nm),
-                                     window, nnratio, check_orientation, width, height, literal_gridid_bug, b + o_ws, wsb, s);
+    CK(cudaMemcpyAsync(b + o_prev, centers, (size_t)n1 * 8, cudaMemcpyHostToDevice, s));
+    int rc = orbm_search_window_device(m, (const orbx_keypoint *)(b + o_kps), b + o_desc, (const int *)(b + o_cnt), cap,
+                                       (const int *)(b + o_cnt) + 2, (const int *)(b + o_cnt) + 3, 1,
+                                       (float *)(b + o_prev), (int *)(b + o_m12), (int *)(b + o_nm), params, b + o_ws, wsb, s);
     if (rc) return rc;
     CK(cudaMemcpyAsync(matches12, b + o_m12, (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(prev_matched, b + o_prev, (size_t)n1 * 8, cudaMemcpyDeviceToHost, s));
+    if (params->update_centers) CK(cudaMemcpyAsync(centers, b + o_prev, (size_t)n1 * 8, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(nmatches, b + o_nm, 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return ORBX_OK;
+}
+
+extern "C" int orbm_search_init_host(orbm_matcher *m, const orbx_keypoint *kp1, const uint8_t *desc1, int n1,
+                                     const orbx_keypoint *kp2, const uint8_t *desc2, int n2,
+                                     float *prev_matched, int32_t *matches12, int32_t *nmatches,
+                                     int window, float nnratio, int check_orientation, int width, int height, int literal_gridid_bug)
+{
+    if (width < 1 || height < 1 || window < 0) return ORBX_E_INVALID;
+    const orbm_window_params p = search_init_params(window, nnratio, check_orientation, width, height, literal_gridid_bug);
+    return orbm_search_window_host(m, kp1, desc1, n1, kp2, desc2, n2, prev_matched, matches12, nmatches, &p);
 }
 
 extern "C" int orbm_popc_peak(int device, double *popc_per_second, double *lop3_per_second)

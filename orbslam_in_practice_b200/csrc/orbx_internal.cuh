@@ -89,4 +89,16 @@ void launch_undistort(const orbx_keypoint *in, orbx_keypoint *out, int n, const 
 int octree_smem_bytes(const Geo &g);
 int octree_configure(int smem_bytes);
 
+// search_init.cu: one windowed-search launch (SearchForInitialization and the projection-style search share it)
+struct SearchInitArgs {
+    const orbx_keypoint *kps; const uint8_t *desc; const int *counts; int cap;      // extractor outputs [F][cap]
+    const int *pair_a, *pair_b; int npairs;
+    float *prev_matched; int *matches12; int *nmatches;                              // [npairs][cap][2], [npairs][cap], [npairs]
+    orbm_window_params w;                                                            // see include/orbx.h
+    int grid_level_min, grid_level_max;                                              // octaves of F2 worth putting in the grid
+    uint32_t *workspace; unsigned long long ws_words_per_pair;
+    int sort_n;                                                                      // power of two >= cap
+};
+int launch_search_init(const SearchInitArgs &a, cudaStream_t s);
+
 } // namespace orbx

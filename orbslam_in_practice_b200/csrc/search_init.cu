@@ -20,18 +20,8 @@ namespace orbx {
 
 constexpr int kGridRows = 48, kGridCols = 64;   // Frame.h:11-12
 constexpr int kHistoLength = 30;                // ORBmatcher.cpp:6
-constexpr int kThLow = 50;                      // ORBmatcher.cpp:7
 constexpr int kSiThreads = 256;
 constexpr uint32_t kInfKey = 0xffffffffu;
-
-struct SearchInitArgs {                      // keep in sync with the declaration in abi.cu
-    const orbx_keypoint *kps; const uint8_t *desc; const int *counts; int cap;      // extractor outputs [F][cap]
-    const int *pair_a, *pair_b; int npairs;
-    float *prev_matched; int *matches12; int *nmatches;                              // [npairs][cap][2], [npairs][cap], [npairs]
-    int window; float nnratio; int check_ori; float max_x, max_y; int literal_bug;
-    uint32_t *workspace; unsigned long long ws_words_per_pair;
-    int sort_n;                                                                      // power of two >= cap
-};
 
 __device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const uint4 *__restrict__ b)
 {
@@ -41,7 +31,7 @@ __device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const 
 }
 
 __global__ void __launch_bounds__(kSiThreads)
-k_search_init(const SearchInitArgs A)
+k_search_init(const __grid_constant__ SearchInitArgs A)
 {
     extern __shared__ __align__(16) unsigned char si_smem[];
     uint32_t *keys = reinterpret_cast<uint32_t *>(si_smem);                         // [sort_n] sorted grid keys of F2
@@ -63,18 +53,20 @@ k_search_init(const SearchInitArgs A)
     uint32_t *ws = A.workspace + (size_t)pair * A.ws_words_per_pair;
 
     // image bounds for zero distortion (Frame.cpp:113-118) and grid cell sizes (:59-60)
-    const float minX = 0.f, minY = 0.f, maxX = A.max_x, maxY = A.max_y;
+    const orbm_window_params &W = A.w;
+    const float minX = 0.f, minY = 0.f, maxX = (float)W.width, maxY = (float)W.height;
     const float wInv = (float)kGridCols / (maxX - minX), hInv = (float)kGridRows / (maxY - minY);
 
-    // ---- 1: grid keys of F2 (octave 0 only: SearchForInitialization queries minLevel = maxLevel = 0) ----
+    // ---- 1: grid keys of F2; only the octaves some query can ask for (SearchForInitialization: octave 0 alone,
+    //      it queries minLevel = maxLevel = 0) ----
     for (int i = tid; i < A.sort_n; i += kSiThreads) {
         uint32_t key = kInfKey;
         if (i < n2) {
             const orbx_keypoint k = kp2[i];
             // GetGridId takes doubles (Frame.cpp:161-168); std::round = half away from zero
             const int ix = (int)round(((double)k.x - (double)minX) * (double)wInv);
-            const int iy = (int)round(((double)k.y - (double)(A.literal_bug ? maxY : minY)) * (double)hInv);
-            if (k.octave == 0 && ix >= 0 && ix < kGridCols && iy >= 0 && iy < kGridRows)
+            const int iy = (int)round(((double)k.y - (double)(W.literal_gridid_bug ? maxY : minY)) * (double)hInv);
+            if (k.octave >= A.grid_level_min && k.octave <= A.grid_level_max && ix >= 0 && ix < kGridCols && iy >= 0 && iy < kGridRows)
                 key = ((uint32_t)(ix * kGridRows + iy) << 16) | (uint32_t)i;
         }
         keys[i] = key;
@@ -104,20 +96,24 @@ k_search_init(const SearchInitArgs A)
         if (c == kGridCols * kGridRows) s_nvalid = lo;
     }
     __syncthreads();
-    const int nvalid = s_nvalid;                        // octave-0 keypoints of F2 that landed in the grid
+    const int nvalid = s_nvalid;                        // keypoints of F2 that landed in the grid
     // workspace rows: one candidate list per query of F1, stride = nvalid entries (+1 word for the count)
     const unsigned long long stride = (unsigned long long)nvalid + 1ull;
     const bool ws_ok = stride * (unsigned long long)n1 <= A.ws_words_per_pair;
     if (!ws_ok) { if (tid == 0) A.nmatches[pair] = -1; return; }          // caller's workspace too small
 
     // ---- 2a: candidate lists, warp per query ----
-    const float r = (float)A.window;
     for (int q = warp; q < n1; q += kSiThreads / 32) {
         uint32_t *list = ws + (unsigned long long)q * stride;
         const orbx_keypoint kq = kp1[q];
         int cnt = 0;
-        if (kq.octave == 0) {                                              // :25-27 level1 > 0 -> continue
-            const float x = prev[2 * q], y = prev[2 * q + 1];
+        const float x = prev[2 * q], y = prev[2 * q + 1];
+        // :25-27 level1 > 0 -> continue (query_level range 0..0 there); a NaN centre marks a query without a projection
+        if (kq.octave >= W.query_level_min && kq.octave <= W.query_level_max && x == x) {
+            const float r = __fmul_rn(W.radius, W.level_scale[kq.octave & 15]);
+            // GetFeaturesInArea's level filter, Frame.cpp:245-258: octave < minLevel or (maxLevel >= 0 and octave > maxLevel) -> skip
+            const int minLevel = W.level_below < 0 ? 0 : kq.octave - W.level_below;
+            const int maxLevel = W.level_above < 0 ? -1 : kq.octave + W.level_above;
             // GetFeaturesInArea cell window, Frame.cpp:225-239 (float math)
             const int cx0 = max(0, (int)floorf((x - minX - r) * wInv));
             const int cx1 = min(kGridCols - 1, (int)ceilf((x - minX + r) * wInv));
@@ -134,7 +130,8 @@ k_search_init(const SearchInitArgs A)
                             const int i2 = (int)(keys[p] & 0xffffu);
                             const orbx_keypoint k2 = kp2[i2];
                             const float dx = k2.x - x, dy = k2.y - y;                  // Frame.cpp:263-266
-                            if (fabsf(dx) < r && fabsf(dy) < r) {
+                            const bool lvl = k2.octave >= minLevel && (maxLevel < 0 || k2.octave <= maxLevel);
+                            if (lvl && fabsf(dx) < r && fabsf(dy) < r) {
                                 ok = true;
                                 ent = (uint32_t)i2 | ((uint32_t)hamming256(a0, a1, d2 + 2 * i2) << 16);
                             }
@@ -165,7 +162,9 @@ k_search_init(const SearchInitArgs A)
                 if (p < cnt) {
                     const uint32_t ent = list[1 + p];
                     const int i2 = (int)(ent & 0xffffu), dist = (int)(ent >> 16);
-                    if (!(matchedDist[i2] <= dist)) key = ((uint32_t)dist << 16) | (uint32_t)p;   // :49-50 gate
+                    // gate 0: :49-50 (matched at a distance <= dist);  gate 1: already taken by an earlier query
+                    const bool skip = W.gate == 0 ? matchedDist[i2] <= dist : m21[i2] >= 0;
+                    if (!skip) key = ((uint32_t)dist << 16) | (uint32_t)p;
                 }
                 const uint32_t hi = max(k1, key);
                 k1 = min(k1, key); k2 = min(k2, hi);
@@ -180,10 +179,11 @@ k_search_init(const SearchInitArgs A)
                 const int bestDist = (int)(k1 >> 16);
                 const int bestDist2 = k2 == kInfKey ? INT_MAX : (int)(k2 >> 16);
                 const int bestIdx2 = (int)(list[1 + (k1 & 0xffffu)] & 0xffffu);
-                if (bestDist <= kThLow && (float)bestDist < __fmul_rn((float)bestDist2, A.nnratio)) {   // :65-67
+                const bool ratio_ok = W.nnratio <= 0.f || (float)bestDist < __fmul_rn((float)bestDist2, W.nnratio);
+                if (bestDist <= W.th_dist && ratio_ok) {                                // :65-67
                     if (m21[bestIdx2] >= 0) { m12[m21[bestIdx2]] = -1; nmatches--; }
                     m12[q] = bestIdx2; m21[bestIdx2] = q; matchedDist[bestIdx2] = bestDist; nmatches++;
-                    if (A.check_ori) {                                        // :79-90
+                    if (W.check_orientation) {                                // :79-90
                         float rot = __fsub_rn(kp1[q].angle, kp2[bestIdx2].angle);
                         if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
                         int bin = (int)roundf(__fmul_rn(rot, factor));
@@ -216,12 +216,12 @@ k_search_init(const SearchInitArgs A)
     int removed = 0;
     for (int q = tid; q < n1; q += kSiThreads) {
         int m = m12[q];
-        if (m >= 0 && A.check_ori) {
+        if (m >= 0 && W.check_orientation) {
             const uint32_t tag = ws[(unsigned long long)q * stride];
             const int bin = (int)(tag & 0xffu);
             if ((tag & 0x80000000u) && bin != s_keep[0] && bin != s_keep[1] && bin != s_keep[2]) { m12[q] = -1; m = -1; ++removed; }
         }
-        if (m >= 0) { prev[2 * q] = kp2[m].x; prev[2 * q + 1] = kp2[m].y; }
+        if (m >= 0 && W.update_centers) { prev[2 * q] = kp2[m].x; prev[2 * q + 1] = kp2[m].y; }
     }
     if (removed) atomicSub(&s_nmatches, removed);
     __syncthreads();

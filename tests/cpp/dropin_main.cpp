@@ -68,6 +68,15 @@ int main(int argc, char **argv)
         int cnt = (int)m12i.size();
         std::fwrite(&n, 4, 1, fo); std::fwrite(&cnt, 4, 1, fo);
         std::fwrite(m12i.data(), 4, m12i.size(), fo);
+        // SearchByProjection-style search: "projection" = the frame-0 keypoint position itself, th = 15
+        ORBSlam::ORBmatcher proj(0.9f, true);
+        std::vector<cv::Point2f> centers(allKps[0].size());
+        for (size_t i = 0; i < centers.size(); ++i) centers[i] = allKps[0][i].pt;
+        std::vector<int> mp;
+        int np_ = proj.SearchByProjection(allKps[0], allDesc[0], centers, allKps[1], allDesc[1], ex->GetScaleFactors(), mp, 15.0f, W, H);
+        int cntp = (int)mp.size();
+        std::fwrite(&np_, 4, 1, fo); std::fwrite(&cntp, 4, 1, fo);
+        std::fwrite(mp.data(), 4, mp.size(), fo);
     }
     std::fclose(fo);
     delete ex;

@@ -72,3 +72,11 @@ def test_cpp_classes_match_oracle(orbx, oracle, tmp_path):
     prev = np.stack([k1["x"], k1["y"]], 1)
     n_o, m_o, _ = oracle.search_for_initialization(k1, dd1, k2, dd2, prev, 100, 0.9, True, 640, 480)
     assert n_si == n_o and np.array_equal(m12, m_o)
+    off += 4 * cnt
+    # ORBmatcher::SearchByProjection (plain-container form) against the oracle's windowed search
+    n_p, cntp = struct.unpack_from("<2i", raw, off); off += 8
+    mp = np.frombuffer(raw, np.int32, cntp, off)
+    P = oracle.window_params(15.0, [float(v) for v in oex.scale_factors], (0, 15), 1, 1, gate=1, th_dist=100, nnratio=0.0,
+                             check_orientation=True, update_centers=False, width=640, height=480)
+    n_po, m_po, _ = oracle.search_window(k1, dd1, k2, dd2, prev, P)
+    assert n_p == n_po and np.array_equal(mp, m_po)

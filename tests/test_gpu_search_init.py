@@ -99,3 +99,24 @@ def test_search_init_host_entry(orbx, oracle):
     # empty second frame / empty first frame
     assert m.search_init_host(k1, d1, k2[:0], d2[:0], prev)[0] == 0
     assert m.search_init_host(k1[:0], d1[:0], k2, d2, prev[:0])[0] == 0
+
+
+@pytest.mark.parametrize("th,below,above,ori", [(7.0, 1, 1, True), (15.0, -1, 0, False), (7.0, 0, -1, True)])
+def test_projection_style_windowed_search_matches_oracle(orbx, oracle, th, below, above, ori):
+    """per-query windows (r = th * scaleFactor[octave]), octave ranges, first-come gate, best <= TH_HIGH.
+    The three cases are upstream SearchByProjection's default / bBackward / bForward level ranges."""
+    a = synth_frame(5); b = np.roll(np.roll(a, 4, axis=1), -3, axis=0)
+    ex = orbx.Extractor(nfeatures=2000, max_width=640, max_height=480, max_batch=2)
+    kps, desc, cnt = ex.extract_host(np.stack([a, b]))
+    k1, d1, k2, d2 = kps[0][:cnt[0]], desc[0][:cnt[0]], kps[1][:cnt[1]], desc[1][:cnt[1]]
+    sf = [float(v) for v in ex.scale_factors]
+    cen = np.stack([k1["x"] + 4, k1["y"] - 3], 1).astype(np.float32)
+    cen[::7, 0] = np.nan
+    P = orbx.WindowParams.projection(th, sf, 640, 480, th_dist=100, check_orientation=ori, level_below=below, level_above=above)
+    Po = oracle.window_params(th, sf, (0, 15), below, above, gate=1, th_dist=100, nnratio=0.0, check_orientation=ori,
+                              update_centers=False, width=640, height=480)
+    m = orbx.Matcher(4096, 4096)
+    n_g, m_g, c_g = m.search_window_host(k1, d1, k2, d2, cen, P)
+    n_o, m_o, c_o = oracle.search_window(k1, d1, k2, d2, cen, Po)
+    assert n_g == n_o and np.array_equal(m_g, m_o) and np.array_equal(c_g, c_o, equal_nan=True)
+    assert n_o > 300

@@ -34,3 +34,38 @@ def test_oracle_equals_reference_matcher_tu(oracle, seed, shift, ratio, ori, bug
         n_o2, m_o2, _ = oracle.search_for_initialization(k1, d1, k2, d2, p_o, 100, ratio, ori, 640, 480, bug)
         n_r2, m_r2, _ = R.run_search_for_initialization(k1, d1, k2, d2, p_r, 100, ratio, ori, 640, 480, bug)
         assert n_o2 == n_r2 and np.array_equal(m_o2, m_r2)
+
+
+@pytest.mark.parametrize("seed,shift,ratio,ori", [(0, (5, 3), 0.9, True), (3, (40, 25), 0.7, False)])
+def test_windowed_search_with_init_parameters_is_search_for_initialization(oracle, seed, shift, ratio, ori):
+    """The generalised windowed search (gate 0, octave 0, fixed window, TH_LOW, ratio) must reproduce the pinned function."""
+    k1, d1, k2, d2 = _pair(oracle, seed, shift)
+    prev = np.stack([k1["x"], k1["y"]], 1)
+    n_a, m_a, p_a = oracle.search_for_initialization(k1, d1, k2, d2, prev, 100, ratio, ori, 640, 480, False)
+    P = oracle.window_params(100.0, None, (0, 0), 0, 0, gate=0, th_dist=50, nnratio=ratio, check_orientation=ori,
+                             update_centers=True, width=640, height=480)
+    n_b, m_b, p_b = oracle.search_window(k1, d1, k2, d2, prev, P)
+    assert n_a == n_b and np.array_equal(m_a, m_b) and np.array_equal(p_a, p_b)
+
+
+def test_projection_style_search_properties(oracle):
+    """Gate 1 (upstream SearchByProjection; reference body empty -> unpinned): checked through its defining properties."""
+    k1, d1, k2, d2 = _pair(oracle, 5, (4, -3))
+    ex = oracle.OracleExtractor(2000)
+    sf = [float(v) for v in ex.scale_factors]
+    cen = np.stack([k1["x"] + 4, k1["y"] - 3], 1).astype(np.float32)     # the "projection": the true shift
+    cen[::7, 0] = np.nan                                                  # points without a projection
+    P = oracle.window_params(7.0, sf, (0, 15), 1, 1, gate=1, th_dist=100, nnratio=0.0, check_orientation=True,
+                             update_centers=False, width=640, height=480)
+    n, m12, cen_out = oracle.search_window(k1, d1, k2, d2, cen, P)
+    assert np.array_equal(cen_out, cen, equal_nan=True)                  # centres untouched
+    assert np.all(m12[::7] == -1)
+    hit = np.flatnonzero(m12 >= 0)
+    assert n == len(hit) and n > 300
+    assert len(np.unique(m12[hit])) == len(hit)                          # one-to-one by construction of gate 1
+    oct1, oct2 = k1["octave"][hit], k2["octave"][m12[hit]]
+    assert np.all(np.abs(oct1 - oct2) <= 1)
+    r = 7.0 * np.asarray(sf, np.float32)[oct1]
+    assert np.all(np.abs(k2["x"][m12[hit]] - cen[hit, 0]) < r) and np.all(np.abs(k2["y"][m12[hit]] - cen[hit, 1]) < r)
+    dist = np.unpackbits(d1[hit] ^ d2[m12[hit]], axis=1).sum(1)
+    assert np.all(dist <= 100)
