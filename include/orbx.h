@@ -15,6 +15,7 @@
  *   orbm_hamming_pairs_host          ORBmatcher::DescriptorDistance    include/ORBmatcher.h:19, src/ORBmatcher.cpp:128-144
  *   orbm_knn2_* / orbm_ratio_select  best-2 scan + acceptance          src/ORBmatcher.cpp:37-67
  *   orbm_search_init_device          ORBmatcher::SearchForInitialization + Frame grid   src/ORBmatcher.cpp:9-126, src/Frame.cpp:144-168,219-271
+ *   orbm_search_window_device        ORBmatcher::SearchByProjection (empty in the reference) over Frame::GetFeaturesInArea   include/ORBmatcher.h:24, src/Frame.cpp:219-271
  *   orbm_merge_shards_device         (database sharding; no reference counterpart)
  *
  * All functions return 0 on success or a negative ORBX_E_* code; nothing throws across the ABI.

@@ -152,6 +152,69 @@ static void linear_table(int ssize, int dsize, bool clamp, std::vector<int2> &ta
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+static int host_reflect101(int i, int n)
+{
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) i = i < 0 ? -i : 2 * (n - 1) - i;
+    return i;
+}
+
+constexpr int kResizeRowsHost = 8;     // = kResizeRows in pyramid.cu
+
+// Padded tables and shared-memory tile bounds of the staged resize kernel (pyramid.cu).  tabx / taby of level L must
+// already be in `tab`.  Tile bounds are maxima over every block of the launch grid, for both border widths.
+static void staged_resize_tables(const LevelGeom &S, LevelGeom &L, std::vector<int2> &tab)
+{
+    while (tab.size() & 3) tab.push_back(make_int2(0, 0));
+    L.tabxp = (int)tab.size();
+    for (int i = 0; i < L.pitch; ++i) {
+        const int X = std::min(std::max(i - kPadX, -kBorder), L.w + kBorder - 1);
+        const int2 t = tab[(size_t)L.tabx + (size_t)host_reflect101(X, L.w)];
+        tab.push_back(t);
+    }
+    while (tab.size() & 3) tab.push_back(make_int2(0, 0));
+    L.tabyp = (int)tab.size();
+    for (int i = 0; i < L.h + 2 * kBorder; ++i) {
+        const int2 t = tab[(size_t)L.taby + (size_t)host_reflect101(i - kBorder, L.h)];
+        const int sy0 = std::min(std::max(t.x, 0), S.h - 1), sy1 = std::min(std::max(t.x + 1, 0), S.h - 1);
+        tab.push_back(make_int2(sy0 | (sy1 << 16), t.y));
+    }
+    const int chunks = L.pitch / 4;
+    L.rs_bw = chunks > 64 ? 128 : 64;                 // small levels: narrower blocks so that few lanes idle past the end of a row
+    // horizontal: every pair of neighbouring pixels must fit an 8-byte window (pair offsets <= 3 apart)
+    L.rs_staged = S.h < 65536 ? 1 : 0;
+    int tile_w = 16;
+    for (int B : { kMinBlurBorder, kBorder }) {
+        for (int c0 = 0; c0 < chunks; c0 += L.rs_bw) {
+            int lo = INT_MAX, hi = -1;
+            for (int c = c0; c < std::min(c0 + L.rs_bw, chunks); ++c) {
+                const int X0 = c * 4 - kPadX;
+                if (X0 + 3 < -B || X0 >= L.w + B) continue;
+                for (int k = 0; k < 4; ++k) {
+                    const int o = tab[(size_t)L.tabxp + (size_t)(c * 4 + k)].x;
+                    lo = std::min(lo, o); hi = std::max(hi, o);
+                }
+                for (int k = 0; k < 4; k += 2)
+                    if (std::abs(tab[(size_t)L.tabxp + (size_t)(c * 4 + k)].x - tab[(size_t)L.tabxp + (size_t)(c * 4 + k + 1)].x) > 3) L.rs_staged = 0;
+            }
+            if (hi >= 0) tile_w = std::max(tile_w, hi + 1 - (lo & ~15) + 8);
+        }
+    }
+    L.rs_tile_w = (tile_w + 15) / 16 * 16;
+    int tile_h = 1;
+    for (int B : { kMinBlurBorder, kBorder })
+        for (int Y0 = -B; Y0 < L.h + B; Y0 += kResizeRowsHost) {
+            int lo = INT_MAX, hi = -1;
+            for (int Y = Y0; Y < std::min(Y0 + kResizeRowsHost, L.h + B); ++Y) {
+                const int v = tab[(size_t)L.tabyp + (size_t)(Y + kBorder)].x;
+                lo = std::min(lo, v & 0xffff); hi = std::max(hi, v >> 16);
+            }
+            tile_h = std::max(tile_h, hi - lo + 1);
+        }
+    L.rs_tile_h = tile_h;
+    if ((size_t)L.rs_tile_w * (size_t)L.rs_tile_h + 64 > 40 * 1024) L.rs_staged = 0;
+}
+
 // geometry for frames of w x h (buffer offsets assume max_batch frames per level)
 static int build_geometry(const orbx_extractor *ex, int w, int h, Geo &g, std::vector<int2> *tables)
 {
@@ -205,6 +268,7 @@ static int build_geometry(const orbx_extractor *ex, int w, int h, Geo &g, std::v
             while (tables->size() & 3) tables->push_back(make_int2(0, 0));   // 32-byte aligned runs for int4 loads
             L.tabx = (int)tables->size(); linear_table(g.lv[l - 1].w, L.w, true, *tables);
             L.taby = (int)tables->size(); linear_table(g.lv[l - 1].h, L.h, false, *tables);
+            staged_resize_tables(g.lv[l - 1], L, *tables);
         }
     }
     g.total_cells = cell_off;
@@ -287,7 +351,7 @@ extern "C" int orbx_create(const orbx_params *p, int max_width, int max_height, 
     const size_t F = (size_t)max_batch;
     DevBuffers &b = ex->buf;
     size_t ntab = 0;
-    for (int l = 1; l < g.nlevels; ++l) ntab += (size_t)g.lv[l].w + g.lv[l].h;
+    for (int l = 1; l < g.nlevels; ++l) ntab += (size_t)g.lv[l].w + 2 * (size_t)g.lv[l].h + (size_t)g.lv[l].pitch + 2 * kBorder + 16;   // plain + padded tables
 #define TRY(x) do { rc = (x); if (rc) { orbx_destroy(ex); return rc; } } while (0)
     TRY(dev_alloc(ex, &b.pyr, g.pyr_frame_total));
     TRY(dev_alloc(ex, &b.blur, g.blur_frame_total));

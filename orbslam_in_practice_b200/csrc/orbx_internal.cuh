@@ -46,6 +46,12 @@ struct LevelGeom {
     int patch_size;           // (int)(31 * scale), ORBextractor.cpp:794
     // resize tables (levels >= 1): entries {src offset, c0 | c1 << 16}
     int tabx, taby;           // offsets into the int2 table array
+    // staged resize (pyramid.cu k_resize): padded tables indexed by padded coordinates, tile bounds from the host
+    int tabxp;                // [pitch] entry(i) = tabx[reflect101(clamp(i - kPadX, -19, w + 18))]
+    int tabyp;                // [h + 38] entry(Y + 19) = {sy0 | sy1 << 16 (clamped source rows), cy0 | cy1 << 16}
+    int rs_bw;                // threads per block (4 pixels each)
+    int rs_tile_w, rs_tile_h; // shared-memory source tile: bytes per row (multiple of 16) and rows, maxima over all blocks
+    int rs_staged;            // 0: the level needs the gather kernel (adjacent source offsets further than 3 apart: scale > 3)
 };
 
 struct Geo {

@@ -105,7 +105,7 @@ k_level0(const __grid_constant__ Geo g, uint8_t *__restrict__ pyr, const uint8_t
 constexpr int kResizeRows = 8;
 
 __global__ void __launch_bounds__(128, 10)
-k_resize(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr_src, uint8_t *__restrict__ pyr_dst,
+k_resize_gather(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr_src, uint8_t *__restrict__ pyr_dst,
          const int2 *__restrict__ tables, int level)
 {
     const LevelGeom &D = g.lv[level];
@@ -188,6 +188,126 @@ k_resize(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr_src, uin
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Staged variant (the one that runs for every scale factor <= 3).  ncu, round 1: the gather kernel above
+// spent ~47 lane-instructions per pixel, most of them 64-bit address arithmetic and byte packing around
+// eight LDG.U8 per four pixels.  Here a block first stages the source rows it needs in shared memory with
+// 16-byte loads; a thread then gets the two taps of TWO neighbouring pixels with two aligned LDS.32 and one
+// PRMT (the four bytes lie inside an 8-byte window because neighbouring source offsets are <= 3 apart --
+// checked on the host), and IDP.2A does both multiplies of a pixel: ~14 instructions per interpolated row of
+// four pixels instead of ~50.  Border pixels need no special case: the padded tables hold their reflected
+// source coordinates and PRMT does not care about the order of the bytes it picks.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 10)
+k_resize(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr_src, uint8_t *__restrict__ pyr_dst,
+         const int2 *__restrict__ tables, int level)
+{
+    extern __shared__ __align__(16) unsigned char rs_tile[];
+    __shared__ int s_lo[4], s_hi[4];
+    const LevelGeom &D = g.lv[level];
+    const LevelGeom &S = g.lv[level - 1];
+    const int B = g.border_on ? kBorder : kMinBlurBorder;
+    const int f = blockIdx.z + g.frame0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int chunk = blockIdx.x * blockDim.x + threadIdx.x;
+    const int X0 = chunk * 4 - kPadX;
+    const bool active = chunk * 4 < D.pitch && X0 + 3 >= -B && X0 < D.w + B;
+    const int Ybase = (int)blockIdx.y * kResizeRows - B;
+    const int TP = D.rs_tile_w;
+
+    // horizontal parameters of the thread's four pixels (padded table: no reflect / clamp here)
+    int o0[4]; uint32_t cf[4];
+    {
+        const int4 *tx = reinterpret_cast<const int4 *>(tables + D.tabxp) + (active ? chunk * 2 : 0);
+        const int4 t01 = __ldg(tx), t23 = __ldg(tx + 1);
+        o0[0] = t01.x; cf[0] = (uint32_t)t01.y; o0[1] = t01.z; cf[1] = (uint32_t)t01.w;
+        o0[2] = t23.x; cf[2] = (uint32_t)t23.y; o0[3] = t23.z; cf[3] = (uint32_t)t23.w;
+    }
+    // vertical parameters of the block's rows: lane r & 7 holds row r
+    const int2 tyl = __ldg(tables + D.tabyp + min(Ybase + (lane & 7), D.h + B - 1) + kBorder);
+    const int smin = __reduce_min_sync(0xffffffffu, tyl.x & 0xffff), smax = __reduce_max_sync(0xffffffffu, tyl.x >> 16);
+    // source columns the block touches
+    {
+        const int lo = active ? min(min(o0[0], o0[1]), min(o0[2], o0[3])) : 0x7fffffff;
+        const int hi = active ? max(max(o0[0], o0[1]), max(o0[2], o0[3])) : -1;
+        const int wlo = __reduce_min_sync(0xffffffffu, lo), whi = __reduce_max_sync(0xffffffffu, hi);
+        if (lane == 0) { s_lo[warp] = wlo; s_hi[warp] = whi; }
+    }
+    __syncthreads();
+    int xlo = s_lo[0], xhi = s_hi[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { xlo = min(xlo, s_lo[w]); xhi = max(xhi, s_hi[w]); }
+    if (xhi < 0) return;                                   // no active pixel in this block (uniform)
+    const int tx0 = xlo & ~15;
+    const uint8_t *__restrict__ src = pyr_src + S.base + (size_t)f * S.frame_stride + (size_t)(kPadY + smin) * S.pitch + kPadX + tx0;
+    {
+        const int nvec = ((xhi + 1 - tx0) >> 4) + 1, nrows = smax - smin + 1, total = nvec * nrows;
+        const int inv = (65536 + nvec - 1) / nvec;        // row = i / nvec for i < 65536 / nvec
+        for (int i = threadIdx.x; i < total; i += blockDim.x) {
+            const int row = (i * inv) >> 16, v = i - row * nvec;
+            *reinterpret_cast<uint4 *>(rs_tile + row * TP + v * 16) = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)row * S.pitch) + v);
+        }
+    }
+    __syncthreads();
+    if (!active) return;
+
+    // per pixel pair: 8-byte window base inside a tile row and the PRMT selector {p0_a, p1_a, p0_b, p1_b}
+    int pbase[2]; uint32_t psel[2];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int a = o0[2 * j] - tx0, b = o0[2 * j + 1] - tx0;
+        pbase[j] = min(a, b) & ~3;
+        const uint32_t da = (uint32_t)(a - pbase[j]), db = (uint32_t)(b - pbase[j]);
+        psel[j] = da | ((da + 1) << 4) | (db << 8) | ((db + 1) << 12);
+    }
+    uint8_t *drow = pyr_dst + D.base + (size_t)f * D.frame_stride + (size_t)chunk * 4 + (size_t)(Ybase + kPadY) * D.pitch;
+    int prev_sy1 = -1;
+    int hp[4] = { 0, 0, 0, 0 };                           // horizontally interpolated lower source row, already >> 4
+    const int2 *typ = tables + D.tabyp + kBorder;
+    int2 ty_next = __ldg(typ + min(Ybase, D.h + B - 1));
+    auto hrow = [&](int sy, int (&h)[4]) {
+        const unsigned char *t = rs_tile + (sy - smin) * TP;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const uint32_t w0 = *reinterpret_cast<const uint32_t *>(t + pbase[j]), w1 = *reinterpret_cast<const uint32_t *>(t + pbase[j] + 4);
+            const uint32_t P = __byte_perm(w0, w1, psel[j]);
+            h[2 * j] = (int)(__dp2a_lo(cf[2 * j], P, 0u) >> 4);
+            h[2 * j + 1] = (int)(__dp2a_hi(cf[2 * j + 1], P, 0u) >> 4);
+        }
+    };
+#pragma unroll 2
+    for (int r = 0; r < kResizeRows; ++r, drow += D.pitch) {
+        if (Ybase + r >= D.h + B) break;
+        // (lanes of this warp may have exited, so the row entry is re-read -- an L1 broadcast hit -- not shuffled)
+        const int2 ty = ty_next;
+        ty_next = __ldg(typ + min(Ybase + r + 1, D.h + B - 1));
+        const int sy0 = ty.x & 0xffff, sy1 = ty.x >> 16;
+        const int cy0 = (short)(ty.y & 0xffff), cy1 = ty.y >> 16;
+        int h0[4], h1[4];
+        if (sy0 == prev_sy1) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) h0[k] = hp[k];
+        } else {
+            hrow(sy0, h0);
+        }
+        if (sy1 == sy0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) h1[k] = h0[k];
+        } else {
+            hrow(sy1, h1);
+        }
+        // ((b0 * (H0 >> 4)) >> 16) + ((b1 * (H1 >> 4)) >> 16) + 2) >> 2 never leaves [0, 255] (see k_resize_gather)
+        uint32_t out = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t v = (uint32_t)(((cy0 * h0[k]) >> 16) + ((cy1 * h1[k]) >> 16) + 2) >> 2;
+            out |= v << (8 * k);
+            hp[k] = h1[k];
+        }
+        prev_sy1 = sy1;
+        *reinterpret_cast<uint32_t *>(drow) = out;
+    }
+}
+
 // copyMakeBorder(REFLECT_101) of one level of one frame, on demand (orbx_download_level with border = 19)
 __global__ void k_fill_border(const __grid_constant__ Geo g, uint8_t *__restrict__ pyr, int level, int frame)
 {
@@ -217,11 +337,14 @@ void launch_level0(const Geo &g, const DevBuffers &b, const uint8_t *d_imgs, siz
 void launch_resize(const Geo &g, const DevBuffers &b, int level, int nframes, cudaStream_t s)
 {
     const int B = g.border_on ? kBorder : kMinBlurBorder;
-    const int chunks = g.lv[level].pitch / 4;
-    // small levels: narrower blocks so that few lanes idle past the end of a row
-    const int bw = chunks > 64 ? 128 : 64;
-    dim3 grd((chunks + bw - 1) / bw, (g.lv[level].h + 2 * B + kResizeRows - 1) / kResizeRows, nframes);
-    k_resize<<<grd, bw, 0, s>>>(g, b.pyr, b.pyr, b.tables, level);
+    const LevelGeom &L = g.lv[level];
+    const int chunks = L.pitch / 4;
+    const int bw = L.rs_bw;
+    dim3 grd((chunks + bw - 1) / bw, (L.h + 2 * B + kResizeRows - 1) / kResizeRows, nframes);
+    if (L.rs_staged)
+        k_resize<<<grd, bw, (size_t)L.rs_tile_w * L.rs_tile_h, s>>>(g, b.pyr, b.pyr, b.tables, level);
+    else
+        k_resize_gather<<<grd, bw, 0, s>>>(g, b.pyr, b.pyr, b.tables, level);
 }
 
 } // namespace orbx
