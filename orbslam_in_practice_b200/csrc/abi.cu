@@ -61,6 +61,7 @@ struct orbx_extractor {
     cudaEvent_t ev_fork[kMaxChunks], ev_join[kMaxChunks];
     unsigned fork_slot;
     int oct_smem;
+    size_t tables_cap;                            // int2 entries allocated for buf.tables
     long long launches;
     // reference tables
     float scale[ORBX_MAX_LEVELS], inv_scale[ORBX_MAX_LEVELS], sigma2[ORBX_MAX_LEVELS], inv_sigma2[ORBX_MAX_LEVELS];
@@ -159,10 +160,9 @@ static int host_reflect101(int i, int n)
     return i;
 }
 
-constexpr int kResizeRowsHost = 8;     // = kResizeRows in pyramid.cu
-
-// Padded tables and shared-memory tile bounds of the staged resize kernel (pyramid.cu).  tabx / taby of level L must
-// already be in `tab`.  Tile bounds are maxima over every block of the launch grid, for both border widths.
+// Padded tables and per-block source ranges of the staged resize kernel (pyramid.cu).  tabx / taby of level L must
+// already be in `tab`.  Everything a block needs to know about its source tile is precomputed here, for both border
+// widths (variant 0: kMinBlurBorder, variant 1: kBorder).
 static void staged_resize_tables(const LevelGeom &S, LevelGeom &L, std::vector<int2> &tab)
 {
     while (tab.size() & 3) tab.push_back(make_int2(0, 0));
@@ -181,41 +181,48 @@ static void staged_resize_tables(const LevelGeom &S, LevelGeom &L, std::vector<i
     }
     const int chunks = L.pitch / 4;
     L.rs_bw = chunks > 64 ? 128 : 64;                 // small levels: narrower blocks so that few lanes idle past the end of a row
-    // horizontal: every pair of neighbouring pixels must fit an 8-byte window (pair offsets <= 3 apart)
-    L.rs_staged = S.h < 65536 ? 1 : 0;
+    L.rs_nbx = (chunks + L.rs_bw - 1) / L.rs_bw;
+    L.rs_staged = S.h < 32768 ? 1 : 0;
+    const int Bv[2] = { kMinBlurBorder, kBorder };
     int tile_w = 16;
-    for (int B : { kMinBlurBorder, kBorder }) {
-        for (int c0 = 0; c0 < chunks; c0 += L.rs_bw) {
+    L.rs_xr = (int)tab.size();
+    for (int v = 0; v < 2; ++v)
+        for (int bx = 0; bx < L.rs_nbx; ++bx) {
             int lo = INT_MAX, hi = -1;
-            for (int c = c0; c < std::min(c0 + L.rs_bw, chunks); ++c) {
+            for (int c = bx * L.rs_bw; c < std::min((bx + 1) * L.rs_bw, chunks); ++c) {
                 const int X0 = c * 4 - kPadX;
-                if (X0 + 3 < -B || X0 >= L.w + B) continue;
+                if (X0 + 3 < -Bv[v] || X0 >= L.w + Bv[v]) continue;
                 for (int k = 0; k < 4; ++k) {
                     const int o = tab[(size_t)L.tabxp + (size_t)(c * 4 + k)].x;
                     lo = std::min(lo, o); hi = std::max(hi, o);
                 }
+                // every pair of neighbouring pixels must fit an 8-byte window: source offsets at most 3 apart
                 for (int k = 0; k < 4; k += 2)
                     if (std::abs(tab[(size_t)L.tabxp + (size_t)(c * 4 + k)].x - tab[(size_t)L.tabxp + (size_t)(c * 4 + k + 1)].x) > 3) L.rs_staged = 0;
             }
             if (hi >= 0) tile_w = std::max(tile_w, hi + 1 - (lo & ~15) + 8);
+            tab.push_back(make_int2(hi >= 0 ? lo : 0, hi));           // hi = -1: no pixel of this block is inside the bordered level
         }
-    }
     L.rs_tile_w = (tile_w + 15) / 16 * 16;
     int tile_h = 1;
-    for (int B : { kMinBlurBorder, kBorder })
-        for (int Y0 = -B; Y0 < L.h + B; Y0 += kResizeRowsHost) {
+    L.rs_yr = (int)tab.size();
+    for (int v = 0; v < 2; ++v) {
+        const int B = Bv[v], nby = (L.h + 2 * B + kResizeRows - 1) / kResizeRows;
+        if (v == 0) L.rs_nby0 = nby;
+        for (int by = 0; by < nby; ++by) {
             int lo = INT_MAX, hi = -1;
-            for (int Y = Y0; Y < std::min(Y0 + kResizeRowsHost, L.h + B); ++Y) {
-                const int v = tab[(size_t)L.tabyp + (size_t)(Y + kBorder)].x;
-                lo = std::min(lo, v & 0xffff); hi = std::max(hi, v >> 16);
+            for (int Y = by * kResizeRows - B; Y < std::min((by + 1) * kResizeRows - B, L.h + B); ++Y) {
+                const int e = tab[(size_t)L.tabyp + (size_t)(Y + kBorder)].x;
+                lo = std::min(lo, e & 0xffff); hi = std::max(hi, e >> 16);
             }
             tile_h = std::max(tile_h, hi - lo + 1);
+            tab.push_back(make_int2(lo, hi));
         }
+    }
     L.rs_tile_h = tile_h;
-    if ((size_t)L.rs_tile_w * (size_t)L.rs_tile_h + 64 > 40 * 1024) L.rs_staged = 0;
+    if ((size_t)L.rs_tile_w * (size_t)L.rs_tile_h + 1024 > 46 * 1024) L.rs_staged = 0;
 }
 
-// geometry for frames of w x h (buffer offsets assume max_batch frames per level)
 static int build_geometry(const orbx_extractor *ex, int w, int h, Geo &g, std::vector<int2> *tables)
 {
     std::memset(&g, 0, sizeof(g));
@@ -302,6 +309,7 @@ static int upload_geometry(orbx_extractor *ex, int w, int h)
         return ORBX_E_CAPACITY;
     ex->geo = ng;
     ex->geo.capacity = ex->full.capacity;   // output row stride stays the creation capacity
+    if (tables.size() > ex->tables_cap) return ORBX_E_CAPACITY;
     if (!tables.empty()) CK(cudaMemcpyAsync(ex->buf.tables, tables.data(), tables.size() * sizeof(int2), cudaMemcpyHostToDevice, ex->stream));
     CK(cudaStreamSynchronize(ex->stream));   // `tables` is pageable host memory about to go out of scope
     ex->cur_w = w; ex->cur_h = h;
@@ -351,11 +359,13 @@ extern "C" int orbx_create(const orbx_params *p, int max_width, int max_height, 
     const size_t F = (size_t)max_batch;
     DevBuffers &b = ex->buf;
     size_t ntab = 0;
-    for (int l = 1; l < g.nlevels; ++l) ntab += (size_t)g.lv[l].w + 2 * (size_t)g.lv[l].h + (size_t)g.lv[l].pitch + 2 * kBorder + 16;   // plain + padded tables
+    for (int l = 1; l < g.nlevels; ++l) ntab += (size_t)g.lv[l].w + 2 * (size_t)g.lv[l].h + (size_t)g.lv[l].pitch + 2 * kBorder + 16 +
+                                               2 * ((size_t)g.lv[l].pitch / 256 + 2) + 2 * ((size_t)(g.lv[l].h + 2 * kBorder) / kResizeRows + 2);   // plain + padded tables + block ranges
 #define TRY(x) do { rc = (x); if (rc) { orbx_destroy(ex); return rc; } } while (0)
     TRY(dev_alloc(ex, &b.pyr, g.pyr_frame_total));
     TRY(dev_alloc(ex, &b.blur, g.blur_frame_total));
-    TRY(dev_alloc(ex, &b.tables, ntab + 8 * ORBX_MAX_LEVELS));
+    ex->tables_cap = ntab + 8 * ORBX_MAX_LEVELS;
+    TRY(dev_alloc(ex, &b.tables, ex->tables_cap));
     TRY(dev_alloc(ex, &b.cell_count, F * g.total_cells));
     TRY(dev_alloc(ex, &b.cell_slots, F * g.slots_per_frame));
     TRY(dev_alloc(ex, &b.keysA, F * g.keys_per_frame));

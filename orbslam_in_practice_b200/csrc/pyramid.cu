@@ -96,13 +96,13 @@ k_level0(const __grid_constant__ Geo g, uint8_t *__restrict__ pyr, const uint8_t
 }
 
 // ---------------------------------------------------------------------------------------------
-// level l >= 1 from level l-1.  One thread = 4 consecutive pixels x kResizeRows rows of the padded
+// level l >= 1 from level l-1.  One thread = 4 consecutive pixels x kGatherRows rows of the padded
 // destination.  The horizontal parameters (source offsets, 11-bit coefficients) are unpacked once
 // and reused for every row; the row index depends only on blockIdx, so source-row pointers are
 // warp-uniform; and, like OpenCV's row cache, the horizontally interpolated lower source row is
 // reused when the next destination row starts on it (scale 1.2: ~5 of 6 rows).
 // ---------------------------------------------------------------------------------------------
-constexpr int kResizeRows = 8;
+constexpr int kGatherRows = 8;
 
 __global__ void __launch_bounds__(128, 10)
 k_resize_gather(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr_src, uint8_t *__restrict__ pyr_dst,
@@ -143,7 +143,7 @@ k_resize_gather(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr_s
         c1[k] = c0[k] >> 16; c0[k] = (short)(c0[k] & 0xffff);
     }
     const int2 *taby = tables + D.taby;
-    const int Ybase = (int)blockIdx.y * kResizeRows - B;
+    const int Ybase = (int)blockIdx.y * kGatherRows - B;
     const int spitch = S.pitch;
     // the y-table entry of the NEXT row is fetched one iteration ahead: otherwise every row pays two dependent
     // global-load latencies (table entry -> source row pointer -> pixels)
@@ -152,7 +152,7 @@ k_resize_gather(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr_s
     int hp[4] = { 0, 0, 0, 0 };                           // horizontally interpolated lower source row, already >> 4
     uint8_t *drow = dst + (size_t)(Ybase + kPadY) * D.pitch;
 #pragma unroll 2
-    for (int r = 0; r < kResizeRows; ++r, drow += D.pitch) {
+    for (int r = 0; r < kGatherRows; ++r, drow += D.pitch) {
         const int Y = Ybase + r;
         if (Y >= D.h + B) break;
         const int2 ty = ty_next;
@@ -198,74 +198,65 @@ k_resize_gather(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr_s
 // four pixels instead of ~50.  Border pixels need no special case: the padded tables hold their reflected
 // source coordinates and PRMT does not care about the order of the bytes it picks.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 10)
+__global__ void __launch_bounds__(128, 8)
 k_resize(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr_src, uint8_t *__restrict__ pyr_dst,
          const int2 *__restrict__ tables, int level)
 {
     extern __shared__ __align__(16) unsigned char rs_tile[];
-    __shared__ int s_lo[4], s_hi[4];
+    __shared__ int4 s_ty[kResizeRows];                     // per destination row: tile byte offsets of the two source rows, cy0, cy1
     const LevelGeom &D = g.lv[level];
     const LevelGeom &S = g.lv[level - 1];
-    const int B = g.border_on ? kBorder : kMinBlurBorder;
+    const int var = g.border_on ? 1 : 0;
+    const int B = var ? kBorder : kMinBlurBorder;
     const int f = blockIdx.z + g.frame0;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int chunk = blockIdx.x * blockDim.x + threadIdx.x;
     const int X0 = chunk * 4 - kPadX;
     const bool active = chunk * 4 < D.pitch && X0 + 3 >= -B && X0 < D.w + B;
     const int Ybase = (int)blockIdx.y * kResizeRows - B;
     const int TP = D.rs_tile_w;
-
-    // horizontal parameters of the thread's four pixels (padded table: no reflect / clamp here)
-    int o0[4]; uint32_t cf[4];
-    {
-        const int4 *tx = reinterpret_cast<const int4 *>(tables + D.tabxp) + (active ? chunk * 2 : 0);
-        const int4 t01 = __ldg(tx), t23 = __ldg(tx + 1);
-        o0[0] = t01.x; cf[0] = (uint32_t)t01.y; o0[1] = t01.z; cf[1] = (uint32_t)t01.w;
-        o0[2] = t23.x; cf[2] = (uint32_t)t23.y; o0[3] = t23.z; cf[3] = (uint32_t)t23.w;
+    // source ranges of this block, precomputed on the host: columns [xr.x, xr.y] (+1 for the second tap), rows [yr.x, yr.y]
+    const int2 xr = __ldg(tables + D.rs_xr + var * D.rs_nbx + blockIdx.x);
+    const int2 yr = __ldg(tables + D.rs_yr + var * D.rs_nby0 + blockIdx.y);
+    if (xr.y < 0) return;                                  // no pixel of this block lies inside the bordered level (uniform)
+    const int tx0 = xr.x & ~15, smin = yr.x;
+    if (threadIdx.x < kResizeRows) {
+        const int2 t = __ldg(tables + D.tabyp + kBorder + min(Ybase + (int)threadIdx.x, D.h + B - 1));
+        s_ty[threadIdx.x] = make_int4(((t.x & 0xffff) - smin) * TP, ((t.x >> 16) - smin) * TP, (short)(t.y & 0xffff), t.y >> 16);
     }
-    // vertical parameters of the block's rows: lane r & 7 holds row r
-    const int2 tyl = __ldg(tables + D.tabyp + min(Ybase + (lane & 7), D.h + B - 1) + kBorder);
-    const int smin = __reduce_min_sync(0xffffffffu, tyl.x & 0xffff), smax = __reduce_max_sync(0xffffffffu, tyl.x >> 16);
-    // source columns the block touches
     {
-        const int lo = active ? min(min(o0[0], o0[1]), min(o0[2], o0[3])) : 0x7fffffff;
-        const int hi = active ? max(max(o0[0], o0[1]), max(o0[2], o0[3])) : -1;
-        const int wlo = __reduce_min_sync(0xffffffffu, lo), whi = __reduce_max_sync(0xffffffffu, hi);
-        if (lane == 0) { s_lo[warp] = wlo; s_hi[warp] = whi; }
-    }
-    __syncthreads();
-    int xlo = s_lo[0], xhi = s_hi[0];
-    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { xlo = min(xlo, s_lo[w]); xhi = max(xhi, s_hi[w]); }
-    if (xhi < 0) return;                                   // no active pixel in this block (uniform)
-    const int tx0 = xlo & ~15;
-    const uint8_t *__restrict__ src = pyr_src + S.base + (size_t)f * S.frame_stride + (size_t)(kPadY + smin) * S.pitch + kPadX + tx0;
-    {
-        const int nvec = ((xhi + 1 - tx0) >> 4) + 1, nrows = smax - smin + 1, total = nvec * nrows;
-        const int inv = (65536 + nvec - 1) / nvec;        // row = i / nvec for i < 65536 / nvec
+        const uint8_t *__restrict__ src = pyr_src + S.base + (size_t)f * S.frame_stride + (size_t)(kPadY + smin) * S.pitch + kPadX + tx0;
+        const int nvec = ((xr.y + 1 - tx0) >> 4) + 1, total = nvec * (yr.y - smin + 1);
+        const int inv = __float2int_rz(__fdividef(65536.f, (float)nvec)) + 1;   // row = i / nvec exactly for i * nvec < 65536
         for (int i = threadIdx.x; i < total; i += blockDim.x) {
             const int row = (i * inv) >> 16, v = i - row * nvec;
             *reinterpret_cast<uint4 *>(rs_tile + row * TP + v * 16) = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)row * S.pitch) + v);
         }
     }
+    // horizontal parameters of the thread's four pixels (padded table: no reflect / clamp here)
+    int pbase[2]; uint32_t psel[2], cf[4];
+    if (active) {
+        const int4 *tx = reinterpret_cast<const int4 *>(tables + D.tabxp) + chunk * 2;
+        const int4 t01 = __ldg(tx), t23 = __ldg(tx + 1);
+        cf[0] = (uint32_t)t01.y; cf[1] = (uint32_t)t01.w; cf[2] = (uint32_t)t23.y; cf[3] = (uint32_t)t23.w;
+        const int o0[4] = { t01.x - tx0, t01.z - tx0, t23.x - tx0, t23.z - tx0 };
+        // per pixel pair: 8-byte window base inside a tile row and the PRMT selector {p0_a, p1_a, p0_b, p1_b}
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int a = o0[2 * j], b = o0[2 * j + 1];
+            pbase[j] = min(a, b) & ~3;
+            const uint32_t da = (uint32_t)(a - pbase[j]), db = (uint32_t)(b - pbase[j]);
+            psel[j] = da | ((da + 1) << 4) | (db << 8) | ((db + 1) << 12);
+        }
+    }
     __syncthreads();
     if (!active) return;
 
-    // per pixel pair: 8-byte window base inside a tile row and the PRMT selector {p0_a, p1_a, p0_b, p1_b}
-    int pbase[2]; uint32_t psel[2];
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        const int a = o0[2 * j] - tx0, b = o0[2 * j + 1] - tx0;
-        pbase[j] = min(a, b) & ~3;
-        const uint32_t da = (uint32_t)(a - pbase[j]), db = (uint32_t)(b - pbase[j]);
-        psel[j] = da | ((da + 1) << 4) | (db << 8) | ((db + 1) << 12);
-    }
     uint8_t *drow = pyr_dst + D.base + (size_t)f * D.frame_stride + (size_t)chunk * 4 + (size_t)(Ybase + kPadY) * D.pitch;
-    int prev_sy1 = -1;
+    const int nrows = min(kResizeRows, D.h + B - Ybase);
+    int prev_off1 = -1;
     int hp[4] = { 0, 0, 0, 0 };                           // horizontally interpolated lower source row, already >> 4
-    const int2 *typ = tables + D.tabyp + kBorder;
-    int2 ty_next = __ldg(typ + min(Ybase, D.h + B - 1));
-    auto hrow = [&](int sy, int (&h)[4]) {
-        const unsigned char *t = rs_tile + (sy - smin) * TP;
+    auto hrow = [&](int off, int (&h)[4]) {
+        const unsigned char *t = rs_tile + off;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             const uint32_t w0 = *reinterpret_cast<const uint32_t *>(t + pbase[j]), w1 = *reinterpret_cast<const uint32_t *>(t + pbase[j] + 4);
@@ -275,35 +266,30 @@ k_resize(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr_src, uin
         }
     };
 #pragma unroll 2
-    for (int r = 0; r < kResizeRows; ++r, drow += D.pitch) {
-        if (Ybase + r >= D.h + B) break;
-        // (lanes of this warp may have exited, so the row entry is re-read -- an L1 broadcast hit -- not shuffled)
-        const int2 ty = ty_next;
-        ty_next = __ldg(typ + min(Ybase + r + 1, D.h + B - 1));
-        const int sy0 = ty.x & 0xffff, sy1 = ty.x >> 16;
-        const int cy0 = (short)(ty.y & 0xffff), cy1 = ty.y >> 16;
+    for (int r = 0; r < nrows; ++r, drow += D.pitch) {
+        const int4 ty = s_ty[r];                           // {offset of source row 0, of source row 1, cy0, cy1}
         int h0[4], h1[4];
-        if (sy0 == prev_sy1) {
+        if (ty.x == prev_off1) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) h0[k] = hp[k];
         } else {
-            hrow(sy0, h0);
+            hrow(ty.x, h0);
         }
-        if (sy1 == sy0) {
+        if (ty.y == ty.x) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) h1[k] = h0[k];
         } else {
-            hrow(sy1, h1);
+            hrow(ty.y, h1);
         }
         // ((b0 * (H0 >> 4)) >> 16) + ((b1 * (H1 >> 4)) >> 16) + 2) >> 2 never leaves [0, 255] (see k_resize_gather)
         uint32_t out = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const uint32_t v = (uint32_t)(((cy0 * h0[k]) >> 16) + ((cy1 * h1[k]) >> 16) + 2) >> 2;
+            const uint32_t v = (uint32_t)(((ty.z * h0[k]) >> 16) + ((ty.w * h1[k]) >> 16) + 2) >> 2;
             out |= v << (8 * k);
             hp[k] = h1[k];
         }
-        prev_sy1 = sy1;
+        prev_off1 = ty.y;
         *reinterpret_cast<uint32_t *>(drow) = out;
     }
 }
@@ -340,7 +326,8 @@ void launch_resize(const Geo &g, const DevBuffers &b, int level, int nframes, cu
     const LevelGeom &L = g.lv[level];
     const int chunks = L.pitch / 4;
     const int bw = L.rs_bw;
-    dim3 grd((chunks + bw - 1) / bw, (L.h + 2 * B + kResizeRows - 1) / kResizeRows, nframes);
+    const int rows = L.rs_staged ? kResizeRows : kGatherRows;
+    dim3 grd((chunks + bw - 1) / bw, (L.h + 2 * B + rows - 1) / rows, nframes);
     if (L.rs_staged)
         k_resize<<<grd, bw, (size_t)L.rs_tile_w * L.rs_tile_h, s>>>(g, b.pyr, b.pyr, b.tables, level);
     else

@@ -216,9 +216,12 @@ def test_strided_host_input_and_two_handles(orbx, oracle):
 @pytest.mark.parametrize("params", [dict(nfeatures=50, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7),
                                     dict(nfeatures=3000, scale_factor=1.1, nlevels=12, ini_th=12, min_th=5),
                                     dict(nfeatures=700, scale_factor=2.0, nlevels=3, ini_th=40, min_th=40),
-                                    dict(nfeatures=400, scale_factor=1.2, nlevels=1, ini_th=7, min_th=20)])
+                                    dict(nfeatures=400, scale_factor=1.2, nlevels=1, ini_th=7, min_th=20),
+                                    dict(nfeatures=300, scale_factor=2.9, nlevels=3, ini_th=20, min_th=7),
+                                    dict(nfeatures=300, scale_factor=3.6, nlevels=2, ini_th=20, min_th=7)])
 def test_parameter_corners(orbx, oracle, params):
-    """Tiny and huge quotas (phase-2-only and never-phase-2 octrees), many / one level, iniTh < minTh."""
+    """Tiny and huge quotas (phase-2-only and never-phase-2 octrees), many / one level, iniTh < minTh, and scale
+    factors at / beyond the staged resize kernel's limit of 3 (3.6 runs the gather kernel)."""
     img = synth_frame(77)
     ex = orbx.Extractor(max_width=640, max_height=480, max_batch=1, **params)
     oex = oracle.OracleExtractor(**params)
