@@ -62,6 +62,8 @@ struct orbx_extractor {
     unsigned fork_slot;
     int oct_smem;
     size_t tables_cap;                            // int2 entries allocated for buf.tables
+    int device_split;                             // orbx_extract_device: independent sub-batches on two streams
+    cudaEvent_t ev_split_fork, ev_split_join;
     long long launches;
     // reference tables
     float scale[ORBX_MAX_LEVELS], inv_scale[ORBX_MAX_LEVELS], sigma2[ORBX_MAX_LEVELS], inv_sigma2[ORBX_MAX_LEVELS];
@@ -349,6 +351,10 @@ extern "C" int orbx_create(const orbx_params *p, int max_width, int max_height, 
         cudaStreamCreateWithFlags(&ex->s_aux[1], cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ex->s_h2d, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ex->s_d2h, cudaStreamNonBlocking) != cudaSuccess) { delete ex; return cuda_fail(cudaGetLastError(), "stream"); }
+    cudaEventCreateWithFlags(&ex->ev_split_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ex->ev_split_join, cudaEventDisableTiming);
+    ex->device_split = 2;
+    if (const char *e = std::getenv("ORBX_DEVICE_SPLIT")) { const int v = std::atoi(e); if (v >= 1 && v <= orbx_extractor::kMaxChunks) ex->device_split = v; }
     for (int i = 0; i < orbx_extractor::kMaxChunks; ++i) {
         cudaEventCreateWithFlags(&ex->ev_h2d[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ex->ev_done[i], cudaEventDisableTiming);
@@ -400,6 +406,8 @@ extern "C" int orbx_destroy(orbx_extractor *ex)
         if (ex->ev_fork[i]) cudaEventDestroy(ex->ev_fork[i]); if (ex->ev_join[i]) cudaEventDestroy(ex->ev_join[i]); }
     for (void *p : ex->allocs) cudaFree(p);
     if (ex->staging_color) cudaFree(ex->staging_color);
+    if (ex->ev_split_fork) cudaEventDestroy(ex->ev_split_fork);
+    if (ex->ev_split_join) cudaEventDestroy(ex->ev_split_join);
     for (auto &set : ex->ev) for (auto &e : set) if (e) cudaEventDestroy(e);
     delete ex;
     return ORBX_OK;
@@ -516,7 +524,21 @@ extern "C" int orbx_extract_device(orbx_extractor *ex, const uint8_t *d_imgs, si
     }
     if (width > ex->max_w || height > ex->max_h || nframes > ex->max_batch) return ORBX_E_CAPACITY;
     if (row_pitch < (size_t)width * ex->in_channels) return ORBX_E_INVALID;
-    return run_pipeline(ex, d_imgs, row_pitch, frame_stride, width, height, 0, nframes, d_kps, d_desc, d_counts, s);
+    // Large batches run as two independent halves on two streams: frames are independent, every kernel here is
+    // instruction-issue bound at 65-77 % issue utilisation, and the halves' different kernels (and their tail waves)
+    // fill each other's idle issue slots.  Profiling keeps one serial pass so that stage times stay attributable.
+    int nsplit = (!ex->profiling && nframes >= 32) ? ex->device_split : 1;
+    if (nsplit <= 1) return run_pipeline(ex, d_imgs, row_pitch, frame_stride, width, height, 0, nframes, d_kps, d_desc, d_counts, s);
+    CK(cudaEventRecord(ex->ev_split_fork, s));
+    CK(cudaStreamWaitEvent(ex->stream2, ex->ev_split_fork, 0));
+    for (int c = 0; c < nsplit; ++c) {
+        const int f0 = (int)((long long)nframes * c / nsplit), f1 = (int)((long long)nframes * (c + 1) / nsplit);
+        int rc = run_pipeline(ex, d_imgs, row_pitch, frame_stride, width, height, f0, f1 - f0, d_kps, d_desc, d_counts, (c & 1) ? ex->stream2 : s);
+        if (rc) return rc;
+    }
+    CK(cudaEventRecord(ex->ev_split_join, ex->stream2));
+    CK(cudaStreamWaitEvent(s, ex->ev_split_join, 0));
+    return ORBX_OK;
 }
 
 extern "C" int orbx_extract_host_end(orbx_extractor *ex)

@@ -29,7 +29,7 @@ __device__ __forceinline__ int reflect101d(int i, int n)
 // lane-instructions per pixel; this one ~13.
 // A warp covers 30 output word columns (120 px; lanes 0 and 31 are halo) x kBlurRows rows.
 // ---------------------------------------------------------------------------------------------
-constexpr int kBlurRows = 32;
+constexpr int kBlurRows = 35;                 // a multiple of the 7-row unrolled window: no rows computed and thrown away
 constexpr int kBlurWarps = 4;
 struct BlurRows { int first[ORBX_MAX_LEVELS + 1]; };   // first blockIdx.y of every level
 // DP2A weight words (low byte x low 16-bit lane, next byte x high lane).  Passed as a kernel parameter so that they
