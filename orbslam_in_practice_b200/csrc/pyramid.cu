@@ -226,9 +226,11 @@ k_resize(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr_src, uin
     {
         const uint8_t *__restrict__ src = pyr_src + S.base + (size_t)f * S.frame_stride + (size_t)(kPadY + smin) * S.pitch + kPadX + tx0;
         const int nvec = ((xr.y + 1 - tx0) >> 4) + 1, total = nvec * (yr.y - smin + 1);
-        const int inv = __float2int_rz(__fdividef(65536.f, (float)nvec)) + 1;   // row = i / nvec exactly for i * nvec < 65536
+        // row = i / nvec without an integer division: inv >= 2^32 / nvec with an excess below 2^11 (float rounding + margin),
+        // exact as long as i * nvec < 2^21 (a tile has < 2^16 vectors: the host caps it at 46 KB)
+        const uint32_t inv = __float2uint_rz(__fdividef(4294967296.f, (float)nvec)) + 1024u;
         for (int i = threadIdx.x; i < total; i += blockDim.x) {
-            const int row = (i * inv) >> 16, v = i - row * nvec;
+            const int row = nvec == 1 ? i : (int)__umulhi((uint32_t)i, inv), v = i - row * nvec;
             *reinterpret_cast<uint4 *>(rs_tile + row * TP + v * 16) = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)row * S.pitch) + v);
         }
     }

@@ -273,3 +273,35 @@ def test_begin_end_pipelining_across_two_handles(orbx, oracle):
         ks["octave"] = kps[:, :, 5].view(np.int32); ks["class_id"] = kps[:, :, 6].view(np.int32)
         for f in range(3):
             _compare_frame(oracle, e, oex, b[f], f, ks, hd.numpy(), hc.numpy(), check_stages=False)
+
+
+def _random_cases(n, seed):
+    rng = np.random.default_rng(seed)
+    cases = []
+    while len(cases) < n:
+        w, h = int(rng.integers(70, 901)), int(rng.integers(70, 701))
+        sf = float(rng.choice([1.1, 1.2, 1.25, 1.3, 1.5, 1.7, 2.0, 2.5]))
+        nl = int(rng.integers(1, 11))
+        # the reference needs one 30-px FAST cell in every level (it divides by zero otherwise)
+        if min(w, h) / sf ** (nl - 1) < 70:
+            continue
+        ini = int(rng.integers(5, 41)); mn = int(rng.integers(2, ini + 1))
+        cases.append((w, h, int(rng.integers(30, 2501)), sf, nl, ini, mn, int(rng.integers(0, 1 << 30))))
+    return cases
+
+
+@pytest.mark.parametrize("case", _random_cases(14, 20260101), ids=lambda c: "%dx%d_n%d_s%g_l%d_t%d-%d" % c[:7])
+def test_random_geometry_sweep(orbx, oracle, case):
+    """Seeded random frame sizes / parameters, eager and lazy border: every stage bit-exact against the oracle."""
+    w, h, nf, sf, nl, ini, mn, seed = case
+    img = synth_frame(seed % 1000, w, h)
+    params = dict(nfeatures=nf, scale_factor=sf, nlevels=nl, ini_th=ini, min_th=mn)
+    ex = orbx.Extractor(max_width=w, max_height=h, max_batch=2, **params)
+    oex = oracle.OracleExtractor(**params)
+    if seed & 1:
+        ex.set_pyramid_border(True)
+    kps, desc, counts = ex.extract_host(np.stack([img, img[::-1].copy()]))
+    _compare_frame(oracle, ex, oex, img, 0, kps, desc, counts)
+    _compare_frame(oracle, ex, oex, img[::-1].copy(), 1, kps, desc, counts)
+    oex(img)
+    assert np.array_equal(ex.level(0, nl - 1, border=19), oracle.reflect101_border(oex.level(nl - 1), 19))
