@@ -38,7 +38,8 @@ extern "C" {
 #define ORBX_E_NOMEM (-3)     /* allocation failed */
 #define ORBX_E_CAPACITY (-4)  /* frame/batch larger than the handle was created for */
 #define ORBX_E_NODEVICE (-5)  /* no usable sm_100 device */
-#define ORBX_E_UNSUPPORTED (-6)
+#define ORBX_E_UNSUPPORTED (-6) /* outside the supported range: a level wider/taller than 4095 + 32 px, a FAST cell > 64 px, or a per-level
+                                  feature quota above ~2 400 (the octree's shared-memory node tables); orbx_last_cuda_error() says which */
 
 #define ORBX_MAX_LEVELS 16
 #define ORBX_EDGE_THRESHOLD 19 /* pyramid border, src/ORBextractor.cpp:24 */

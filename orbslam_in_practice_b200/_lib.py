@@ -133,7 +133,7 @@ def check(rc):
         L = load()
         msg = L.orbx_strerror(rc).decode()
         cu = L.orbx_last_cuda_error().decode()
-        raise OrbxError("liborbx: %s (%d)%s" % (msg, rc, (" [" + cu + "]") if rc == -2 and cu else ""))
+        raise OrbxError("liborbx: %s (%d)%s" % (msg, rc, (" [" + cu + "]") if rc in (-2, -6) and cu else ""))
 
 
 def _p(a):

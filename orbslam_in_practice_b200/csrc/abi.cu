@@ -316,6 +316,11 @@ static int upload_geometry(orbx_extractor *ex, int w, int h)
     CK(cudaStreamSynchronize(ex->stream));   // `tables` is pageable host memory about to go out of scope
     ex->cur_w = w; ex->cur_h = h;
     ex->oct_smem = octree_smem_bytes(ex->geo);
+    // the octree keeps its node tables in shared memory: a level quota beyond ~2 400 features does not fit one SM
+    if (ex->oct_smem > 227 * 1024) {
+        std::snprintf(g_cuda_err, sizeof(g_cuda_err), "per-level feature quota too large for the octree's shared-memory node tables (%d bytes)", ex->oct_smem);
+        return ORBX_E_UNSUPPORTED;
+    }
     if (octree_configure(ex->oct_smem)) return cuda_fail(cudaGetLastError(), "octree smem");
     return ORBX_OK;
 }

@@ -113,6 +113,12 @@ def test_capacity_errors(orbx):
         ex.extract_host(np.zeros((480, 640), np.uint8))
     with pytest.raises(orbx.OrbxError):
         ex.extract_host(np.zeros((2, 240, 320), np.uint8))
+    # a per-level quota the octree's shared-memory node tables cannot hold is refused with ORBX_E_UNSUPPORTED (-6), loudly
+    with pytest.raises(orbx.OrbxError, match="unsupported"):
+        big = orbx.Extractor(nfeatures=3900, nlevels=1, max_width=640, max_height=480, max_batch=1)
+        big.extract_host(np.zeros((480, 640), np.uint8))
+    ok = orbx.Extractor(nfeatures=2300, nlevels=1, max_width=640, max_height=480, max_batch=1)
+    assert ok.extract_host(np.zeros((480, 640), np.uint8))[2][0] == 0
 
 
 def test_4k_frame_nfeatures_8000(orbx, oracle):
