@@ -122,6 +122,12 @@ int orbx_set_input_format(orbx_extractor *ex, int channels, int rgb_order);
  * every extract call writes it for all levels and frames on the device. */
 int orbx_set_pyramid_border(orbx_extractor *ex, int enabled);
 
+/* orbx_extract_device runs a batch of >= 32 frames as `nsplit` independent sub-batches alternating between the caller's
+ * stream and an internal one (joined before it returns control of the stream): the sub-batches' different kernels fill
+ * each other's idle issue slots.  Default 2 (environment ORBX_DEVICE_SPLIT overrides at creation).  Use 1 when the
+ * caller already overlaps consecutive batches itself with several handles on several streams. */
+int orbx_set_device_split(orbx_extractor *ex, int nsplit);
+
 /* --- stage access of the LAST extract call (synchronous; for mvImagePyramid and parity tests) --- */
 int orbx_level_dims(const orbx_extractor *ex, int level, int *width, int *height);
 /* copies level pixels of `frame` to host.  border = 0 -> width x height; border = 19 -> the

@@ -459,6 +459,13 @@ extern "C" int orbx_set_pyramid_border(orbx_extractor *ex, int enabled)
     return ORBX_OK;
 }
 
+extern "C" int orbx_set_device_split(orbx_extractor *ex, int nsplit)
+{
+    if (!ex || nsplit < 1 || nsplit > orbx_extractor::kMaxChunks) return ORBX_E_INVALID;
+    ex->device_split = nsplit;
+    return ORBX_OK;
+}
+
 static int ensure_geometry(orbx_extractor *ex, int w, int h)
 {
     if (w == ex->cur_w && h == ex->cur_h) return ORBX_OK;

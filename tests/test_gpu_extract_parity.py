@@ -311,3 +311,37 @@ def test_random_geometry_sweep(orbx, oracle, case):
     _compare_frame(oracle, ex, oex, img[::-1].copy(), 1, kps, desc, counts)
     oex(img)
     assert np.array_equal(ex.level(0, nl - 1, border=19), oracle.reflect101_border(oex.level(nl - 1), 19))
+
+
+def test_device_entry_sub_batches_give_identical_results(orbx, oracle):
+    """orbx_extract_device on >= 32 resident frames runs as independent sub-batches on two streams
+    (orbx_set_device_split): outputs must not depend on the split, and equal the oracle's."""
+    import torch
+    F = 40
+    imgs = synth_batch(range(100, 100 + F), 320, 240)
+    dev = torch.device("cuda:0")
+    d_img = torch.from_numpy(imgs).to(dev)
+    ex = orbx.Extractor(nfeatures=500, max_width=320, max_height=240, max_batch=F)
+    cap = ex.capacity
+    st = torch.cuda.Stream(); torch.cuda.set_stream(st)
+    outs = []
+    for split in (1, 2, 3):
+        ex.set_device_split(split)
+        k = torch.zeros((F, cap, 7), dtype=torch.float32, device=dev)
+        d = torch.zeros((F, cap, 32), dtype=torch.uint8, device=dev)
+        c = torch.zeros(F, dtype=torch.int32, device=dev)
+        ex.extract_device(d_img.data_ptr(), 320, 320 * 240, 320, 240, F, k.data_ptr(), d.data_ptr(), c.data_ptr(), st.cuda_stream)
+        st.synchronize()
+        outs.append((k.cpu().numpy(), d.cpu().numpy(), c.cpu().numpy()))
+    for k, d, c in outs[1:]:
+        assert np.array_equal(c, outs[0][2])
+        for f in range(F):
+            n = int(c[f])
+            assert np.array_equal(k[f, :n], outs[0][0][f, :n]) and np.array_equal(d[f, :n], outs[0][1][f, :n])
+    oex = oracle.OracleExtractor(nfeatures=500)
+    for f in (0, 19, 20, 39):                       # both sides of the sub-batch boundaries
+        ko, do = oex(imgs[f])
+        n = int(outs[1][2][f])
+        assert n == len(ko)
+        assert np.array_equal(outs[1][0][f, :n, 0], ko["x"]) and np.array_equal(outs[1][0][f, :n, 1], ko["y"])
+        assert np.unpackbits(outs[1][1][f, :n] ^ do).sum() <= 1e-3 * do.size * 8
