@@ -38,7 +38,7 @@ struct BlurWeights { uint32_t k0k2, z_k1, k3k1, k2k0, z_k0, k2k2, k0_z, k1k3, k1
 
 __device__ __forceinline__ uint32_t dp2(uint32_t a, uint32_t wts, uint32_t c) { return __dp2a_lo(a, wts, c); }
 
-__global__ void __launch_bounds__(32 * kBlurWarps)
+__global__ void __launch_bounds__(32 * kBlurWarps, 10)
 k_blur(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, uint8_t *__restrict__ blur, const BlurRows rows,
        const __grid_constant__ BlurWeights W)
 {
