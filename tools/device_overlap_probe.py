@@ -11,7 +11,7 @@ dev = torch.device("cuda", 0)
 frames = np.ascontiguousarray(np.concatenate([synth_batch(range(32), W, H)] * (B // 32)))
 d_frames = torch.from_numpy(frames).to(dev)
 hs = []
-for i in range(2):
+for i in range(4):
     ex = _lib.Extractor(1000, 1.2, 8, 20, 7, W, H, B, 0)
     cap = ex.capacity
     hs.append((ex, torch.empty((B, cap, 7), dtype=torch.float32, device=dev), torch.empty((B, cap, 32), dtype=torch.uint8, device=dev),
@@ -19,11 +19,11 @@ for i in range(2):
 
 
 def step(i, two):
-    ex, k, d, c, s = hs[i & 1] if two else hs[0]
+    ex, k, d, c, s = hs[i % two] if two else hs[0]
     ex.extract_device(d_frames.data_ptr(), W, W * H, W, H, B, k.data_ptr(), d.data_ptr(), c.data_ptr(), s.cuda_stream)
 
 
-for two in (False, True, False, True):
+for two in (0, 2, 3, 4, 0, 2, 3, 4):
     for i in range(4):
         step(i, two)
     torch.cuda.synchronize()
@@ -38,4 +38,4 @@ for two in (False, True, False, True):
     e1.record(torch.cuda.default_stream(dev))
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    print("two handles/streams" if two else "one handle/stream  ", "%.3f ms/step  %.0f frames/s" % (ms / K, B * K / ms * 1e3), flush=True)
+    print("%d handles/streams" % (two or 1), "%.3f ms/step  %.0f frames/s" % (ms / K, B * K / ms * 1e3), flush=True)
