@@ -38,6 +38,8 @@ k_search_init(const __grid_constant__ SearchInitArgs A)
     unsigned short *cellstart = reinterpret_cast<unsigned short *>(keys + A.sort_n);// [64 * 49 + 1] first key of (ix, iy)
     int *matchedDist = reinterpret_cast<int *>(cellstart + ((kGridCols * (kGridRows + 1) + 2) & ~1));   // [cap]
     int *m21 = matchedDist + A.cap;                                                  // [cap]
+    unsigned short *qcnt = reinterpret_cast<unsigned short *>(m21 + A.cap);          // [cap] candidates per query of F1
+    unsigned short *active = qcnt + A.cap;                                           // [cap] queries with candidates, ascending
     __shared__ int hist[kHistoLength];
     __shared__ int s_nvalid, s_nmatches, s_keep[3];
 
@@ -143,7 +145,7 @@ k_search_init(const __grid_constant__ SearchInitArgs A)
                 }
             }
         }
-        if (lane == 0) list[0] = (uint32_t)cnt;
+        if (lane == 0) { list[0] = (uint32_t)cnt; qcnt[q] = (unsigned short)cnt; }
     }
     __syncthreads();
 
@@ -151,16 +153,40 @@ k_search_init(const __grid_constant__ SearchInitArgs A)
     if (warp == 0) {
         const float factor = kHistoLength / 360.0f;                          // :17
         int nmatches = 0;
-        for (int q = 0; q < n1; ++q) {
-            const uint32_t *list = ws + (unsigned long long)q * stride;
-            const int cnt = (int)list[0];
-            if (cnt == 0) continue;                                            // :32-33 (also covers octave > 0)
+        // Only queries with candidates take part (:32-33 skips the others, which also covers wrong octaves); their
+        // indices are compacted in ascending order first.  The lists live in global memory: a query's first 64 entries
+        // are fetched one iteration ahead, so the serial chain never waits on a load (ncu: the replay used to be ~70 %
+        // of the kernel's time, spent on dependent global loads by a single warp).
+        int na = 0;
+        for (int b0 = 0; b0 < n1; b0 += 32) {
+            const int q = b0 + lane;
+            const bool on = q < n1 && qcnt[q] != 0;
+            const uint32_t bal = __ballot_sync(0xffffffffu, on);
+            if (on) active[na + __popc(bal & ((1u << lane) - 1u))] = (unsigned short)q;
+            na += __popc(bal);
+        }
+        __syncwarp();
+        int qn = 0, cn = 0;
+        const uint32_t *ln = ws;
+        uint32_t n0 = 0, n1e = 0;
+        if (na > 0) {
+            qn = active[0]; cn = qcnt[qn]; ln = ws + (unsigned long long)qn * stride;
+            n0 = lane < cn ? ln[1 + lane] : 0u; n1e = 32 + lane < cn ? ln[33 + lane] : 0u;
+        }
+        for (int ai = 0; ai < na; ++ai) {
+            const int q = qn, cnt = cn;
+            const uint32_t *list = ln;
+            const uint32_t e0 = n0, e1 = n1e;
+            if (ai + 1 < na) {
+                qn = active[ai + 1]; cn = qcnt[qn]; ln = ws + (unsigned long long)qn * stride;
+                n0 = lane < cn ? ln[1 + lane] : 0u; n1e = 32 + lane < cn ? ln[33 + lane] : 0u;
+            }
             uint32_t k1 = kInfKey, k2 = kInfKey;                              // two smallest (dist << 16 | scan position)
             for (int b0 = 0; b0 < cnt; b0 += 32) {
                 const int p = b0 + lane;
                 uint32_t key = kInfKey;
                 if (p < cnt) {
-                    const uint32_t ent = list[1 + p];
+                    const uint32_t ent = b0 == 0 ? e0 : (b0 == 32 ? e1 : list[1 + p]);
                     const int i2 = (int)(ent & 0xffffu), dist = (int)(ent >> 16);
                     // gate 0: :49-50 (matched at a distance <= dist);  gate 1: already taken by an earlier query
                     const bool skip = W.gate == 0 ? matchedDist[i2] <= dist : m21[i2] >= 0;
@@ -175,10 +201,13 @@ k_search_init(const __grid_constant__ SearchInitArgs A)
                 const uint32_t lo = min(k1, o1), mid = max(k1, o1);
                 k2 = min(min(k2, o2), mid); k1 = lo;
             }
+            // the winner's list entry: from the prefetched registers when it is among the first 64
+            const int wp = (int)(k1 & 0xffffu);
+            const uint32_t w0 = __shfl_sync(0xffffffffu, e0, wp & 31), w1 = __shfl_sync(0xffffffffu, e1, wp & 31);
             if (lane == 0 && k1 != kInfKey) {
                 const int bestDist = (int)(k1 >> 16);
                 const int bestDist2 = k2 == kInfKey ? INT_MAX : (int)(k2 >> 16);
-                const int bestIdx2 = (int)(list[1 + (k1 & 0xffffu)] & 0xffffu);
+                const int bestIdx2 = (int)((wp < 32 ? w0 : (wp < 64 ? w1 : list[1 + wp])) & 0xffffu);
                 const bool ratio_ok = W.nnratio <= 0.f || (float)bestDist < __fmul_rn((float)bestDist2, W.nnratio);
                 if (bestDist <= W.th_dist && ratio_ok) {                                // :65-67
                     if (m21[bestIdx2] >= 0) { m12[m21[bestIdx2]] = -1; nmatches--; }
@@ -230,7 +259,7 @@ k_search_init(const __grid_constant__ SearchInitArgs A)
 
 size_t search_init_smem_bytes(int cap, int sort_n)
 {
-    return (size_t)sort_n * 4 + (size_t)((kGridCols * (kGridRows + 1) + 2) & ~1) * 2 + (size_t)cap * 8 + 16;
+    return (size_t)sort_n * 4 + (size_t)((kGridCols * (kGridRows + 1) + 2) & ~1) * 2 + (size_t)cap * 12 + 16;
 }
 
 int launch_search_init(const SearchInitArgs &a, cudaStream_t s)
