@@ -20,7 +20,7 @@ namespace orbx {
 
 constexpr int kGridRows = 48, kGridCols = 64;   // Frame.h:11-12
 constexpr int kHistoLength = 30;                // ORBmatcher.cpp:6
-constexpr int kSiThreads = 256;
+constexpr int kSiThreads = 512;
 constexpr uint32_t kInfKey = 0xffffffffu;
 
 __device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const uint4 *__restrict__ b)
