@@ -61,25 +61,28 @@ k_search_init(const __grid_constant__ SearchInitArgs A)
 
     // ---- 1: grid keys of F2; only the octaves some query can ask for (SearchForInitialization: octave 0 alone,
     //      it queries minLevel = maxLevel = 0) ----
-    for (int i = tid; i < A.sort_n; i += kSiThreads) {
-        uint32_t key = kInfKey;
-        if (i < n2) {
-            const orbx_keypoint k = kp2[i];
-            // GetGridId takes doubles (Frame.cpp:161-168); std::round = half away from zero
-            const int ix = (int)round(((double)k.x - (double)minX) * (double)wInv);
-            const int iy = (int)round(((double)k.y - (double)(W.literal_gridid_bug ? maxY : minY)) * (double)hInv);
-            if (k.octave >= A.grid_level_min && k.octave <= A.grid_level_max && ix >= 0 && ix < kGridCols && iy >= 0 && iy < kGridRows)
-                key = ((uint32_t)(ix * kGridRows + iy) << 16) | (uint32_t)i;
-        }
-        keys[i] = key;
+    // Keys are appended in any order (they are unique, so the sorted result does not depend on it), then only the next
+    // power of two above their number is sorted: SearchForInitialization keeps ~1/5 of the keypoints (octave 0).
+    if (tid == 0) { s_nvalid = 0; s_nmatches = 0; }
+    if (tid < kHistoLength) hist[tid] = 0;
+    __syncthreads();
+    for (int i = tid; i < n2; i += kSiThreads) {
+        const orbx_keypoint k = kp2[i];
+        // GetGridId takes doubles (Frame.cpp:161-168); std::round = half away from zero
+        const int ix = (int)round(((double)k.x - (double)minX) * (double)wInv);
+        const int iy = (int)round(((double)k.y - (double)(W.literal_gridid_bug ? maxY : minY)) * (double)hInv);
+        if (k.octave >= A.grid_level_min && k.octave <= A.grid_level_max && ix >= 0 && ix < kGridCols && iy >= 0 && iy < kGridRows)
+            keys[atomicAdd(&s_nvalid, 1)] = ((uint32_t)(ix * kGridRows + iy) << 16) | (uint32_t)i;
     }
     for (int i = tid; i < A.cap; i += kSiThreads) { matchedDist[i] = INT_MAX; m21[i] = -1; m12[i] = -1; }
-    if (tid < kHistoLength) hist[tid] = 0;
-    if (tid == 0) s_nmatches = 0;
     __syncthreads();
-    for (int k = 2; k <= A.sort_n; k <<= 1)
+    int sort_m = 32;
+    while (sort_m < s_nvalid) sort_m <<= 1;                                          // <= A.sort_n
+    for (int i = s_nvalid + tid; i < sort_m; i += kSiThreads) keys[i] = kInfKey;
+    __syncthreads();
+    for (int k = 2; k <= sort_m; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < A.sort_n; i += kSiThreads) {
+            for (int i = tid; i < sort_m; i += kSiThreads) {
                 const int p = i ^ j;
                 if (p > i) {
                     const uint32_t a = keys[i], b = keys[p];
@@ -92,10 +95,9 @@ k_search_init(const __grid_constant__ SearchInitArgs A)
     // first key position of every (ix, iy) and the end sentinel: lower_bound by binary search
     for (int c = tid; c <= kGridCols * kGridRows; c += kSiThreads) {
         const uint32_t target = (uint32_t)c << 16;
-        int lo = 0, hi = A.sort_n;
+        int lo = 0, hi = sort_m;
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < target) lo = mid + 1; else hi = mid; }
-        cellstart[c] = (unsigned short)lo;
-        if (c == kGridCols * kGridRows) s_nvalid = lo;
+        cellstart[c] = (unsigned short)lo;                                           // the sentinel entry equals s_nvalid
     }
     __syncthreads();
     const int nvalid = s_nvalid;                        // keypoints of F2 that landed in the grid
