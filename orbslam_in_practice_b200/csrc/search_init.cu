@@ -125,13 +125,16 @@ k_search_init(const __grid_constant__ SearchInitArgs A)
             const int cy1 = min(kGridRows - 1, (int)ceilf((y - minY + r) * hInv));
             if (cx0 < kGridCols && cx1 >= 0 && cy0 < kGridRows && cy1 >= 0) {
                 const uint4 a0 = __ldg(d1 + 2 * q), a1 = __ldg(d1 + 2 * q + 1);
-                for (int ix = cx0; ix <= cx1; ++ix) {
-                    const int s = cellstart[ix * kGridRows + cy0], e = cellstart[ix * kGridRows + cy1 + 1];
-                    for (int b0 = s; b0 < e; b0 += 32) {
-                        const int p = b0 + lane;
-                        bool ok = false; uint32_t ent = 0;
-                        if (p < e) {
-                            const int i2 = (int)(keys[p] & 0xffffu);
+                // one 32-key chunk of the sorted keys [b0, e); keys are visited in ascending order = the reference's
+                // enumeration (ix outer, iy inner, insertion order inside a cell); cells outside rows cy0..cy1 are skipped
+                auto chunk = [&](int b0, int e) {
+                    const int p = b0 + lane;
+                    bool ok = false; uint32_t ent = 0;
+                    if (p < e) {
+                        const uint32_t key = keys[p];
+                        const int i2 = (int)(key & 0xffffu), cell = (int)(key >> 16);
+                        const int iy = cell - (cell / kGridRows) * kGridRows;
+                        if (iy >= cy0 && iy <= cy1) {
                             const orbx_keypoint k2 = kp2[i2];
                             const float dx = k2.x - x, dy = k2.y - y;                  // Frame.cpp:263-266
                             const bool lvl = k2.octave >= minLevel && (maxLevel < 0 || k2.octave <= maxLevel);
@@ -140,9 +143,21 @@ k_search_init(const __grid_constant__ SearchInitArgs A)
                                 ent = (uint32_t)i2 | ((uint32_t)hamming256(a0, a1, d2 + 2 * i2) << 16);
                             }
                         }
-                        const uint32_t bal = __ballot_sync(0xffffffffu, ok);
-                        if (ok) list[1 + cnt + __popc(bal & ((1u << lane) - 1u))] = ent;
-                        cnt += __popc(bal);
+                    }
+                    const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+                    if (ok) list[1 + cnt + __popc(bal & ((1u << lane) - 1u))] = ent;
+                    cnt += __popc(bal);
+                };
+                // Columns cx0..cx1 are one contiguous key range.  Walking it whole (and skipping the rows outside the
+                // window) needs fewer 32-key chunks than one pass per column whenever the band holds <= 32 keys per
+                // column on average -- the common case (SearchForInitialization: ~3 keys per column pass otherwise).
+                const int ks = cellstart[cx0 * kGridRows], ke = cellstart[cx1 * kGridRows + kGridRows];
+                if (ke - ks <= 32 * (cx1 - cx0 + 1)) {
+                    for (int b0 = ks; b0 < ke; b0 += 32) chunk(b0, ke);
+                } else {
+                    for (int ix = cx0; ix <= cx1; ++ix) {
+                        const int s_ = cellstart[ix * kGridRows + cy0], e_ = cellstart[ix * kGridRows + cy1 + 1];
+                        for (int b0 = s_; b0 < e_; b0 += 32) chunk(b0, e_);
                     }
                 }
             }
