@@ -212,11 +212,12 @@ k_search_init(const __grid_constant__ SearchInitArgs A)
                 const uint32_t hi = max(k1, key);
                 k1 = min(k1, key); k2 = min(k2, hi);
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {                                // merge the lanes' sorted pairs
-                const uint32_t o1 = __shfl_xor_sync(0xffffffffu, k1, o), o2 = __shfl_xor_sync(0xffffffffu, k2, o);
-                const uint32_t lo = min(k1, o1), mid = max(k1, o1);
-                k2 = min(min(k2, o2), mid); k1 = lo;
+            // merge the lanes' sorted pairs with two warp reductions (REDUX): the smallest key, then the smallest of what
+            // is left (keys are unique -- they contain the scan position -- except for the "none" value)
+            {
+                const uint32_t best = __reduce_min_sync(0xffffffffu, k1);
+                k2 = __reduce_min_sync(0xffffffffu, k1 == best ? k2 : k1);
+                k1 = best;
             }
             // the winner's list entry: from the prefetched registers when it is among the first 64
             const int wp = (int)(k1 & 0xffffu);
