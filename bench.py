@@ -411,22 +411,30 @@ def run_ours(args):
         wsb = _lib.load().orbm_search_init_workspace_bytes(cap, P)
         ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
 
-        def si_step():
-            prev.copy_(prev0)
-            msi.search_init_device(d_kps.data_ptr(), d_desc.data_ptr(), d_cnt.data_ptr(), cap, pa.data_ptr(), pb.data_ptr(), P,
-                                   prev.data_ptr(), m12.data_ptr(), nm.data_ptr(), 100, 0.9, True, W, H, ws.data_ptr(), wsb, stream)
-        for _ in range(3):
-            si_step()
-        barrier()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s0.record()
-        for _ in range(K):
-            si_step()
-        s1.record(); barrier()
-        si_ms = max_over_ranks(s0.elapsed_time(s1)) / K
+        def si_run(pb_t):
+            def si_step():
+                prev.copy_(prev0)
+                msi.search_init_device(d_kps.data_ptr(), d_desc.data_ptr(), d_cnt.data_ptr(), cap, pa.data_ptr(), pb_t.data_ptr(), P,
+                                       prev.data_ptr(), m12.data_ptr(), nm.data_ptr(), 100, 0.9, True, W, H, ws.data_ptr(), wsb, stream)
+            for _ in range(3):
+                si_step()
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(K):
+                si_step()
+            s1.record(); barrier()
+            return max_over_ranks(s0.elapsed_time(s1)) / K, float(nm.float().mean().item())
+
+        si_ms, si_mm = si_run(pb)
+        # the same launch with every frame paired with an identical copy (the batch tiles `nuniq` distinct frames): every
+        # octave-0 keypoint finds its match, which exercises the acceptance / one-to-one / histogram path of the replay
+        pb_same = ((pa + nuniq) % BATCH).to(torch.int32)
+        si_ms_same, si_mm_same = si_run(pb_same)
         search_init = {"metric": "search_for_initialization_pairs_per_s", "value": world * P / (si_ms * 1e-3), "unit": "frame pairs/s",
                        "ms_per_step": si_ms, "config": {"workload": "%d consecutive 640x480 frame pairs per GPU, window 100, ratio 0.9, rotation check" % P},
-                       "mean_matches": float(nm.float().mean().item())}
+                       "mean_matches": si_mm,
+                       "identical_frame_pairs": {"value": world * P / (si_ms_same * 1e-3), "ms_per_step": si_ms_same, "mean_matches": si_mm_same}}
         del ws
 
     match = None

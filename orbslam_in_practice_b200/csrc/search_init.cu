@@ -40,6 +40,7 @@ k_search_init(const __grid_constant__ SearchInitArgs A)
     int *m21 = matchedDist + A.cap;                                                  // [cap]
     unsigned short *qcnt = reinterpret_cast<unsigned short *>(m21 + A.cap);          // [cap] candidates per query of F1
     unsigned short *active = qcnt + A.cap;                                           // [cap] queries with candidates, ascending
+    float *ang2 = reinterpret_cast<float *>(active + A.cap);                         // [cap] angles of F2's keypoints (read by the replay)
     __shared__ int hist[kHistoLength];
     __shared__ int s_nvalid, s_nmatches, s_keep[3];
 
@@ -68,6 +69,7 @@ k_search_init(const __grid_constant__ SearchInitArgs A)
     __syncthreads();
     for (int i = tid; i < n2; i += kSiThreads) {
         const orbx_keypoint k = kp2[i];
+        ang2[i] = k.angle;
         // GetGridId takes doubles (Frame.cpp:161-168); std::round = half away from zero
         const int ix = (int)round(((double)k.x - (double)minX) * (double)wInv);
         const int iy = (int)round(((double)k.y - (double)(W.literal_gridid_bug ? maxY : minY)) * (double)hInv);
@@ -186,17 +188,21 @@ k_search_init(const __grid_constant__ SearchInitArgs A)
         int qn = 0, cn = 0;
         const uint32_t *ln = ws;
         uint32_t n0 = 0, n1e = 0;
+        float an = 0.f;                                                        // angle of the next query's keypoint
         if (na > 0) {
             qn = active[0]; cn = qcnt[qn]; ln = ws + (unsigned long long)qn * stride;
             n0 = lane < cn ? ln[1 + lane] : 0u; n1e = 32 + lane < cn ? ln[33 + lane] : 0u;
+            an = kp1[qn].angle;
         }
         for (int ai = 0; ai < na; ++ai) {
             const int q = qn, cnt = cn;
             const uint32_t *list = ln;
             const uint32_t e0 = n0, e1 = n1e;
+            const float angle1 = an;
             if (ai + 1 < na) {
                 qn = active[ai + 1]; cn = qcnt[qn]; ln = ws + (unsigned long long)qn * stride;
                 n0 = lane < cn ? ln[1 + lane] : 0u; n1e = 32 + lane < cn ? ln[33 + lane] : 0u;
+                an = kp1[qn].angle;
             }
             uint32_t k1 = kInfKey, k2 = kInfKey;                              // two smallest (dist << 16 | scan position)
             for (int b0 = 0; b0 < cnt; b0 += 32) {
@@ -231,7 +237,7 @@ k_search_init(const __grid_constant__ SearchInitArgs A)
                     if (m21[bestIdx2] >= 0) { m12[m21[bestIdx2]] = -1; nmatches--; }
                     m12[q] = bestIdx2; m21[bestIdx2] = q; matchedDist[bestIdx2] = bestDist; nmatches++;
                     if (W.check_orientation) {                                // :79-90
-                        float rot = __fsub_rn(kp1[q].angle, kp2[bestIdx2].angle);
+                        float rot = __fsub_rn(angle1, ang2[bestIdx2]);
                         if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
                         int bin = (int)roundf(__fmul_rn(rot, factor));
                         if (bin == kHistoLength) bin = 0;
@@ -277,7 +283,7 @@ k_search_init(const __grid_constant__ SearchInitArgs A)
 
 size_t search_init_smem_bytes(int cap, int sort_n)
 {
-    return (size_t)sort_n * 4 + (size_t)((kGridCols * (kGridRows + 1) + 2) & ~1) * 2 + (size_t)cap * 12 + 16;
+    return (size_t)sort_n * 4 + (size_t)((kGridCols * (kGridRows + 1) + 2) & ~1) * 2 + (size_t)cap * 16 + 16;
 }
 
 int launch_search_init(const SearchInitArgs &a, cudaStream_t s)
