@@ -16,6 +16,7 @@
  *   orbm_knn2_* / orbm_ratio_select  best-2 scan + acceptance          src/ORBmatcher.cpp:37-67
  *   orbm_search_init_device          ORBmatcher::SearchForInitialization + Frame grid   src/ORBmatcher.cpp:9-126, src/Frame.cpp:144-168,219-271
  *   orbm_search_window_device        ORBmatcher::SearchByProjection (empty in the reference) over Frame::GetFeaturesInArea   include/ORBmatcher.h:24, src/Frame.cpp:219-271
+ *   orbm_search_groups_device        ORBmatcher::SearchByBoW (empty in the reference; group = vocabulary node)   include/ORBmatcher.h:22
  *   orbm_merge_shards_device         (database sharding; no reference counterpart)
  *
  * All functions return 0 on success or a negative ORBX_E_* code; nothing throws across the ABI.
@@ -269,6 +270,22 @@ int orbm_search_window_device(orbm_matcher *m, const orbx_keypoint *d_kps, const
 int orbm_search_window_host(orbm_matcher *m, const orbx_keypoint *kp1, const uint8_t *desc1, int n1,
                             const orbx_keypoint *kp2, const uint8_t *desc2, int n2,
                             float *centers, int32_t *matches12, int32_t *nmatches, const orbm_window_params *params);
+
+/* Group-restricted search: the other empty matcher entry point of the reference, SearchByBoW (include/ORBmatcher.h:22), in the
+ * form upstream ORB-SLAM2 gives it.  Every keypoint carries a group id (the vocabulary node DBoW2's FeatureVector assigns it;
+ * 0xffff = none -- the vocabulary itself is not part of the reference and stays with the caller).  Groups are visited in
+ * ascending id and, inside a group, F1's keypoints in ascending index; a query scans the F2 keypoints of its group in
+ * ascending index, skipping those already matched, keeps the best two distances (both start at 256), accepts when
+ * best <= th_dist and (float)best < nnratio * (float)second, then the rotation-histogram filter.  Same kernel, workspace
+ * and output conventions as orbm_search_init_device; d_groups is [nframes][capacity] uint16.  PARITY UNPINNED by the
+ * reference (empty body); pinned against this repo's oracle restatement of the upstream loop only. */
+int orbm_search_groups_device(orbm_matcher *m, const orbx_keypoint *d_kps, const uint8_t *d_desc, const int32_t *d_counts,
+                              const uint16_t *d_groups, int capacity, const int32_t *d_pair_a, const int32_t *d_pair_b, int npairs,
+                              int32_t *d_matches12, int32_t *d_nmatches, int th_dist, float nnratio, int check_orientation,
+                              void *d_workspace, size_t workspace_bytes, void *stream);
+int orbm_search_groups_host(orbm_matcher *m, const orbx_keypoint *kp1, const uint8_t *desc1, const uint16_t *group1, int n1,
+                            const orbx_keypoint *kp2, const uint8_t *desc2, const uint16_t *group2, int n2,
+                            int32_t *matches12, int32_t *nmatches, int th_dist, float nnratio, int check_orientation);
 
 /* Integer-pipe microbenchmark used for the kNN roofline: runs a dependent-free POPC loop on every
  * SM and returns measured 32-bit POPC results per second (device-event timed). */

@@ -80,6 +80,8 @@ def lib():
     L.orbo_knn2_mt.argtypes = [vp, i32, vp, i32, i32, vp, vp, vp, i32]
     L.orbo_ratio_select.argtypes = [vp, vp, vp, i32, i32, f32, vp]
     L.orbo_merge_shards.argtypes = [vp, vp, vp, i32, i32, vp, vp, vp]
+    L.orbo_search_groups.restype = i32
+    L.orbo_search_groups.argtypes = [vp, vp, vp, i32, vp, vp, vp, i32, vp, i32, f32, i32]
     L.orbo_search_window.restype = i32
     L.orbo_search_window.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp, vp]
     L.orbo_search_for_initialization.restype = i32
@@ -320,6 +322,17 @@ def search_window(kp1, desc1, kp2, desc2, centers, params):
     m12 = np.zeros(len(kp1), np.int32)
     n = lib().orbo_search_window(_p(kp1), _p(desc1), len(kp1), _p(kp2), _p(desc2), len(kp2), _p(cen), _p(m12), C.byref(params))
     return n, m12, cen
+
+
+def search_groups(kp1, desc1, group1, kp2, desc2, group2, th_dist=50, nnratio=0.7, check_orientation=True):
+    kp1 = np.ascontiguousarray(kp1, KEYPOINT_DTYPE)
+    kp2 = np.ascontiguousarray(kp2, KEYPOINT_DTYPE)
+    desc1, desc2 = _u8(desc1), _u8(desc2)
+    g1 = np.ascontiguousarray(group1, np.uint16); g2 = np.ascontiguousarray(group2, np.uint16)
+    m12 = np.zeros(len(kp1), np.int32)
+    n = lib().orbo_search_groups(_p(kp1), _p(desc1), _p(g1), len(kp1), _p(kp2), _p(desc2), _p(g2), len(kp2), _p(m12),
+                                 th_dist, nnratio, int(check_orientation))
+    return n, m12
 
 
 def extract_many(imgs, nthreads, nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7):

@@ -1125,6 +1125,60 @@ int orbo_search_window(const orbo_keypoint *kp1, const uint8_t *desc1, int n1,
     return nmatches;
 }
 
+/* Group-restricted search = upstream ORB-SLAM2's ORBmatcher::SearchByBoW(KeyFrame*, Frame&, ...) with the vocabulary node of
+ * every keypoint given as a group id (the reference's own body is empty, include/ORBmatcher.h:22 -- PARITY UNPINNED).
+ * Upstream walks the two FeatureVectors (std::map, ascending node id) in lock step; for a common node, for every F1 feature
+ * of the node in ascending index: scan the node's F2 features in ascending index, skip the already matched ones, keep the
+ * best two distances (both start at 256), accept on bestDist1 <= TH_LOW and (float)bestDist1 < ratio * (float)bestDist2,
+ * then the rotation histogram as in SearchForInitialization.  group 0xffff = keypoint without a node. */
+int orbo_search_groups(const orbo_keypoint *kp1, const uint8_t *desc1, const uint16_t *g1, int n1,
+                       const orbo_keypoint *kp2, const uint8_t *desc2, const uint16_t *g2, int n2,
+                       int32_t *m12, int th_dist, float nnratio, int check_ori)
+{
+    int nmatches = 0;
+    for (int i = 0; i < n1; ++i) m12[i] = -1;
+    int *m21 = (int *)malloc(sizeof(int) * (size_t)(n2 + 1));
+    for (int i = 0; i < n2; ++i) m21[i] = -1;
+    int *rot[HISTO_LENGTH]; int rotn[HISTO_LENGTH];
+    for (int i = 0; i < HISTO_LENGTH; ++i) { rot[i] = (int *)malloc(sizeof(int) * (size_t)(n1 + 1)); rotn[i] = 0; }
+    const float factor = HISTO_LENGTH / 360.0f;
+    for (int node = 0; node < 0xffff; ++node) {                        /* ascending node id, like the map iteration */
+        for (int i1 = 0; i1 < n1; ++i1) {
+            if (g1[i1] != node) continue;
+            int best1 = 256, best2 = 256, bestIdx = -1;
+            for (int i2 = 0; i2 < n2; ++i2) {
+                if (g2[i2] != node) continue;
+                if (m21[i2] >= 0) continue;
+                const int dist = orbo_descriptor_distance(desc1 + (size_t)i1 * 32, desc2 + (size_t)i2 * 32);
+                if (dist < best1) { best2 = best1; best1 = dist; bestIdx = i2; }
+                else if (dist < best2) best2 = dist;
+            }
+            if (bestIdx < 0 || best1 > th_dist) continue;
+            if (!((float)best1 < nnratio * (float)best2)) continue;
+            m12[i1] = bestIdx; m21[bestIdx] = i1; nmatches++;
+            if (check_ori) {
+                float rotv = kp1[i1].angle - kp2[bestIdx].angle;
+                if (rotv < 0.0) rotv += 360.0f;
+                int bin = (int)roundf(rotv * factor);
+                if (bin == HISTO_LENGTH) bin = 0;
+                rot[bin][rotn[bin]++] = i1;
+            }
+        }
+    }
+    if (check_ori) {
+        int ind1 = -1, ind2 = -1, ind3 = -1;
+        compute_three_maxima(rotn, HISTO_LENGTH, &ind1, &ind2, &ind3);
+        for (int i = 0; i < HISTO_LENGTH; ++i) {
+            if (i == ind1 || i == ind2 || i == ind3) continue;
+            for (int j = 0; j < rotn[i]; ++j)
+                if (m12[rot[i][j]] >= 0) { m12[rot[i][j]] = -1; nmatches--; }
+        }
+    }
+    for (int i = 0; i < HISTO_LENGTH; ++i) free(rot[i]);
+    free(m21);
+    return nmatches;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* multi-thread extraction helper for the CPU baseline                                        */
 /* ------------------------------------------------------------------------------------------ */

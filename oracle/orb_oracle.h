@@ -148,6 +148,13 @@ int orbo_search_window(const orbo_keypoint *kp1, const uint8_t *desc1, int n1,
                        const orbo_keypoint *kp2, const uint8_t *desc2, int n2,
                        float *centers /* n1 x 2, NaN x = skip */, int32_t *matches12 /* n1 */, const orbo_window_params *params);
 
+/* Group-restricted search (upstream SearchByBoW with the vocabulary node of each keypoint as a uint16 group id, 0xffff = none;
+ * reference body empty, include/ORBmatcher.h:22 -> parity unpinned).  Nodes ascending, F1 features of a node ascending, F2
+ * features of the node ascending; already matched F2 features are skipped; best two distances start at 256. */
+int orbo_search_groups(const orbo_keypoint *kp1, const uint8_t *desc1, const uint16_t *group1, int n1,
+                       const orbo_keypoint *kp2, const uint8_t *desc2, const uint16_t *group2, int n2,
+                       int32_t *matches12, int th_dist, float nnratio, int check_orientation);
+
 /* multi-thread helper for the CPU baseline: extract `nframes` frames with `nthreads` pthreads,
  * one extractor per thread.  counts[nframes] receives keypoint counts. */
 int orbo_extract_many(int nfeatures, float scaleFactor, int nlevels, int iniThFAST, int minThFAST,

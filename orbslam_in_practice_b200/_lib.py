@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "orbm_create", "orbm_destroy", "orbm_launch_count", "orbm_hamming_pairs_host",
     "orbm_knn2_device", "orbm_knn2_host", "orbm_ratio_select_device", "orbm_merge_shards_device",
     "orbm_popc_peak", "orbm_search_init_workspace_bytes", "orbm_search_init_device", "orbm_search_init_host",
-    "orbm_search_window_device", "orbm_search_window_host",
+    "orbm_search_window_device", "orbm_search_window_host", "orbm_search_groups_device", "orbm_search_groups_host",
     "orbm_exchange_create", "orbm_exchange_open", "orbm_knn2_sharded_device", "orbm_exchange_status",
 ]
 
@@ -117,6 +117,8 @@ def load():
     L.orbm_popc_peak.argtypes = [i32, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.orbm_search_window_device.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, vp, vp, vp, sz, vp]
     L.orbm_search_window_host.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, vp, C.POINTER(i32), vp]
+    L.orbm_search_groups_device.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, i32, f32, i32, vp, sz, vp]
+    L.orbm_search_groups_host.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, C.POINTER(i32), i32, f32, i32]
     L.orbm_search_init_workspace_bytes.restype = sz
     L.orbm_search_init_workspace_bytes.argtypes = [i32, i32]
     L.orbm_exchange_create.argtypes = [vp, i32, i32, i32, vp]
@@ -330,6 +332,16 @@ class Matcher:
         check(load().orbm_search_window_host(self.h, _p(kp1), _p(desc1), len(kp1), _p(kp2), _p(desc2), len(kp2), _p(cen), _p(m12),
                                              C.byref(n), C.byref(params)))
         return n.value, m12, cen
+
+    def search_groups_host(self, kp1, desc1, group1, kp2, desc2, group2, th_dist=50, nnratio=0.7, check_ori=True):
+        """SearchByBoW-style matching restricted to equal group ids (uint16, 0xffff = none).  Returns (nmatches, matches12)."""
+        kp1 = np.ascontiguousarray(kp1, KEYPOINT_DTYPE); kp2 = np.ascontiguousarray(kp2, KEYPOINT_DTYPE)
+        desc1 = np.ascontiguousarray(desc1, np.uint8); desc2 = np.ascontiguousarray(desc2, np.uint8)
+        g1 = np.ascontiguousarray(group1, np.uint16); g2 = np.ascontiguousarray(group2, np.uint16)
+        m12 = np.zeros(len(kp1), np.int32); n = C.c_int()
+        check(load().orbm_search_groups_host(self.h, _p(kp1), _p(desc1), _p(g1), len(kp1), _p(kp2), _p(desc2), _p(g2), len(kp2),
+                                             _p(m12), C.byref(n), th_dist, nnratio, int(check_ori)))
+        return n.value, m12
 
     def search_window_device(self, kps_ptr, desc_ptr, counts_ptr, capacity, pair_a_ptr, pair_b_ptr, npairs, centers_ptr,
                              matches_ptr, nmatches_ptr, params, ws_ptr, ws_bytes, stream=0):

@@ -108,6 +108,24 @@ int ORBmatcher::SearchByProjection(const std::vector<cv::KeyPoint> &vLastKeys, c
     return nmatches;
 }
 
+int ORBmatcher::SearchByBoW(const std::vector<cv::KeyPoint> &vKeys1, const cv::Mat &Descriptors1, const std::vector<unsigned short> &vNodes1,
+                            const std::vector<cv::KeyPoint> &vKeys2, const cv::Mat &Descriptors2, const std::vector<unsigned short> &vNodes2,
+                            std::vector<int> &vnMatches12)
+{
+    const int n1 = (int)vKeys1.size(), n2 = (int)vKeys2.size();
+    vnMatches12.assign((size_t)n1, -1);
+    if (n1 == 0) return 0;
+    if ((int)vNodes1.size() != n1 || (int)vNodes2.size() != n2) throw std::runtime_error("ORBmatcher: one vocabulary node per keypoint expected");
+    Ensure(n1 > n2 ? n1 : n2, n1 > n2 ? n1 : n2);
+    const std::vector<unsigned char> d1 = pack_rows(Descriptors1), d2 = n2 ? pack_rows(Descriptors2) : std::vector<unsigned char>();
+    int nmatches = 0;
+    check(orbm_search_groups_host(mHandle, (const orbx_keypoint *)vKeys1.data(), d1.data(), vNodes1.data(), n1,
+                                  (const orbx_keypoint *)vKeys2.data(), d2.data(), vNodes2.data(), n2,
+                                  vnMatches12.data(), &nmatches, TH_LOW, mfNNratio, mbCheckOrientation ? 1 : 0), "search_groups");
+    if (nmatches < 0) throw std::runtime_error("ORBmatcher: search workspace too small");
+    return nmatches;
+}
+
 int ORBmatcher::SearchBruteForce(const cv::Mat &queries, const cv::Mat &database, std::vector<int> &vnMatches12)
 {
     std::vector<int> d1, i1, d2;

@@ -4,7 +4,8 @@
 // DescriptorDistance(a, b) (src/ORBmatcher.cpp:128-144), and the brute-force best-2 candidate scan with
 // TH_LOW / ratio acceptance (src/ORBmatcher.cpp:37-67) that SearchForInitialization, SearchByProjection
 // and SearchByBoW are built on.  The Frame/KeyFrame-typed entry points stay in the caller's code base
-// (SearchByBoW / SearchByProjection have empty bodies in the reference, ORBmatcher.h:22,24).
+// (SearchByBoW / SearchByProjection have empty bodies in the reference, ORBmatcher.h:22,24; the plain-container forms
+// below follow upstream ORB-SLAM2).
 #pragma once
 
 #include <vector>
@@ -53,6 +54,16 @@ public:
                            const std::vector<cv::KeyPoint> &vCurrentKeys, const cv::Mat &CurrentDescriptors,
                            const std::vector<float> &vScaleFactors, std::vector<int> &vnMatches, float th,
                            int imageWidth, int imageHeight);
+
+    // SearchByBoW(KeyFrame* pKF1, Frame F2, std::vector<MapPoint*>& vpMatches12) (include/ORBmatcher.h:22) on plain
+    // containers.  The reference's body is empty and it has no vocabulary, so the caller supplies the vocabulary node of
+    // every keypoint (DBoW2's FeatureVector, as a uint16 id; 0xffff = none) and the loop follows upstream ORB-SLAM2:
+    // nodes ascending, a node's F1 features ascending, candidates = the node's F2 features not matched yet, best two
+    // distances from 256, accept on best <= TH_LOW and best < mfNNratio * second, rotation histogram.
+    // vnMatches12[i] = F2 keypoint index or -1; returns #matches.
+    int SearchByBoW(const std::vector<cv::KeyPoint> &vKeys1, const cv::Mat &Descriptors1, const std::vector<unsigned short> &vNodes1,
+                    const std::vector<cv::KeyPoint> &vKeys2, const cv::Mat &Descriptors2, const std::vector<unsigned short> &vNodes2,
+                    std::vector<int> &vnMatches12);
 
     static const int TH_LOW;
     static const int TH_HIGH;

@@ -1046,12 +1046,83 @@ extern "C" int orbm_search_window_device(orbm_matcher *m, const orbx_keypoint *d
     // octaves of F2 any query can reach; the grid (and the sort) only holds those
     a.grid_level_min = params->level_below < 0 ? 0 : params->query_level_min - params->level_below;
     a.grid_level_max = params->level_above < 0 ? INT_MAX : params->query_level_max + params->level_above;
+    a.groups = nullptr; a.second_init = INT_MAX;
     a.workspace = (uint32_t *)d_workspace; a.ws_words_per_pair = workspace_bytes / sizeof(uint32_t) / (size_t)npairs;
     int sn = 32; while (sn < capacity) sn <<= 1;
     a.sort_n = sn;
     if (launch_search_init(a, stream ? (cudaStream_t)stream : m->stream)) return cuda_fail(cudaGetLastError(), "search_init smem");
     m->launches += 1;
     CK(cudaGetLastError());
+    return ORBX_OK;
+}
+
+extern "C" int orbm_search_groups_device(orbm_matcher *m, const orbx_keypoint *d_kps, const uint8_t *d_desc, const int32_t *d_counts,
+                                         const uint16_t *d_groups, int capacity, const int32_t *d_pair_a, const int32_t *d_pair_b, int npairs,
+                                         int32_t *d_matches12, int32_t *d_nmatches, int th_dist, float nnratio, int check_orientation,
+                                         void *d_workspace, size_t workspace_bytes, void *stream)
+{
+    if (!m || npairs < 0 || capacity < 1 || capacity >= 65536 || th_dist < 0) return ORBX_E_INVALID;
+    if (npairs == 0) return ORBX_OK;
+    if (!d_kps || !d_desc || !d_counts || !d_groups || !d_pair_a || !d_pair_b || !d_matches12 || !d_nmatches || !d_workspace) return ORBX_E_INVALID;
+    if (((uintptr_t)d_desc & 15) || ((uintptr_t)d_workspace & 3) || ((uintptr_t)d_groups & 1)) return ORBX_E_INVALID;
+    CK(cudaSetDevice(m->device));
+    SearchInitArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.kps = d_kps; a.desc = d_desc; a.counts = d_counts; a.cap = capacity;
+    a.pair_a = d_pair_a; a.pair_b = d_pair_b; a.npairs = npairs;
+    a.prev_matched = nullptr; a.matches12 = d_matches12; a.nmatches = d_nmatches;
+    a.w.gate = 1; a.w.th_dist = th_dist; a.w.nnratio = nnratio; a.w.check_orientation = check_orientation ? 1 : 0;
+    a.w.update_centers = 0; a.w.width = 1; a.w.height = 1;
+    a.groups = d_groups; a.second_init = 256;                 // upstream starts both best distances at 256
+    a.workspace = (uint32_t *)d_workspace; a.ws_words_per_pair = workspace_bytes / sizeof(uint32_t) / (size_t)npairs;
+    int sn = 32; while (sn < capacity) sn <<= 1;
+    a.sort_n = sn;
+    if (launch_search_init(a, stream ? (cudaStream_t)stream : m->stream)) return cuda_fail(cudaGetLastError(), "search_init smem");
+    m->launches += 1;
+    CK(cudaGetLastError());
+    return ORBX_OK;
+}
+
+extern "C" int orbm_search_groups_host(orbm_matcher *m, const orbx_keypoint *kp1, const uint8_t *desc1, const uint16_t *group1, int n1,
+                                       const orbx_keypoint *kp2, const uint8_t *desc2, const uint16_t *group2, int n2,
+                                       int32_t *matches12, int32_t *nmatches, int th_dist, float nnratio, int check_orientation)
+{
+    if (!m || n1 < 0 || n2 < 0 || n1 >= 65536 || n2 >= 65536 || !nmatches) return ORBX_E_INVALID;
+    if (n1 == 0) { *nmatches = 0; return ORBX_OK; }
+    if (!kp1 || !desc1 || !group1 || !matches12 || (n2 && (!kp2 || !desc2 || !group2))) return ORBX_E_INVALID;
+    CK(cudaSetDevice(m->device));
+    cudaStream_t s = m->stream;
+    const int cap = (n1 > n2 ? n1 : n2) < 1 ? 1 : (n1 > n2 ? n1 : n2);
+    const size_t wsb = orbm_search_init_workspace_bytes(cap, 1);
+    // one scratch allocation laid out as [kps 2][desc 2][groups 2][counts 2 + pairs 2][m12][nm][workspace]
+    const size_t o_kps = 0, o_desc = (o_kps + 2 * (size_t)cap * sizeof(orbx_keypoint) + 15) & ~(size_t)15,
+                 o_grp = (o_desc + 2 * (size_t)cap * 32 + 15) & ~(size_t)15, o_cnt = (o_grp + 2 * (size_t)cap * 2 + 15) & ~(size_t)15,
+                 o_m12 = o_cnt + 64, o_nm = o_m12 + (size_t)cap * 4, o_ws = (o_nm + 16 + 15) & ~(size_t)15;
+    const size_t need = o_ws + wsb;
+    if (need > m->si_bytes) {
+        if (m->si_buf) CK(cudaFree(m->si_buf));
+        m->si_buf = nullptr; m->si_bytes = 0;
+        if (cudaMalloc(&m->si_buf, need) != cudaSuccess) { cuda_fail(cudaGetLastError(), "cudaMalloc"); return ORBX_E_NOMEM; }
+        m->si_bytes = need;
+    }
+    unsigned char *b = (unsigned char *)m->si_buf;
+    const int meta[4] = { n1, n2, 0, 1 };
+    CK(cudaMemcpyAsync(b + o_kps, kp1, (size_t)n1 * sizeof(orbx_keypoint), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(b + o_desc, desc1, (size_t)n1 * 32, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(b + o_grp, group1, (size_t)n1 * 2, cudaMemcpyHostToDevice, s));
+    if (n2) {
+        CK(cudaMemcpyAsync(b + o_kps + (size_t)cap * sizeof(orbx_keypoint), kp2, (size_t)n2 * sizeof(orbx_keypoint), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(b + o_desc + (size_t)cap * 32, desc2, (size_t)n2 * 32, cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(b + o_grp + (size_t)cap * 2, group2, (size_t)n2 * 2, cudaMemcpyHostToDevice, s));
+    }
+    CK(cudaMemcpyAsync(b + o_cnt, meta, sizeof(meta), cudaMemcpyHostToDevice, s));
+    int rc = orbm_search_groups_device(m, (const orbx_keypoint *)(b + o_kps), b + o_desc, (const int *)(b + o_cnt), (const uint16_t *)(b + o_grp), cap,
+                                       (const int *)(b + o_cnt) + 2, (const int *)(b + o_cnt) + 3, 1, (int *)(b + o_m12), (int *)(b + o_nm),
+                                       th_dist, nnratio, check_orientation, b + o_ws, wsb, s);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(matches12, b + o_m12, (size_t)n1 * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(nmatches, b + o_nm, 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
     return ORBX_OK;
 }
 

@@ -105,6 +105,8 @@ struct SearchInitArgs {
     float *prev_matched; int *matches12; int *nmatches;                              // [npairs][cap][2], [npairs][cap], [npairs]
     orbm_window_params w;                                                            // see include/orbx.h
     int grid_level_min, grid_level_max;                                              // octaves of F2 worth putting in the grid
+    const unsigned short *groups;                                                    // [F][cap] group (vocabulary node) per keypoint, 0xffff = none; NULL = windowed search
+    int second_init;                                                                 // value of the second-best distance when there is none (INT_MAX / 256)
     uint32_t *workspace; unsigned long long ws_words_per_pair;
     int sort_n;                                                                      // power of two >= cap
 };

@@ -30,6 +30,23 @@ __device__ __forceinline__ int hamming256(const uint4 a0, const uint4 a1, const 
            __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
 }
 
+// block-wide bitonic sort of n (a power of two) keys in shared memory; ends with a barrier
+__device__ __forceinline__ void block_bitonic_sort(uint32_t *keys, int n, int tid)
+{
+    for (int k = 2; k <= n; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < n; i += kSiThreads) {
+                const int p = i ^ j;
+                if (p > i) {
+                    const uint32_t a = keys[i], b = keys[p];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { keys[i] = b; keys[p] = a; }
+                }
+            }
+            __syncthreads();
+        }
+}
+
 __global__ void __launch_bounds__(kSiThreads)
 k_search_init(const __grid_constant__ SearchInitArgs A)
 {
@@ -54,6 +71,8 @@ k_search_init(const __grid_constant__ SearchInitArgs A)
     float *prev = A.prev_matched + (size_t)pair * A.cap * 2;
     int *m12 = A.matches12 + (size_t)pair * A.cap;
     uint32_t *ws = A.workspace + (size_t)pair * A.ws_words_per_pair;
+    // group mode (SearchByBoW-style): candidates of a query are the F2 keypoints of the same group, no window
+    const unsigned short *g1 = A.groups ? A.groups + (size_t)fa * A.cap : nullptr, *g2 = A.groups ? A.groups + (size_t)fb * A.cap : nullptr;
 
     // image bounds for zero distortion (Frame.cpp:113-118) and grid cell sizes (:59-60)
     const orbm_window_params &W = A.w;
@@ -73,7 +92,10 @@ k_search_init(const __grid_constant__ SearchInitArgs A)
         // GetGridId takes doubles (Frame.cpp:161-168); std::round = half away from zero
         const int ix = (int)round(((double)k.x - (double)minX) * (double)wInv);
         const int iy = (int)round(((double)k.y - (double)(W.literal_gridid_bug ? maxY : minY)) * (double)hInv);
-        if (k.octave >= A.grid_level_min && k.octave <= A.grid_level_max && ix >= 0 && ix < kGridCols && iy >= 0 && iy < kGridRows)
+        if (g2) {
+            const uint32_t g = g2[i];
+            if (g != 0xffffu) keys[atomicAdd(&s_nvalid, 1)] = (g << 16) | (uint32_t)i;
+        } else if (k.octave >= A.grid_level_min && k.octave <= A.grid_level_max && ix >= 0 && ix < kGridCols && iy >= 0 && iy < kGridRows)
             keys[atomicAdd(&s_nvalid, 1)] = ((uint32_t)(ix * kGridRows + iy) << 16) | (uint32_t)i;
     }
     for (int i = tid; i < A.cap; i += kSiThreads) { matchedDist[i] = INT_MAX; m21[i] = -1; m12[i] = -1; }
@@ -82,20 +104,9 @@ k_search_init(const __grid_constant__ SearchInitArgs A)
     while (sort_m < s_nvalid) sort_m <<= 1;                                          // <= A.sort_n
     for (int i = s_nvalid + tid; i < sort_m; i += kSiThreads) keys[i] = kInfKey;
     __syncthreads();
-    for (int k = 2; k <= sort_m; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < sort_m; i += kSiThreads) {
-                const int p = i ^ j;
-                if (p > i) {
-                    const uint32_t a = keys[i], b = keys[p];
-                    const bool up = (i & k) == 0;
-                    if ((a > b) == up) { keys[i] = b; keys[p] = a; }
-                }
-            }
-            __syncthreads();
-        }
+    block_bitonic_sort(keys, sort_m, tid);
     // first key position of every (ix, iy) and the end sentinel: lower_bound by binary search
-    for (int c = tid; c <= kGridCols * kGridRows; c += kSiThreads) {
+    for (int c = tid; c <= kGridCols * kGridRows && !g2; c += kSiThreads) {
         const uint32_t target = (uint32_t)c << 16;
         int lo = 0, hi = sort_m;
         while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < target) lo = mid + 1; else hi = mid; }
@@ -113,6 +124,24 @@ k_search_init(const __grid_constant__ SearchInitArgs A)
         uint32_t *list = ws + (unsigned long long)q * stride;
         const orbx_keypoint kq = kp1[q];
         int cnt = 0;
+        if (g1) {
+            const uint32_t g = g1[q];
+            if (g != 0xffffu) {
+                // the group's keys are one contiguous range of the sorted array, in F2 index order (= the node's feature list)
+                int lo = 0, hi = sort_m;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < (g << 16)) lo = mid + 1; else hi = mid; }
+                int e = lo; hi = sort_m;
+                while (e < hi) { const int mid = (e + hi) >> 1; if (keys[mid] < ((g + 1u) << 16)) e = mid + 1; else hi = mid; }
+                const uint4 a0 = __ldg(d1 + 2 * q), a1 = __ldg(d1 + 2 * q + 1);
+                for (int p = lo + lane; p < e; p += 32) {
+                    const int i2 = (int)(keys[p] & 0xffffu);
+                    list[1 + p - lo] = (uint32_t)i2 | ((uint32_t)hamming256(a0, a1, d2 + 2 * i2) << 16);
+                }
+                cnt = e - lo;
+            }
+            if (lane == 0) { list[0] = (uint32_t)cnt; qcnt[q] = (unsigned short)cnt; }
+            continue;
+        }
         const float x = prev[2 * q], y = prev[2 * q + 1];
         // :25-27 level1 > 0 -> continue (query_level range 0..0 there); a NaN centre marks a query without a projection
         if (kq.octave >= W.query_level_min && kq.octave <= W.query_level_max && x == x) {
@@ -168,6 +197,23 @@ k_search_init(const __grid_constant__ SearchInitArgs A)
     }
     __syncthreads();
 
+    // group mode replays the queries node by node (ascending group, then ascending index -- the order in which upstream's
+    // SearchByBoW walks the two feature vectors): sort (group << 16 | q) of the queries that have candidates
+    if (g1) {
+        if (tid == 0) s_nvalid = 0;
+        __syncthreads();
+        for (int q = tid; q < n1; q += kSiThreads)
+            if (qcnt[q] != 0) keys[atomicAdd(&s_nvalid, 1)] = ((uint32_t)g1[q] << 16) | (uint32_t)q;
+        __syncthreads();
+        int m = 32;
+        while (m < s_nvalid) m <<= 1;
+        for (int i = s_nvalid + tid; i < m; i += kSiThreads) keys[i] = kInfKey;
+        __syncthreads();
+        block_bitonic_sort(keys, m, tid);
+        for (int i = tid; i < s_nvalid; i += kSiThreads) active[i] = (unsigned short)(keys[i] & 0xffffu);
+        __syncthreads();
+    }
+
     // ---- 2b: the order-dependent replay, one warp ----
     if (warp == 0) {
         const float factor = kHistoLength / 360.0f;                          // :17
@@ -176,8 +222,8 @@ k_search_init(const __grid_constant__ SearchInitArgs A)
         // indices are compacted in ascending order first.  The lists live in global memory: a query's first 64 entries
         // are fetched one iteration ahead, so the serial chain never waits on a load (ncu: the replay used to be ~70 %
         // of the kernel's time, spent on dependent global loads by a single warp).
-        int na = 0;
-        for (int b0 = 0; b0 < n1; b0 += 32) {
+        int na = g1 ? s_nvalid : 0;
+        for (int b0 = 0; b0 < n1 && !g1; b0 += 32) {
             const int q = b0 + lane;
             const bool on = q < n1 && qcnt[q] != 0;
             const uint32_t bal = __ballot_sync(0xffffffffu, on);
@@ -230,7 +276,7 @@ k_search_init(const __grid_constant__ SearchInitArgs A)
             const uint32_t w0 = __shfl_sync(0xffffffffu, e0, wp & 31), w1 = __shfl_sync(0xffffffffu, e1, wp & 31);
             if (lane == 0 && k1 != kInfKey) {
                 const int bestDist = (int)(k1 >> 16);
-                const int bestDist2 = k2 == kInfKey ? INT_MAX : (int)(k2 >> 16);
+                const int bestDist2 = k2 == kInfKey ? A.second_init : (int)(k2 >> 16);
                 const int bestIdx2 = (int)((wp < 32 ? w0 : (wp < 64 ? w1 : list[1 + wp])) & 0xffffu);
                 const bool ratio_ok = W.nnratio <= 0.f || (float)bestDist < __fmul_rn((float)bestDist2, W.nnratio);
                 if (bestDist <= W.th_dist && ratio_ok) {                                // :65-67

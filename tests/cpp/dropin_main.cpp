@@ -77,6 +77,16 @@ int main(int argc, char **argv)
         int cntp = (int)mp.size();
         std::fwrite(&np_, 4, 1, fo); std::fwrite(&cntp, 4, 1, fo);
         std::fwrite(mp.data(), 4, mp.size(), fo);
+        // SearchByBoW-style search: "vocabulary node" = first descriptor byte / 8
+        ORBSlam::ORBmatcher bow(0.7f, true);
+        std::vector<unsigned short> nodes0(allKps[0].size()), nodes1(allKps[1].size());
+        for (size_t i = 0; i < nodes0.size(); ++i) nodes0[i] = (unsigned short)(allDesc[0].ptr<unsigned char>((int)i)[0] >> 3);
+        for (size_t i = 0; i < nodes1.size(); ++i) nodes1[i] = (unsigned short)(allDesc[1].ptr<unsigned char>((int)i)[0] >> 3);
+        std::vector<int> mb;
+        int nb = bow.SearchByBoW(allKps[0], allDesc[0], nodes0, allKps[1], allDesc[1], nodes1, mb);
+        int cntb = (int)mb.size();
+        std::fwrite(&nb, 4, 1, fo); std::fwrite(&cntb, 4, 1, fo);
+        std::fwrite(mb.data(), 4, mb.size(), fo);
     }
     std::fclose(fo);
     delete ex;

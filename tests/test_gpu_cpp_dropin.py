@@ -80,3 +80,9 @@ def test_cpp_classes_match_oracle(orbx, oracle, tmp_path):
                              check_orientation=True, update_centers=False, width=640, height=480)
     n_po, m_po, _ = oracle.search_window(k1, dd1, k2, dd2, prev, P)
     assert n_p == n_po and np.array_equal(mp, m_po)
+    off += 4 * cntp
+    # ORBmatcher::SearchByBoW (plain-container form, node = first descriptor byte / 8) against the oracle's group search
+    n_b, cntb = struct.unpack_from("<2i", raw, off); off += 8
+    mb = np.frombuffer(raw, np.int32, cntb, off)
+    n_bo, m_bo = oracle.search_groups(k1, dd1, (dd1[:, 0] >> 3).astype(np.uint16), k2, dd2, (dd2[:, 0] >> 3).astype(np.uint16), 50, 0.7, True)
+    assert n_b == n_bo and np.array_equal(mb, m_bo)

@@ -120,3 +120,20 @@ def test_projection_style_windowed_search_matches_oracle(orbx, oracle, th, below
     n_o, m_o, c_o = oracle.search_window(k1, d1, k2, d2, cen, Po)
     assert n_g == n_o and np.array_equal(m_g, m_o) and np.array_equal(c_g, c_o, equal_nan=True)
     assert n_o > 300
+
+
+@pytest.mark.parametrize("ngroups,ratio,ori", [(32, 0.7, True), (1, 0.6, False), (200, 0.9, True)])
+def test_group_restricted_search_matches_oracle(orbx, oracle, ngroups, ratio, ori):
+    """SURVEY 8f-4, SearchByBoW form: candidates = the other frame's keypoints of the same group (vocabulary node)."""
+    a = synth_frame(6); b = np.roll(np.roll(a, 3, axis=1), 2, axis=0)
+    ex = orbx.Extractor(nfeatures=2000, max_width=640, max_height=480, max_batch=2)
+    kps, desc, cnt = ex.extract_host(np.stack([a, b]))
+    k1, d1, k2, d2 = kps[0][:cnt[0]], desc[0][:cnt[0]], kps[1][:cnt[1]], desc[1][:cnt[1]]
+    g1 = (d1[:, 0].astype(np.uint32) * ngroups // 256).astype(np.uint16)
+    g2 = (d2[:, 0].astype(np.uint32) * ngroups // 256).astype(np.uint16)
+    g1[::11] = 0xffff; g2[5::13] = 0xffff
+    m = orbx.Matcher(4096, 4096)
+    n_g, m_g = m.search_groups_host(k1, d1, g1, k2, d2, g2, 50, ratio, ori)
+    n_o, m_o = oracle.search_groups(k1, d1, g1, k2, d2, g2, 50, ratio, ori)
+    assert n_g == n_o and np.array_equal(m_g, m_o)
+    assert n_o > 100

@@ -69,3 +69,21 @@ def test_projection_style_search_properties(oracle):
     assert np.all(np.abs(k2["x"][m12[hit]] - cen[hit, 0]) < r) and np.all(np.abs(k2["y"][m12[hit]] - cen[hit, 1]) < r)
     dist = np.unpackbits(d1[hit] ^ d2[m12[hit]], axis=1).sum(1)
     assert np.all(dist <= 100)
+
+
+def test_group_search_properties(oracle):
+    """SearchByBoW-style search (reference body empty -> unpinned): matches stay inside a group, are one-to-one, pass the
+    acceptance, and with a single all-embracing group + generous ratio the first query takes the global best match."""
+    k1, d1, k2, d2 = _pair(oracle, 6, (3, 2))
+    g1 = (d1[:, 0] >> 3).astype(np.uint16); g2 = (d2[:, 0] >> 3).astype(np.uint16)
+    g1[::11] = 0xffff
+    n, m12 = oracle.search_groups(k1, d1, g1, k2, d2, g2, 50, 0.7, True)
+    hit = np.flatnonzero(m12 >= 0)
+    assert n == len(hit) and n > 200
+    assert np.all(g1[hit] == g2[m12[hit]]) and np.all(g1[hit] != 0xffff)
+    assert len(np.unique(m12[hit])) == len(hit)
+    assert np.all(np.unpackbits(d1[hit] ^ d2[m12[hit]], axis=1).sum(1) <= 50)
+    one = np.zeros(len(k1), np.uint16); two = np.zeros(len(k2), np.uint16)
+    n1, m1 = oracle.search_groups(k1[:1], d1[:1], one[:1], k2, d2, two, 256, 10.0, False)
+    dist = np.unpackbits(d1[:1] ^ d2, axis=1).sum(1)
+    assert n1 == 1 and m1[0] == int(np.argmin(dist))

@@ -2,7 +2,8 @@
 usage: python tools/fuzz_match.py [ncases] [seed]      (needs a GPU; test infrastructure, not product)
   * best-2 kNN on random sizes with planted duplicates and near-duplicates (ties, d1 == d2)
   * windowed search (SearchForInitialization / SearchByProjection instances) with random windows, level ranges,
-    gates, ratios and orientation checks on keypoints extracted from shifted synthetic frames"""
+    gates, ratios and orientation checks on keypoints extracted from shifted synthetic frames
+  * group-restricted search (SearchByBoW instance) with 1 .. 5000 groups"""
 import os, sys, time
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import numpy as np
@@ -67,7 +68,26 @@ def main():
             print("FAIL window seed=%d shift=(%d,%d) gate=%d r=%g lv=(%d,%d) q=(%d,%d) ratio=%g ori=%d upd=%d th=%d: %d vs %d"
                   % (sd, dx, dy, gate, radius, below, above, qlo, qhi, ratio, ori, upd, thd, n_g, n_o), flush=True)
     print("windowed search: %d cases, %d failures, %.1f s" % (n, wfails, time.time() - t0), flush=True)
-    return 1 if (fails or wfails) else 0
+
+    t0 = time.time()
+    gfails = 0
+    for case in range(n):
+        sd = int(rng.integers(0, 500)); dx, dy = int(rng.integers(-10, 11)), int(rng.integers(-10, 11))
+        a = synth_frame(sd); b = np.roll(np.roll(a, dx, axis=1), dy, axis=0)
+        kps, desc, cnt = ex.extract_host(np.stack([a, b]))
+        k1, d1, k2, d2 = kps[0][:cnt[0]], desc[0][:cnt[0]], kps[1][:cnt[1]], desc[1][:cnt[1]]
+        ng = int(rng.choice([1, 7, 32, 100, 1000, 5000]))
+        g1 = (d1[:, :2].view(np.uint16)[:, 0].astype(np.uint32) * ng // 65536).astype(np.uint16)
+        g2 = (d2[:, :2].view(np.uint16)[:, 0].astype(np.uint32) * ng // 65536).astype(np.uint16)
+        g1[rng.random(len(g1)) < 0.1] = 0xffff; g2[rng.random(len(g2)) < 0.1] = 0xffff
+        ratio = float(rng.choice([0.5, 0.6, 0.75, 0.9, 1.5])); ori = bool(rng.integers(0, 2)); thd = int(rng.choice([30, 50, 100, 256]))
+        n_g, m_g = m.search_groups_host(k1, d1, g1, k2, d2, g2, thd, ratio, ori)
+        n_o, m_o = oracle.search_groups(k1, d1, g1, k2, d2, g2, thd, ratio, ori)
+        if n_g != n_o or not np.array_equal(m_g, m_o):
+            gfails += 1
+            print("FAIL groups seed=%d ng=%d ratio=%g ori=%d th=%d: %d vs %d" % (sd, ng, ratio, ori, thd, n_g, n_o), flush=True)
+    print("group search: %d cases, %d failures, %.1f s" % (n, gfails, time.time() - t0), flush=True)
+    return 1 if (fails or wfails or gfails) else 0
 
 
 if __name__ == "__main__":
