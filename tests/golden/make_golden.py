@@ -97,6 +97,31 @@ def main():
     m = O.ratio_select(d1, i1, d2, 50, 0.7)
     out["knn"] = {"ndb": 20000, "nq": 3000, "db_sha256": sha(db), "q_sha256": sha(q), "d1_sha256": sha(d1),
                   "idx1_sha256": sha(i1), "d2_sha256": sha(d2), "match_sha256": sha(m), "n_matched": int((m >= 0).sum())}
+    # matcher entry points on a frame pair (frame 0 and a shifted copy), extracted by the oracle with nfeatures = 2000
+    fa = synth_frame(0); fb = np.roll(np.roll(fa, 5, axis=1), 3, axis=0)
+    exm = O.OracleExtractor(nfeatures=2000)
+    k1, dd1 = exm(fa); k2, dd2 = exm(fb)
+    prev = np.stack([k1["x"], k1["y"]], 1)
+    n_si, m_si, p_si = O.search_for_initialization(k1, dd1, k2, dd2, prev, 100, 0.9, True, 640, 480)
+    assert R.build_match(), "oracle/_ref/ref_match must be buildable here"
+    n_rf, m_rf, p_rf = R.run_search_for_initialization(k1, dd1, k2, dd2, prev, 100, 0.9, True, 640, 480, False)
+    assert n_si == n_rf and np.array_equal(m_si, m_rf) and np.array_equal(p_si, p_rf), "SearchForInitialization: oracle != reference TU"
+    sf = [float(v) for v in exm.scale_factors]
+    cen = np.stack([k1["x"] + 5, k1["y"] + 3], 1).astype(np.float32)
+    wp = O.window_params(7.0, sf, (0, 15), 1, 1, gate=1, th_dist=100, nnratio=0.0, check_orientation=True, update_centers=False,
+                         width=640, height=480)
+    n_w, m_w, _ = O.search_window(k1, dd1, k2, dd2, cen, wp)
+    g1 = (dd1[:, 0] >> 3).astype(np.uint16); g2 = (dd2[:, 0] >> 3).astype(np.uint16)
+    n_g, m_g = O.search_groups(k1, dd1, g1, k2, dd2, g2, 50, 0.7, True)
+    out["search"] = {"pair": "synth seed 0 vs the same frame rolled by (5, 3), nfeatures 2000",
+                     "n1": int(len(k1)), "n2": int(len(k2)), "desc1_sha256": sha(dd1), "desc2_sha256": sha(dd2),
+                     "search_init": {"window": 100, "ratio": 0.9, "ori": True, "n": int(n_si), "m12_sha256": sha(m_si), "prev_sha256": sha(p_si),
+                                     "pinned": "equal to the reference's src/ORBmatcher.cpp (oracle/_ref/ref_match) at generation time"},
+                     "projection": {"th": 7.0, "levels": [1, 1], "th_dist": 100, "n": int(n_w), "m12_sha256": sha(m_w),
+                                    "pinned": "unpinned by the reference (empty body); oracle restatement of upstream"},
+                     "bow": {"group": "first descriptor byte >> 3", "th_dist": 50, "ratio": 0.7, "n": int(n_g), "m12_sha256": sha(m_g),
+                             "pinned": "unpinned by the reference (empty body); oracle restatement of upstream"}}
+    print("search", n_si, n_w, n_g)
     # known-answer vectors for DescriptorDistance
     a = np.zeros((4, 32), np.uint8); b = np.zeros((4, 32), np.uint8)
     b[1] = 0xff; a[2, :4] = [0x0f, 0xf0, 0xaa, 0x55]; a[3] = np.arange(32); b[3] = np.arange(32)[::-1]

@@ -80,3 +80,24 @@ def test_full_size_knn_properties(orbx):
         dist = np.unpackbits(q[qi][None] ^ db, axis=1).sum(1)
         order = np.argsort(dist, kind="stable")
         assert i1[qi] == order[0] and d1[qi] == dist[order[0]] and d2[qi] == dist[order[1]]
+
+
+def test_cuda_matcher_entry_points_match_golden(orbx):
+    """The three search instances through the C ABI against the committed golden hashes (no oracle involved)."""
+    from orbslam_in_practice_b200.synth import synth_frame
+    g = GOLD["search"]
+    fa = synth_frame(0); fb = np.roll(np.roll(fa, 5, axis=1), 3, axis=0)
+    ex = orbx.Extractor(nfeatures=2000, max_width=640, max_height=480, max_batch=2)
+    kps, desc, cnt = ex.extract_host(np.stack([fa, fb]))
+    k1, d1, k2, d2 = kps[0][:cnt[0]], desc[0][:cnt[0]], kps[1][:cnt[1]], desc[1][:cnt[1]]
+    assert len(k1) == g["n1"] and len(k2) == g["n2"] and sha(d1) == g["desc1_sha256"] and sha(d2) == g["desc2_sha256"]
+    m = orbx.Matcher(4096, 4096)
+    prev = np.stack([k1["x"], k1["y"]], 1)
+    n, m12, p = m.search_init_host(k1, d1, k2, d2, prev, 100, 0.9, True, 640, 480)
+    assert n == g["search_init"]["n"] and sha(m12) == g["search_init"]["m12_sha256"] and sha(p) == g["search_init"]["prev_sha256"]
+    cen = np.stack([k1["x"] + 5, k1["y"] + 3], 1).astype(np.float32)
+    P = orbx.WindowParams.projection(7.0, [float(v) for v in ex.scale_factors], 640, 480, th_dist=100, check_orientation=True)
+    n, m12, _ = m.search_window_host(k1, d1, k2, d2, cen, P)
+    assert n == g["projection"]["n"] and sha(m12) == g["projection"]["m12_sha256"]
+    n, m12 = m.search_groups_host(k1, d1, (d1[:, 0] >> 3).astype(np.uint16), k2, d2, (d2[:, 0] >> 3).astype(np.uint16), 50, 0.7, True)
+    assert n == g["bow"]["n"] and sha(m12) == g["bow"]["m12_sha256"]

@@ -91,3 +91,25 @@ def test_fast_score_identity(oracle):
         assert len(kp) > 0
         for k in kp[:200]:
             assert s0[k["y"], k["x"]] == k["score"] and k["score"] >= t
+
+
+def test_matcher_entry_points_golden(oracle):
+    """SearchForInitialization (pinned against the reference's ORBmatcher.cpp when the golden was written) and the two
+    upstream-form searches, on the golden frame pair."""
+    from orbslam_in_practice_b200.synth import synth_frame
+    g = GOLD["search"]
+    fa = synth_frame(0); fb = np.roll(np.roll(fa, 5, axis=1), 3, axis=0)
+    ex = oracle.OracleExtractor(nfeatures=2000)
+    k1, d1 = ex(fa); k2, d2 = ex(fb)
+    assert len(k1) == g["n1"] and len(k2) == g["n2"] and sha(d1) == g["desc1_sha256"] and sha(d2) == g["desc2_sha256"]
+    prev = np.stack([k1["x"], k1["y"]], 1)
+    n, m12, p = oracle.search_for_initialization(k1, d1, k2, d2, prev, 100, 0.9, True, 640, 480)
+    assert n == g["search_init"]["n"] and sha(m12) == g["search_init"]["m12_sha256"] and sha(p) == g["search_init"]["prev_sha256"]
+    sf = [float(v) for v in ex.scale_factors]
+    cen = np.stack([k1["x"] + 5, k1["y"] + 3], 1).astype(np.float32)
+    wp = oracle.window_params(7.0, sf, (0, 15), 1, 1, gate=1, th_dist=100, nnratio=0.0, check_orientation=True, update_centers=False,
+                              width=640, height=480)
+    n, m12, _ = oracle.search_window(k1, d1, k2, d2, cen, wp)
+    assert n == g["projection"]["n"] and sha(m12) == g["projection"]["m12_sha256"]
+    n, m12 = oracle.search_groups(k1, d1, (d1[:, 0] >> 3).astype(np.uint16), k2, d2, (d2[:, 0] >> 3).astype(np.uint16), 50, 0.7, True)
+    assert n == g["bow"]["n"] and sha(m12) == g["bow"]["m12_sha256"]
