@@ -335,24 +335,27 @@ def run_ours(args):
 
     # Same steps through the split call (orbx_extract_host_begin / _end) on two handles: step k+1's upload is in flight
     # while step k's kernels run.  Every step still uploads its own 256 frames and downloads its own results.
+    # Three batches in flight saturate the upload path of this box (49.6 GB/s against 47.8 with two, tools/e2e_depth_probe.py).
     ex_b = _lib.Extractor(NFEAT, SCALE, NLEVELS, INI_TH, MIN_TH, W, H, BATCH, local)
+    DEPTH = 3 if W * H <= 1 << 20 else 2
     slots = []
-    for e in (ex, ex_b):
+    for e in (ex, ex_b, ex2)[:DEPTH]:
         slots.append((e, torch.from_numpy(frames_np).pin_memory(), torch.empty((BATCH, cap, 7), dtype=torch.float32).pin_memory(),
                       torch.empty((BATCH, cap, 32), dtype=torch.uint8).pin_memory(), torch.empty(BATCH, dtype=torch.int32).pin_memory()))
 
     def begin(i):
-        e, hf, hk, hd, hc = slots[i & 1]
+        e, hf, hk, hd, hc = slots[i % DEPTH]
         e.extract_host_begin(hf.data_ptr(), W, W * H, W, H, BATCH, hk.data_ptr(), hd.data_ptr(), hc.data_ptr())
 
     def end(i):
-        slots[i & 1][0].extract_host_end()
+        slots[i % DEPTH][0].extract_host_end()
 
     def run_pipelined(n):
-        begin(0)
+        for i in range(min(DEPTH - 1, n)):
+            begin(i)
         for i in range(n):
-            if i + 1 < n:
-                begin(i + 1)
+            if i + DEPTH - 1 < n:
+                begin(i + DEPTH - 1)
             end(i)
 
     run_pipelined(Wm + 1)
@@ -362,7 +365,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
     barrier()
-    assert int(slots[0][4].sum()) == kp_total and int(slots[1][4].sum()) == kp_total, "pipelined host path disagrees"
+    assert all(int(sl[4].sum()) == kp_total for sl in slots), "pipelined host path disagrees"
     del ex_b
     clocks = sampler.stop()
     e2e_value = world * BATCH * K / (e2e_ms * 1e-3)
@@ -455,8 +458,8 @@ def run_ours(args):
                 "single_handle": {"value": world * BATCH * K / (ms_single * 1e-3), "unit": "frames/s", "ms_per_step": ms_single / K},
                 "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / K,
-                        "api": "orbx_extract_host_begin/_end (C ABI) on two handles, pinned host buffers: consecutive steps overlap "
-                               "(upload of step k+1 during the kernels of step k); every step uploads its frames and downloads its results",
+                        "api": "orbx_extract_host_begin/_end (C ABI) on %d handles, pinned host buffers: consecutive steps overlap "
+                               "(uploads of the next steps during the kernels of step k); every step uploads its frames and downloads its results" % DEPTH,
                         "single_blocking_call": {"value": e2e_sync_value, "ms_per_step": e2e_sync_ms / K, "api": "orbx_extract_host"}},
                 "gpu_launches": int(launches),
                 "roofline": roofline, "clocks": clocks}
