@@ -168,13 +168,17 @@ k_describe(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, const
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int f = blockIdx.y + g.frame0;
     uint32_t *patch = patch_all[warp];
-    // lane i owns descriptor byte i = pattern points 16i .. 16i+15 = 32 signed bytes = 8 words
-    uint32_t pw[8];
-    {
-        const uint4 p0 = __ldg(reinterpret_cast<const uint4 *>(pattern_words) + lane * 2);
-        const uint4 p1 = __ldg(reinterpret_cast<const uint4 *>(pattern_words) + lane * 2 + 1);
-        pw[0] = p0.x; pw[1] = p0.y; pw[2] = p0.z; pw[3] = p0.w; pw[4] = p1.x; pw[5] = p1.y; pw[6] = p1.z; pw[7] = p1.w;
+    // lane i owns descriptor byte i = pattern points 16i .. 16i+15.  The pattern lives in shared memory as floats, one
+    // float4 (x0, y0, x1, y1 of a test pair) per (pair k, lane): consecutive lanes read consecutive 16 bytes.  Held in
+    // registers (8 packed words + the floats the compiler hoisted out of the slot loop) it cost 96 bytes of spills.
+    __shared__ float4 pat[8][32];
+    if (threadIdx.x < 256) {
+        const int k = threadIdx.x >> 5, l = threadIdx.x & 31;
+        const uint32_t w = __ldg(pattern_words + l * 8 + k);
+        pat[k][l] = make_float4((float)(int)(signed char)(w), (float)(int)(signed char)(w >> 8),
+                                (float)(int)(signed char)(w >> 16), (float)(int)(signed char)(w >> 24));
     }
+    __syncthreads();
     // per-level keypoint counts -> inclusive prefix in lanes 0..nlevels-1 (level-major concatenation, :1036-1063)
     const int myc = lane < g.nlevels ? nkept[f * g.nlevels + lane] : 0;
     int incl = myc;
@@ -243,9 +247,8 @@ k_describe(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, const
         int val = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const uint32_t w = pw[k];
-            const float x0 = (float)(int)(signed char)(w), y0 = (float)(int)(signed char)(w >> 8);
-            const float x1 = (float)(int)(signed char)(w >> 16), y1 = (float)(int)(signed char)(w >> 24);
+            const float4 pp = pat[k][lane];
+            const float x0 = pp.x, y0 = pp.y, x1 = pp.z, y1 = pp.w;
             const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
             const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
             const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
