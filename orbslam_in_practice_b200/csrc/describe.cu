@@ -158,7 +158,7 @@ constexpr int kPatchWords = (2 * kPatchR + 1 + 3 + 3) / 4; // 37 px + up to 3 px
 // One warp per keypoint.  ncu, round 1: the direct-gather version needed ~20 L1 wavefronts for each
 // of the 16 scattered descriptor loads per lane; the 37x37 blurred patch is therefore staged in
 // shared memory with coalesced word loads and gathered from there (<= 4-way bank conflicts).
-__global__ void __launch_bounds__(kDescWarps * 32, 4)
+__global__ void __launch_bounds__(kDescWarps * 32, 5)
 k_describe(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, const uint8_t *__restrict__ blur,
            const uint32_t *__restrict__ kept, const int *__restrict__ nkept,
            orbx_keypoint *__restrict__ out_kps, uint8_t *__restrict__ out_desc, int *__restrict__ out_counts,
