@@ -225,6 +225,28 @@ static void staged_resize_tables(const LevelGeom &S, LevelGeom &L, std::vector<i
     if ((size_t)L.rs_tile_w * (size_t)L.rs_tile_h + 1024 > 46 * 1024) L.rs_staged = 0;
 }
 
+// FAST cell descriptors of a frame geometry (ORBextractor.cpp:745-762: the cell rectangle and its skip rules), one int4
+// per cell: the kernel's per-warp prologue becomes one 16-byte load instead of a level search, a division and the clamps.
+static void build_cell_table(const Geo &g, std::vector<int4> &tab)
+{
+    tab.assign((size_t)g.total_cells, make_int4(0, 0, 0, 0));
+    for (int l = 0; l < g.nlevels; ++l) {
+        const LevelGeom &L = g.lv[l];
+        for (int ci = 0; ci < L.nRows; ++ci)
+            for (int cj = 0; cj < L.nCols; ++cj) {
+                const int c = ci * L.nCols + cj;
+                const int iniY = kMinBorder + ci * L.hCell, iniX = kMinBorder + cj * L.wCell;
+                int cw = 0, ch = 0;
+                if (!(iniY >= L.maxBorderY - 3 || iniX >= L.maxBorderX - 6)) {
+                    cw = std::min(iniX + L.wCell + 6, L.maxBorderX) - iniX;
+                    ch = std::min(iniY + L.hCell + 6, L.maxBorderY) - iniY;
+                    if (cw - 6 <= 0 || ch - 6 <= 0) cw = ch = 0;
+                }
+                tab[(size_t)L.cell_base + c] = make_int4(l, iniX | (iniY << 16), cw | (ch << 16), (int)(L.slot_base + (unsigned long long)c * L.cell_cap));
+            }
+    }
+}
+
 static int build_geometry(const orbx_extractor *ex, int w, int h, Geo &g, std::vector<int2> *tables)
 {
     std::memset(&g, 0, sizeof(g));
@@ -312,6 +334,12 @@ static int upload_geometry(orbx_extractor *ex, int w, int h)
     ex->geo = ng;
     ex->geo.capacity = ex->full.capacity;   // output row stride stays the creation capacity
     if (tables.size() > ex->tables_cap) return ORBX_E_CAPACITY;
+    {
+        std::vector<int4> cells;
+        build_cell_table(ng, cells);
+        if (!cells.empty()) CK(cudaMemcpyAsync(ex->buf.cell_tab, cells.data(), cells.size() * sizeof(int4), cudaMemcpyHostToDevice, ex->stream));
+        CK(cudaStreamSynchronize(ex->stream));      // pageable host memory about to go out of scope
+    }
     if (!tables.empty()) CK(cudaMemcpyAsync(ex->buf.tables, tables.data(), tables.size() * sizeof(int2), cudaMemcpyHostToDevice, ex->stream));
     CK(cudaStreamSynchronize(ex->stream));   // `tables` is pageable host memory about to go out of scope
     ex->cur_w = w; ex->cur_h = h;
@@ -377,6 +405,7 @@ extern "C" int orbx_create(const orbx_params *p, int max_width, int max_height, 
     TRY(dev_alloc(ex, &b.blur, g.blur_frame_total));
     ex->tables_cap = ntab + 8 * ORBX_MAX_LEVELS;
     TRY(dev_alloc(ex, &b.tables, ex->tables_cap));
+    TRY(dev_alloc(ex, &b.cell_tab, (size_t)g.total_cells));
     TRY(dev_alloc(ex, &b.cell_count, F * g.total_cells));
     TRY(dev_alloc(ex, &b.cell_slots, F * g.slots_per_frame));
     TRY(dev_alloc(ex, &b.keysA, F * g.keys_per_frame));

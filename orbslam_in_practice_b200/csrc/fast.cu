@@ -44,7 +44,7 @@ __device__ __forceinline__ int arc9_maxmin(const int (&e)[16])
 
 __global__ void __launch_bounds__(kFastThreads)
 k_fast_cells(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr,
-             int *__restrict__ cell_count, uint32_t *__restrict__ cell_slots, const FastSmem sm)
+             int *__restrict__ cell_count, uint32_t *__restrict__ cell_slots, const int4 *__restrict__ cell_tab, const FastSmem sm)
 {
     extern __shared__ __align__(16) unsigned char fast_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -56,22 +56,14 @@ k_fast_cells(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr,
     uint16_t *queue = reinterpret_cast<uint16_t *>(mine + sm.off_queue);      // phase A survivors
     const int kTP = sm.tp, kSP = sm.sp;
 
-    int level = 0;
-#pragma unroll 1
-    for (int l = 1; l < g.nlevels; ++l) if (cell >= g.lv[l].cell_base) level = l;
-    const LevelGeom &L = g.lv[level];
-    const int c = cell - L.cell_base;
-    const int ci = c / L.nCols, cj = c - ci * L.nCols;
+    // cell rectangle, ORBextractor.cpp:745-762, precomputed on the host (build_cell_table): one 16-byte load
+    const int4 ct = __ldg(cell_tab + cell);
+    const LevelGeom &L = g.lv[ct.x];
     int *count_out = cell_count + (size_t)f * g.total_cells + cell;
-
-    // cell rectangle, ORBextractor.cpp:745-762 (all values are integers held in floats there)
-    const int iniY = kMinBorder + ci * L.hCell, iniX = kMinBorder + cj * L.wCell;
-    int maxY = iniY + L.hCell + 6, maxX = iniX + L.wCell + 6;
-    if (iniY >= L.maxBorderY - 3 || iniX >= L.maxBorderX - 6) { if (lane == 0) *count_out = 0; return; }
-    maxY = min(maxY, L.maxBorderY); maxX = min(maxX, L.maxBorderX);
-    const int cw = maxX - iniX, ch = maxY - iniY;      // cell image size handed to cv::FAST
+    const int iniX = ct.y & 0xffff, iniY = ct.y >> 16;
+    const int cw = ct.z & 0xffff, ch = ct.z >> 16;     // cell image size handed to cv::FAST (0: the reference skips the cell)
+    if (cw == 0) { if (lane == 0) *count_out = 0; return; }
     const int iw = cw - 6, ih = ch - 6;                // pixels FAST actually tests
-    if (iw <= 0 || ih <= 0) { if (lane == 0) *count_out = 0; return; }
 
     // ---- phase 0: stage the tile with aligned 16-byte loads: tile column 0 is the 16-byte aligned pixel at
     //      or left of iniX (rows are 64-byte aligned, the interior starts at byte 32), so cell column c lives
@@ -194,7 +186,7 @@ k_fast_cells(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr,
     }
 
     // ---- phase D: ordered emission (row-major = ascending bit index) ----
-    uint32_t *slots = cell_slots + (size_t)f * g.slots_per_frame + L.slot_base + (size_t)c * L.cell_cap;
+    uint32_t *slots = cell_slots + (size_t)f * g.slots_per_frame + (size_t)(unsigned)ct.w;
     int base = 0;
     if (found) {
         for (int w0 = 0; w0 < nbm; w0 += 32) {
@@ -211,7 +203,7 @@ k_fast_cells(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr,
                 const int idx = wi * 32 + b;
                 const int y = idx >> bsh, x = idx & ((1 << bsh) - 1);
                 // keypoint in level coordinates relative to (16,16): cell pixel (x+3, y+3) + (j*wCell, i*hCell)
-                slots[pos++] = pack_cand(x + 3 + cj * L.wCell, y + 3 + ci * L.hCell, score[(y + 1) * kSP + (x + 1)]);
+                slots[pos++] = pack_cand(x + 3 + iniX - kMinBorder, y + 3 + iniY - kMinBorder, score[(y + 1) * kSP + (x + 1)]);
             }
             base += __shfl_sync(0xffffffffu, inc, 31);
         }
@@ -235,7 +227,7 @@ void launch_fast(const Geo &g, const DevBuffers &b, int nframes, cudaStream_t s)
     // per-device function attribute; a handful of nanoseconds, so no process-wide caching (one handle per device each)
     if (bytes > 48 * 1024) cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     dim3 grd((g.total_cells + kFastWarps - 1) / kFastWarps, nframes);
-    k_fast_cells<<<grd, kFastThreads, bytes, s>>>(g, b.pyr, b.cell_count, b.cell_slots, sm);
+    k_fast_cells<<<grd, kFastThreads, bytes, s>>>(g, b.pyr, b.cell_count, b.cell_slots, b.cell_tab, sm);
 }
 
 } // namespace orbx

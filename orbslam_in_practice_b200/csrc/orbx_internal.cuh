@@ -74,6 +74,7 @@ struct DevBuffers {
     uint8_t *pyr;        // bordered pyramid levels, level-major then frame
     uint8_t *blur;       // blurred levels
     int2 *tables;        // resize tables
+    int4 *cell_tab;      // [total_cells] FAST cell descriptors {level, iniX | iniY << 16, cw | ch << 16 (0: skipped cell), slot offset}
     int *cell_count;     // [F][total_cells]
     uint32_t *cell_slots;// [F][slots_per_frame]
     uint32_t *keysA, *keysB;   // [F][keys_per_frame]
