@@ -54,14 +54,14 @@ k_level0(const __grid_constant__ Geo g, uint8_t *__restrict__ pyr, const uint8_t
         // cvtColor(..2GRAY) fused into the level-0 pass (src/Tracking.cpp:57-70); OpenCV 8U fixed point, 15 bits
         const int C = g.in_channels, ro = g.in_rgb ? 0 : 2, bo = g.in_rgb ? 2 : 0;
         for (int j = 0; j < nrows; ++j) {
-            const uint8_t *row = src + (size_t)reflect101(Y0 + j, L.h) * in_pitch;
+            const uint8_t *row = src + (size_t)reflect_fast(Y0 + j, L.h) * in_pitch;
             uint32_t w[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 uint32_t v = 0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const uint8_t *p = row + (size_t)reflect101(min(max(X0 + 4 * q + k, -B), L.w + B - 1), L.w) * C;
+                    const uint8_t *p = row + (size_t)reflect_fast(min(max(X0 + 4 * q + k, -B), L.w + B - 1), L.w) * C;
                     const int gray = (__ldg(p + ro) * 9798 + __ldg(p + 1) * 19235 + __ldg(p + bo) * 3735 + 16384) >> 15;
                     v |= (uint32_t)gray << (8 * k);
                 }
