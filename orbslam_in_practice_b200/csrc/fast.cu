@@ -29,7 +29,7 @@ struct FastSmem { int tp, sp, tile_rows, npix_max, off_score, off_queue, off_bm,
 __device__ __forceinline__ int min3(int a, int b, int c) { return __vimin3_s32(a, b, c); }
 __device__ __forceinline__ int max3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
 
-// max over the 16 arcs of 9 contiguous ring values of their minimum (cornerScore<16>'s core)
+// max over the 16 arcs of 9 contiguous ring values of their minimum (cornerScore<16>'s core, bright arcs)
 __device__ __forceinline__ int arc9_maxmin(const int (&e)[16])
 {
     int m3[16], m9[16];
@@ -39,9 +39,30 @@ __device__ __forceinline__ int arc9_maxmin(const int (&e)[16])
     for (int k = 0; k < 16; ++k) m9[k] = min3(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
     int b0 = max3(m9[0], m9[1], m9[2]), b1 = max3(m9[3], m9[4], m9[5]), b2 = max3(m9[6], m9[7], m9[8]);
     int b3 = max3(m9[9], m9[10], m9[11]), b4 = max3(m9[12], m9[13], m9[14]);
-    return max3(max3(b0, b1, b2), max3(b3, b4, m9[15]), -512);
+    return max3(max3(b0, b1, b2), b3, max3(b4, m9[15], m9[15]));
+}
+// min over the 16 arcs of their maximum (dark arcs)
+__device__ __forceinline__ int arc9_minmax(const int (&e)[16])
+{
+    int m3[16], m9[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) m3[k] = max3(e[k], e[(k + 1) & 15], e[(k + 2) & 15]);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) m9[k] = max3(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+    int b0 = min3(m9[0], m9[1], m9[2]), b1 = min3(m9[3], m9[4], m9[5]), b2 = min3(m9[6], m9[7], m9[8]);
+    int b3 = min3(m9[9], m9[10], m9[11]), b4 = min3(m9[12], m9[13], m9[14]);
+    return min3(min3(b0, b1, b2), b3, min3(b4, m9[15], m9[15]));
 }
 
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// TP: tile pitch as a compile-time constant (64 covers every cell up to 28 + 36 = 43 px wide incl. the alignment
+// slack, i.e. all VGA / KITTI / 4K geometries), 0 = the runtime pitch sm.tp.
+template <int TP>
 __global__ void __launch_bounds__(kFastThreads)
 k_fast_cells(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr,
              int *__restrict__ cell_count, uint32_t *__restrict__ cell_slots, const int4 *__restrict__ cell_tab, const FastSmem sm)
@@ -53,8 +74,9 @@ k_fast_cells(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr,
     unsigned char *mine = fast_smem + warp * sm.per_warp;
     uint8_t *tile = mine;                                                     // [tile_rows][tp]
     uint8_t *score = mine + sm.off_score;                                     // [tile_rows - 4][sp]
-    uint16_t *queue = reinterpret_cast<uint16_t *>(mine + sm.off_queue);      // phase A survivors
-    const int kTP = sm.tp, kSP = sm.sp;
+    uint16_t *queue = reinterpret_cast<uint16_t *>(mine + sm.off_queue);      // phase A survivors: bright from the front, dark from the back
+    const int kTP = TP ? TP : sm.tp, kSP = sm.sp;
+    const int qlast = sm.npix_max - 1;
 
     // cell rectangle, ORBextractor.cpp:745-762, precomputed on the host (build_cell_table): one 16-byte load
     const int4 ct = __ldg(cell_tab + cell);
@@ -65,17 +87,20 @@ k_fast_cells(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr,
     if (cw == 0) { if (lane == 0) *count_out = 0; return; }
     const int iw = cw - 6, ih = ch - 6;                // pixels FAST actually tests
 
-    // ---- phase 0: stage the tile with aligned 16-byte loads: tile column 0 is the 16-byte aligned pixel at
-    //      or left of iniX (rows are 64-byte aligned, the interior starts at byte 32), so cell column c lives
-    //      at tile column c + xoff.  Eight rows per warp pass (4 lanes x 16 B cover <= 64 px + 15 slack). ----
+    // ---- phase 0: stage the tile with 16-byte cp.async (no registers, every row of the lane in flight at once):
+    //      tile column 0 is the 16-byte aligned pixel at or left of iniX (rows are 64-byte aligned, the interior
+    //      starts at byte 32), so cell column c lives at tile column c + xoff.  4 rows per warp pass. ----
     const int xoff = iniX & 15;
     {
         const uint8_t *img = pyr + L.base + (size_t)f * L.frame_stride + (size_t)(kPadY + iniY) * L.pitch + kPadX + (iniX - xoff);
         const int vpr = (cw + xoff + 15) >> 4;              // 16-byte vectors per tile row (<= kTP / 16)
         const int sub = lane & 7, rr = lane >> 3;           // up to 8 vectors per row, 4 rows per pass
-        if (sub < vpr)
-            for (int r = rr; r < ch; r += 4)
-                *reinterpret_cast<uint4 *>(tile + r * kTP + sub * 16) = __ldg(reinterpret_cast<const uint4 *>(img + (size_t)r * L.pitch) + sub);
+        if (sub < vpr) {
+            const uint8_t *src = img + (size_t)rr * L.pitch + sub * 16;
+            uint8_t *dst = tile + rr * kTP + sub * 16;
+            const size_t sstep = (size_t)4 * L.pitch;
+            for (int r = rr; r < ch; r += 4, src += sstep, dst += 4 * kTP) cp_async16(dst, src);
+        }
     }
     // NMS bitmap: one 32- or 64-bit row of bits per pixel row (bit = column), so bit order is row-major and the
     // emission needs no division
@@ -97,68 +122,90 @@ k_fast_cells(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr,
             for (int i = lane; i < nwords; i += 32) s32[i] = 0;
             for (int i = lane; i < nbm; i += 32) bm[i] = 0;
         }
+        cp_async_wait_all();                               // the tile (first attempt; nothing pending on the second)
         __syncwarp();
 
-        // ---- phase A: compass pre-test, lane = column.  Each lane collects its column's verdicts for up to
-        //      32 rows in two bitmasks, then the warp compacts them into the queue with one scan. ----
-        int nq = 0;
+        // ---- phase A: compass pre-test, lane = column, walking down the rows with the column's last six pixels in
+        //      registers (N of row y is the centre of row y+3 and S of row y+6): three loads per pixel.  The two
+        //      verdicts are sign bits, (v + t) - min(max(N,S),max(E,W)) < 0 and max(min(N,S),min(E,W)) + t - v < 0,
+        //      shifted into per-lane masks with one funnel shift each (row y ends up at bit nr-1-y). ----
+        int nb = 0, nd = 0;                                // queue fill: bright [0, nb), dark (qlast - nd, qlast]
         for (int x0 = 0; x0 < iw; x0 += 32) {
             const int x = x0 + lane;
             const bool inx = x < iw;
             for (int yb = 0; yb < ih; yb += 32) {
                 const int rows = min(32, ih - yb);
+                const int nr = (rows + 7) & ~7;            // rows walked (the extra ones are masked off below)
                 const uint8_t *p = tile + (yb + 3) * kTP + 3 + xoff + (inx ? x : 0);
-                uint32_t mb = 0, md = 0, bit = 1;
-#pragma unroll 4
-                for (int y = 0; y < rows; ++y, p += kTP, bit <<= 1) {
-                    const int v = p[0];
-                    const int n = p[3 * kTP], s = p[-3 * kTP], e = p[3], w = p[-3];
-                    const int hiv = min(max(n, s), max(e, w)) - v;          // > t: a bright arc is possible
-                    const int lov = v - max(min(n, s), min(e, w));          // > t: a dark arc is possible
-                    mb |= hiv > th ? bit : 0u;
-                    md |= lov > th ? bit : 0u;
+                int c0 = p[-3 * kTP], c1 = p[-2 * kTP], c2 = p[-kTP], c3 = p[0], c4 = p[kTP], c5 = p[2 * kTP];
+                uint32_t mb = 0, md = 0;
+#pragma unroll 1
+                for (int y0 = 0; y0 < nr; y0 += 8, p += 8 * kTP) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int n = p[(k + 3) * kTP], e = p[k * kTP + 3], w = p[k * kTP - 3];
+                        const int hi = min(max(n, c0), max(e, w));
+                        const int lo = max(min(n, c0), min(e, w));
+                        mb = __funnelshift_l((uint32_t)(c3 + th - hi), mb, 1);
+                        md = __funnelshift_l((uint32_t)(lo + th - c3), md, 1);
+                        c0 = c1; c1 = c2; c2 = c3; c3 = c4; c4 = c5; c5 = n;
+                    }
                 }
-                if (!inx) { mb = 0; md = 0; }
-                uint32_t any = mb | md;
-                const int cnt = __popc(any);
+                const uint32_t valid = inx ? (0xffffffffu >> (32 - nr)) & (0xffffffffu << (nr - rows)) : 0u;
+                mb &= valid; md &= valid;
+                uint32_t both = mb & md;
+                mb &= ~both; md &= ~both;                  // bright only / dark only / (rare) both
+                // one scan for both queue ends: bright (incl. both) in the low half, dark in the high half
+                const int cnt = (__popc(mb) + __popc(both)) | (__popc(md) << 16);
                 int inc = cnt;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-                int pos = nq + inc - cnt;
-                while (any) {
-                    const int y = __ffs(any) - 1;
-                    any &= any - 1;
-                    // queue entry: x | y << 6 | bright << 12 | dark << 13   (x, y < 64)
-                    queue[pos++] = (uint16_t)(x | ((yb + y) << 6) | (((mb >> y) & 1u) << 12) | (((md >> y) & 1u) << 13));
+                const int excl = inc - cnt;
+                // queue entry: x | y << 6 | both << 12   (x, y < 64); bit b of a mask is row yb + nr - 1 - b
+                const int ebase = x | ((yb + nr - 1) << 6);
+                uint16_t *qb = queue + nb + (excl & 0xffff);
+                while (mb) {
+                    const int b = 31 - __clz(mb);
+                    mb ^= 1u << b;
+                    *qb++ = (uint16_t)(ebase - (b << 6));
                 }
-                nq += __shfl_sync(0xffffffffu, inc, 31);
+                while (both) {
+                    const int b = 31 - __clz(both);
+                    both ^= 1u << b;
+                    *qb++ = (uint16_t)((ebase - (b << 6)) | 0x1000);
+                }
+                uint16_t *qd = queue + qlast - nd - (excl >> 16);
+                while (md) {
+                    const int b = 31 - __clz(md);
+                    md ^= 1u << b;
+                    *qd-- = (uint16_t)(ebase - (b << 6));
+                }
+                const int tot = __shfl_sync(0xffffffffu, inc, 31);
+                nb += tot & 0xffff; nd += tot >> 16;
             }
         }
         __syncwarp();
+        const int nq = nb + nd;
 
-        // ---- phase B: exact score of the candidate polarity ----
+        // ---- phase B: exact score.  The queue is sorted by polarity, so all chunks but one run a single path on the
+        //      raw ring bytes: bright = max over arcs of the arc's minimum - v, dark = v - min over arcs of the arc's
+        //      maximum (cornerScore's two halves; an arc of each polarity cannot coexist, 18 > 16 ring pixels). ----
         for (int i0 = 0; i0 < nq; i0 += 32) {
             const int i = i0 + lane;
             if (i < nq) {
-                const uint32_t ent = queue[i];
+                const bool dark = i >= nb;
+                const uint32_t ent = queue[dark ? qlast - (i - nb) : i];
                 const int x = ent & 63, y = (ent >> 6) & 63;
                 const uint8_t *p = tile + (y + 3) * kTP + (x + 3 + xoff);
                 const int v = p[0];
+                int e[16];
+                e[0] = p[3 * kTP];      e[1] = p[3 * kTP + 1];   e[2] = p[2 * kTP + 2];    e[3] = p[kTP + 3];
+                e[4] = p[3];            e[5] = p[-kTP + 3];      e[6] = p[-2 * kTP + 2];   e[7] = p[-3 * kTP + 1];
+                e[8] = p[-3 * kTP];     e[9] = p[-3 * kTP - 1];  e[10] = p[-2 * kTP - 2];  e[11] = p[-kTP - 3];
+                e[12] = p[-3];          e[13] = p[kTP - 3];      e[14] = p[2 * kTP - 2];   e[15] = p[3 * kTP - 1];
                 int best = -512;
-                // first pass: the lane's own candidate polarity (bright: e = ring - v, dark: e = v - ring), so
-                // lanes of both kinds run the same code; second pass only for the rare both-polarity survivors
-                const int npol = ((ent >> 12) & 1) + ((ent >> 13) & 1);
-#pragma unroll 1
-                for (int pass = 0; pass < npol; ++pass) {
-                    const bool dark = pass == 1 || !(ent & 0x1000u);
-                    const int sgn = dark ? -1 : 1, off = dark ? v : -v;
-                    int e[16];
-                    e[0] = sgn * p[3 * kTP] + off;      e[1] = sgn * p[3 * kTP + 1] + off;  e[2] = sgn * p[2 * kTP + 2] + off;  e[3] = sgn * p[kTP + 3] + off;
-                    e[4] = sgn * p[3] + off;            e[5] = sgn * p[-kTP + 3] + off;     e[6] = sgn * p[-2 * kTP + 2] + off; e[7] = sgn * p[-3 * kTP + 1] + off;
-                    e[8] = sgn * p[-3 * kTP] + off;     e[9] = sgn * p[-3 * kTP - 1] + off; e[10] = sgn * p[-2 * kTP - 2] + off; e[11] = sgn * p[-kTP - 3] + off;
-                    e[12] = sgn * p[-3] + off;          e[13] = sgn * p[kTP - 3] + off;     e[14] = sgn * p[2 * kTP - 2] + off;  e[15] = sgn * p[3 * kTP - 1] + off;
-                    best = max(best, arc9_maxmin(e));
-                }
+                if (!dark) best = arc9_maxmin(e) - v;
+                if (dark || (ent & 0x1000u)) best = max(best, v - arc9_minmax(e));
                 if (best > th)                            // corner at th; cornerScore = best - 1 >= th
                     score[(y + 1) * kSP + (x + 1)] = (uint8_t)(best - 1);
             }
@@ -168,7 +215,7 @@ k_fast_cells(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr,
         // ---- phase C: strict 3x3 NMS inside the cell; walks the same queue (non-corners have score 0) ----
         bool mine_any = false;
         for (int i = lane; i < nq; i += 32) {
-            const uint32_t ent = queue[i];
+            const uint32_t ent = queue[i >= nb ? qlast - (i - nb) : i];
             const int x = ent & 63, y = (ent >> 6) & 63;
             const uint8_t *q = score + (y + 1) * kSP + (x + 1);
             const int s = q[0];
@@ -223,11 +270,20 @@ void launch_fast(const Geo &g, const DevBuffers &b, int nframes, cudaStream_t s)
     sm.off_queue = sm.off_score + up16((mh + 2) * sm.sp);
     sm.off_bm = sm.off_queue + up16(sm.npix_max * 2);
     sm.per_warp = sm.off_bm + up16(mh * 2 * 4);
+    // phase A walks its rows in groups of eight: the rows past the cell are masked off, but they are read, so the
+    // warp's region must reach (mh rounded up to 8) + 6 rows plus the column slack of one more row
+    const int walk = ((mh + 7) / 8 * 8 + 7) * sm.tp;
+    if (sm.per_warp < walk) sm.per_warp = up16(walk);
     const size_t bytes = (size_t)sm.per_warp * kFastWarps;
-    // per-device function attribute; a handful of nanoseconds, so no process-wide caching (one handle per device each)
-    if (bytes > 48 * 1024) cudaFuncSetAttribute(k_fast_cells, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     dim3 grd((g.total_cells + kFastWarps - 1) / kFastWarps, nframes);
-    k_fast_cells<<<grd, kFastThreads, bytes, s>>>(g, b.pyr, b.cell_count, b.cell_slots, b.cell_tab, sm);
+    // per-device function attribute; a handful of nanoseconds, so no process-wide caching (one handle per device each)
+    if (sm.tp == 64) {
+        if (bytes > 48 * 1024) cudaFuncSetAttribute(k_fast_cells<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        k_fast_cells<64><<<grd, kFastThreads, bytes, s>>>(g, b.pyr, b.cell_count, b.cell_slots, b.cell_tab, sm);
+    } else {
+        if (bytes > 48 * 1024) cudaFuncSetAttribute(k_fast_cells<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        k_fast_cells<0><<<grd, kFastThreads, bytes, s>>>(g, b.pyr, b.cell_count, b.cell_slots, b.cell_tab, sm);
+    }
 }
 
 } // namespace orbx
