@@ -3,6 +3,7 @@
 #include "orbx_internal.cuh"
 
 #include <mutex>
+#include <cstdlib>
 
 namespace orbx {
 
@@ -150,34 +151,76 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
 }
 
 constexpr int kDescWarps = 8;
-constexpr int kSlotsPerWarp = 4;          // keypoints handled by one warp (amortises the pattern load)
+constexpr int kSlotsDefault = 4;          // keypoints handled by one warp (amortises the pattern load and the sincos)
 constexpr int kPatchR = 18;               // largest |rotated pattern offset| (18 px)
 constexpr int kPatchRows = 2 * kPatchR + 1;               // 37
 constexpr int kPatchWords = (2 * kPatchR + 1 + 3 + 3) / 4; // 37 px + up to 3 px of alignment slack = 11 words
+constexpr int kStagePasses = (kPatchRows + 1) / 2;        // two patch rows (22 lanes) per cp.async pass
+constexpr int kPatchAlloc = 2 * kStagePasses * kPatchWords; // words per patch buffer (one spare row for the last pass)
+// IC_Angle as dot products: the 31 x 31 window is read as 9 aligned words per row, three rows per warp pass
+// (lane = row-in-pass * 9 + word), and a host-built table holds for every (alignment, pass, lane) the four
+// column weights u and the four row weights v as signed bytes, zero outside the circular patch (umax) and
+// outside the window -- m10 += dp4a(pixels, u-weights), m01 += dp4a(pixels, v-weights).
+constexpr int kMomentPasses = 11;         // 33 rows >= 31
+constexpr int kMomentTabWords = 4 * kMomentPasses * 32 * 2;
 
-// One warp per keypoint.  ncu, round 1: the direct-gather version needed ~20 L1 wavefronts for each
+__device__ __forceinline__ int dp4a_u8s8(uint32_t pix, uint32_t wts, int acc)
+{
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(pix), "r"(wts), "r"(acc));
+    return d;
+}
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
+// blurred 37 x 37 patch (word aligned, 11 words per row) -> shared memory: lanes 0..21 copy two rows per pass
+__device__ __forceinline__ void stage_patch(uint32_t *patch, const uint8_t *blur, const LevelGeom &L, int f, int x, int y, int lane)
+{
+    const int bp = L.blur_pitch;
+    const int xa = (x - kPatchR) & ~3;                    // first staged column (keypoints sit >= 19 px inside)
+    if (lane < 2 * kPatchWords) {
+        const int r = lane >= kPatchWords ? 1 : 0, wx = lane - r * kPatchWords;
+        const uint8_t *src = blur + L.blur_base + (size_t)f * L.blur_frame_stride + (size_t)(y - kPatchR + r) * bp + xa + 4 * wx;
+        uint32_t *dst = patch + lane;
+#pragma unroll
+        for (int it = 0; it < kStagePasses; ++it, src += 2 * bp)
+            if (it < kStagePasses - 1 || r == 0) cp_async4(dst + it * 2 * kPatchWords, src);
+    }
+    cp_async_commit();
+}
+
+// One warp per four keypoints.  ncu, round 1: the direct-gather version needed ~20 L1 wavefronts for each
 // of the 16 scattered descriptor loads per lane; the 37x37 blurred patch is therefore staged in
-// shared memory with coalesced word loads and gathered from there (<= 4-way bank conflicts).
-__global__ void __launch_bounds__(kDescWarps * 32, 5)
+// shared memory (cp.async, double buffered: the next keypoint's patch lands while this one's descriptor is
+// computed) and gathered from there (<= 4-way bank conflicts).  Three phases per warp: (1) the moments of its
+// four keypoints, (2) fastAtan2 + the double-precision sincos ONCE, lane s working on keypoint s, (3) per keypoint
+// the rotated BRIEF tests and the output row.
+template <int MINB, int kSlotsPerWarp>
+__global__ void __launch_bounds__(kDescWarps * 32, MINB)
 k_describe(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, const uint8_t *__restrict__ blur,
            const uint32_t *__restrict__ kept, const int *__restrict__ nkept,
            orbx_keypoint *__restrict__ out_kps, uint8_t *__restrict__ out_desc, int *__restrict__ out_counts,
-           const uint32_t *__restrict__ pattern_words)
+           const uint32_t *__restrict__ pattern_words, const uint2 *__restrict__ moment_tab)
 {
-    __shared__ uint32_t patch_all[kDescWarps][kPatchRows * kPatchWords];
+    __shared__ uint32_t patch_all[kDescWarps][2][kPatchAlloc];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int f = blockIdx.y + g.frame0;
-    uint32_t *patch = patch_all[warp];
     // lane i owns descriptor byte i = pattern points 16i .. 16i+15.  The pattern lives in shared memory as floats, one
     // float4 (x0, y0, x1, y1 of a test pair) per (pair k, lane): consecutive lanes read consecutive 16 bytes.  Held in
     // registers (8 packed words + the floats the compiler hoisted out of the slot loop) it cost 96 bytes of spills.
     __shared__ float4 pat[8][32];
+    __shared__ uint2 mtab[4 * kMomentPasses * 32];          // IC_Angle weights, see kMomentPasses
     if (threadIdx.x < 256) {
         const int k = threadIdx.x >> 5, l = threadIdx.x & 31;
         const uint32_t w = __ldg(pattern_words + l * 8 + k);
         pat[k][l] = make_float4((float)(int)(signed char)(w), (float)(int)(signed char)(w >> 8),
                                 (float)(int)(signed char)(w >> 16), (float)(int)(signed char)(w >> 24));
     }
+    for (int i = threadIdx.x; i < 4 * kMomentPasses * 32; i += kDescWarps * 32) mtab[i] = __ldg(moment_tab + i);
     __syncthreads();
     // per-level keypoint counts -> inclusive prefix in lanes 0..nlevels-1 (level-major concatenation, :1036-1063)
     const int myc = lane < g.nlevels ? nkept[f * g.nlevels + lane] : 0;
@@ -188,62 +231,92 @@ k_describe(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, const
     if (blockIdx.x == 0 && threadIdx.x == 0) out_counts[f] = total;
     const uint32_t lvl_mask = g.nlevels >= 32 ? 0xffffffffu : ((1u << g.nlevels) - 1u);
 
-    const int slot0 = (blockIdx.x * kDescWarps + warp) * kSlotsPerWarp;
-#pragma unroll 1
-    for (int si = 0; si < kSlotsPerWarp; ++si) {
-        const int slot = slot0 + si;                          // output row inside the frame
-        if (slot >= total) return;
-        const int level = __popc(__ballot_sync(0xffffffffu, slot >= incl) & lvl_mask);
-        const int first = __shfl_sync(0xffffffffu, incl - myc, level);
-        const LevelGeom &L = g.lv[level];
-        const uint32_t key = kept[(size_t)f * g.kept_total + L.kept_base + (slot - first)];
-        const int x = cand_x(key) + kMinBorder, y = cand_y(key) + kMinBorder;   // :801-802
+    const int slot0 = (blockIdx.x * kDescWarps + warp) * kSlotsPerWarp;   // first output row of this warp inside the frame
+    const int nslot = min(kSlotsPerWarp, total - slot0);
+    if (nslot <= 0) return;
 
-        // ---- stage the blurred 37x37 patch (word aligned) ----
-        const int bp = L.blur_pitch;
-        const int xa = (x - kPatchR) & ~3;                    // first staged column (keypoints sit >= 19 px inside)
-        const uint8_t *bsrc = blur + L.blur_base + (size_t)f * L.blur_frame_stride + (size_t)(y - kPatchR) * bp + xa;
-        __syncwarp();
-#pragma unroll
-        for (int it = 0; it < (kPatchRows * kPatchWords + 31) / 32; ++it) {
-            const int idx = it * 32 + lane;
-            if (idx < kPatchRows * kPatchWords) {
-                const int r = idx / kPatchWords, wx = idx - r * kPatchWords;
-                patch[idx] = __ldg(reinterpret_cast<const uint32_t *>(bsrc + (size_t)r * bp) + wx);
-            }
+    // lane s < nslot looks up keypoint s: its level from the prefix sums, then its packed key (one load latency for all four)
+    uint32_t my_key = 0; int my_level = 0;
+    {
+        const int slot = slot0 + min(lane, nslot - 1);
+        int first = 0;
+        for (int l = 0; l < g.nlevels; ++l) {
+            const int e = __shfl_sync(0xffffffffu, incl, l);
+            if (slot >= e) { my_level = l + 1; first = e; }
         }
+        my_key = __ldg(kept + (size_t)f * g.kept_total + g.lv[my_level].kept_base + (slot - first));
+    }
 
-        // ---- IC_Angle on the un-blurred level (:27-54): lane = column u, rows walked in +/- pairs ----
+    // ---- phase 1: IC_Angle moments on the un-blurred level (:27-54) for the warp's keypoints; lane s keeps keypoint s.
+    //      The eleven pixel words of keypoint s+1 are loaded before the dot products of keypoint s. ----
+    const int mrow = lane / 9, mword = lane - mrow * 9;    // lanes 27..31 read a fourth row with zero weights
+    float my_m01 = 0.f, my_m10 = 0.f;
+    uint32_t px[kMomentPasses], nx[kMomentPasses];
+    int al = 0, nal = 0;
+    auto load_window = [&](int si, uint32_t (&dst)[kMomentPasses], int &al_out, bool stage) {
+        const uint32_t key = __shfl_sync(0xffffffffu, my_key, si);
+        const int level = __shfl_sync(0xffffffffu, my_level, si);
+        const LevelGeom &L = g.lv[level];
+        const int x = cand_x(key) + kMinBorder, y = cand_y(key) + kMinBorder;   // :801-802
+        if (stage) stage_patch(patch_all[warp][0], blur, L, f, x, y, lane);
         const int pitch = L.pitch;
-        const uint8_t *ctr = pyr + L.base + (size_t)f * L.frame_stride + (size_t)(kPadY + y) * pitch + kPadX + x;
-        int m10 = 0, m01 = 0;
-        const int u = lane - kHalfPatch;
-        const int au = u < 0 ? -u : u;
-        if (lane < 2 * kHalfPatch + 1) {
-            const uint8_t *pu = ctr + u, *pd = ctr + u;
-            int colsum = pu[0];
+        al_out = (x - kHalfPatch + kPadX) & 3;             // bytes between the aligned first word and column x-15
+        const uint8_t *src = pyr + L.base + (size_t)f * L.frame_stride + (size_t)(kPadY + y - kHalfPatch + mrow) * pitch
+                             + (kPadX + x - kHalfPatch - al_out) + 4 * mword;
 #pragma unroll
-            for (int v = 1; v <= kHalfPatch; ++v) {
-                pu -= pitch; pd += pitch;
-                if (au <= g.umax[v]) {
-                    const int a_ = pd[0], b_ = pu[0];          // val_plus, val_minus
-                    colsum += a_ + b_; m01 += v * (a_ - b_);
-                }
-            }
-            m10 = u * colsum;
+        for (int it = 0; it < kMomentPasses; ++it, src += 3 * pitch) dst[it] = __ldg(reinterpret_cast<const uint32_t *>(src));
+    };
+    load_window(0, px, al, true);
+#pragma unroll 1
+    for (int si = 0; si < nslot; ++si) {
+        if (si + 1 < nslot) load_window(si + 1, nx, nal, false);
+        const uint2 *tab = mtab + al * (kMomentPasses * 32) + lane;
+        int m10 = 0, m01 = 0;
+#pragma unroll
+        for (int it = 0; it < kMomentPasses; ++it) {
+            const uint2 wt = tab[it * 32];
+            m10 = dp4a_u8s8(px[it], wt.x, m10);
+            m01 = dp4a_u8s8(px[it], wt.y, m01);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { m10 += __shfl_xor_sync(0xffffffffu, m10, o); m01 += __shfl_xor_sync(0xffffffffu, m01, o); }
-        const float angle = fast_atan2_deg((float)m01, (float)m10);
+        if (lane == si) { my_m01 = (float)m01; my_m10 = (float)m10; }
+#pragma unroll
+        for (int it = 0; it < kMomentPasses; ++it) px[it] = nx[it];
+        al = nal;
+    }
 
-        // ---- rotated BRIEF: lane i produces descriptor byte i from its 16 pattern points ----
+    // ---- phase 2: angle and rotation of keypoint s in lane s ----
+    const float my_angle = fast_atan2_deg(my_m01, my_m10);
+    float my_a, my_b;
+    {
         const float factorPI = (float)(3.14159265358979323846 / (double)180.f);
-        const float ang = __fmul_rn(angle, factorPI);
+        const float ang = __fmul_rn(my_angle, factorPI);
         double sd, cd;
         sincos((double)ang, &sd, &cd);                       // one range reduction for both
-        const float a = (float)cd, b = (float)sd;
+        my_a = (float)cd; my_b = (float)sd;
+    }
+
+    // ---- phase 3: rotated BRIEF, lane i produces descriptor byte i from its 16 pattern points ----
+#pragma unroll 1
+    for (int si = 0; si < nslot; ++si) {
+        const int slot = slot0 + si;
+        const uint32_t key = __shfl_sync(0xffffffffu, my_key, si);
+        const int level = __shfl_sync(0xffffffffu, my_level, si);
+        const float a = __shfl_sync(0xffffffffu, my_a, si), b = __shfl_sync(0xffffffffu, my_b, si);
+        const int x = cand_x(key) + kMinBorder, y = cand_y(key) + kMinBorder;
+        const LevelGeom &L = g.lv[level];
+        if (si + 1 < nslot) {                                // next keypoint's patch into the other buffer
+            const uint32_t nkey = __shfl_sync(0xffffffffu, my_key, si + 1);
+            const int nlevel = __shfl_sync(0xffffffffu, my_level, si + 1);
+            stage_patch(patch_all[warp][(si + 1) & 1], blur, g.lv[nlevel], f, cand_x(nkey) + kMinBorder, cand_y(nkey) + kMinBorder, lane);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
         __syncwarp();
-        const uint8_t *pc = reinterpret_cast<const uint8_t *>(patch) + kPatchR * (kPatchWords * 4) + (x - xa);   // patch centre
+        const int xa = (x - kPatchR) & ~3;
+        const uint8_t *pc = reinterpret_cast<const uint8_t *>(patch_all[warp][si & 1]) + kPatchR * (kPatchWords * 4) + (x - xa);   // patch centre
         int val = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -258,40 +331,76 @@ k_describe(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, const
         }
         out_desc[((size_t)f * g.capacity + slot) * 32 + lane] = (uint8_t)val;
 
-        if (lane == 0) {
+        if (lane == si) {
             orbx_keypoint kp;
             kp.x = (float)x; kp.y = (float)y;
             if (level != 0) { kp.x = __fmul_rn(kp.x, L.scale); kp.y = __fmul_rn(kp.y, L.scale); }   // :1055-1061
             kp.size = (float)L.patch_size;
-            kp.angle = angle;
+            kp.angle = my_angle;
             kp.response = (float)cand_score(key);
             kp.octave = level;
             kp.class_id = -1;
             out_kps[(size_t)f * g.capacity + slot] = kp;
         }
+        __syncwarp();                                        // this buffer is the staging target of the next iteration
     }
 }
 
-static uint32_t *g_pattern_dev[64] = { nullptr };   // per device copy of the pattern as packed words
+struct DescribeTables { uint32_t *pattern; uint2 *moments; };
+static DescribeTables g_desc_tab[64] = {};   // per device: the pattern as packed words, the IC_Angle weight table
 
 void launch_describe(const Geo &g, const DevBuffers &b, int nframes, orbx_keypoint *d_kps, uint8_t *d_desc, int *d_counts, cudaStream_t s)
 {
     int dev = 0;
     cudaGetDevice(&dev);
+    if (dev >= 64) dev = 63;
     static std::mutex pattern_mutex;                      // handles are per-thread objects; this table is process-wide
     std::lock_guard<std::mutex> lock(pattern_mutex);
-    if (dev < 64 && !g_pattern_dev[dev]) {
+    if (!g_desc_tab[dev].pattern) {
         static const signed char h_pattern[1024] = {
 #include "orb_pattern_31.inc"
         };
         uint32_t *p = nullptr;
         cudaMalloc(&p, 1024);
         cudaMemcpy(p, h_pattern, 1024, cudaMemcpyHostToDevice);
-        g_pattern_dev[dev] = p;
+        // IC_Angle weights: entry [al][pass][lane] = {u weights, v weights} of the word at row 3*pass + lane/9,
+        // word lane%9 of the window whose first byte is column -15 - al (umax is fixed by HALF_PATCH_SIZE = 15)
+        static uint32_t h_tab[kMomentTabWords];
+        for (int al = 0; al < 4; ++al)
+            for (int it = 0; it < kMomentPasses; ++it)
+                for (int l = 0; l < 32; ++l) {
+                    const int r = 3 * it + l / 9, w = l % 9, v = r - kHalfPatch;
+                    uint32_t wu = 0, wv = 0;
+                    for (int j = 0; j < 4; ++j) {
+                        const int u = 4 * w + j - al - kHalfPatch;
+                        const int av = v < 0 ? -v : v, au = u < 0 ? -u : u;
+                        if (l < 27 && av <= kHalfPatch && au <= g.umax[av]) {
+                            wu |= (uint32_t)(uint8_t)(signed char)u << (8 * j);
+                            wv |= (uint32_t)(uint8_t)(signed char)v << (8 * j);
+                        }
+                    }
+                    h_tab[((al * kMomentPasses + it) * 32 + l) * 2] = wu;
+                    h_tab[((al * kMomentPasses + it) * 32 + l) * 2 + 1] = wv;
+                }
+        uint2 *m = nullptr;
+        cudaMalloc(&m, sizeof(h_tab));
+        cudaMemcpy(m, h_tab, sizeof(h_tab), cudaMemcpyHostToDevice);
+        g_desc_tab[dev].pattern = p; g_desc_tab[dev].moments = m;
     }
-    const int per_block = kDescWarps * kSlotsPerWarp;
+    static int minb = getenv("ORBX_DESC_MINB") ? atoi(getenv("ORBX_DESC_MINB")) : 4;
+    static int carve = getenv("ORBX_DESC_CARVE") ? atoi(getenv("ORBX_DESC_CARVE")) : -1;
+    static int slots = getenv("ORBX_DESC_SLOTS") ? atoi(getenv("ORBX_DESC_SLOTS")) : 8;
+    const int per_block = kDescWarps * slots;
     dim3 grd((g.capacity + per_block - 1) / per_block, nframes);
-    k_describe<<<grd, kDescWarps * 32, 0, s>>>(g, b.pyr, b.blur, b.kept, b.nkept, d_kps, d_desc, d_counts, g_pattern_dev[dev]);
+#define ORBX_DESC_LAUNCH(MB, SL) do { \
+        if (carve >= 0) cudaFuncSetAttribute(k_describe<MB, SL>, cudaFuncAttributePreferredSharedMemoryCarveout, carve); \
+        k_describe<MB, SL><<<grd, kDescWarps * 32, 0, s>>>(g, b.pyr, b.blur, b.kept, b.nkept, d_kps, d_desc, d_counts, g_desc_tab[dev].pattern, g_desc_tab[dev].moments); } while (0)
+    if (minb == 4 && slots == 4) ORBX_DESC_LAUNCH(4, 4);
+    else if (minb == 4 && slots == 8) ORBX_DESC_LAUNCH(4, 8);
+    else if (minb == 4 && slots == 16) ORBX_DESC_LAUNCH(4, 16);
+    else if (slots == 8) ORBX_DESC_LAUNCH(5, 8);
+    else if (slots == 16) ORBX_DESC_LAUNCH(5, 16);
+    else ORBX_DESC_LAUNCH(5, 4);
 }
 
 // ---------------------------------------------------------------------------------------------
