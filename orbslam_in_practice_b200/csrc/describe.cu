@@ -3,7 +3,6 @@
 #include "orbx_internal.cuh"
 
 #include <mutex>
-#include <cstdlib>
 
 namespace orbx {
 
@@ -151,7 +150,7 @@ __device__ __forceinline__ float fast_atan2_deg(float y, float x)
 }
 
 constexpr int kDescWarps = 8;
-constexpr int kSlotsDefault = 4;          // keypoints handled by one warp (amortises the pattern load and the sincos)
+constexpr int kDescSlots = 8;             // keypoints handled by one warp (amortises the pattern load and the sincos)
 constexpr int kPatchR = 18;               // largest |rotated pattern offset| (18 px)
 constexpr int kPatchRows = 2 * kPatchR + 1;               // 37
 constexpr int kPatchWords = (2 * kPatchR + 1 + 3 + 3) / 4; // 37 px + up to 3 px of alignment slack = 11 words
@@ -387,20 +386,14 @@ void launch_describe(const Geo &g, const DevBuffers &b, int nframes, orbx_keypoi
         cudaMemcpy(m, h_tab, sizeof(h_tab), cudaMemcpyHostToDevice);
         g_desc_tab[dev].pattern = p; g_desc_tab[dev].moments = m;
     }
-    static int minb = getenv("ORBX_DESC_MINB") ? atoi(getenv("ORBX_DESC_MINB")) : 4;
-    static int carve = getenv("ORBX_DESC_CARVE") ? atoi(getenv("ORBX_DESC_CARVE")) : -1;
-    static int slots = getenv("ORBX_DESC_SLOTS") ? atoi(getenv("ORBX_DESC_SLOTS")) : 8;
-    const int per_block = kDescWarps * slots;
+    const int per_block = kDescWarps * kDescSlots;
     dim3 grd((g.capacity + per_block - 1) / per_block, nframes);
-#define ORBX_DESC_LAUNCH(MB, SL) do { \
-        if (carve >= 0) cudaFuncSetAttribute(k_describe<MB, SL>, cudaFuncAttributePreferredSharedMemoryCarveout, carve); \
-        k_describe<MB, SL><<<grd, kDescWarps * 32, 0, s>>>(g, b.pyr, b.blur, b.kept, b.nkept, d_kps, d_desc, d_counts, g_desc_tab[dev].pattern, g_desc_tab[dev].moments); } while (0)
-    if (minb == 4 && slots == 4) ORBX_DESC_LAUNCH(4, 4);
-    else if (minb == 4 && slots == 8) ORBX_DESC_LAUNCH(4, 8);
-    else if (minb == 4 && slots == 16) ORBX_DESC_LAUNCH(4, 16);
-    else if (slots == 8) ORBX_DESC_LAUNCH(5, 8);
-    else if (slots == 16) ORBX_DESC_LAUNCH(5, 16);
-    else ORBX_DESC_LAUNCH(5, 4);
+    // measured on a B200 (256 VGA frames): the kernel is bound by the L1 data pipe, and a small L1 (the default carve-out
+    // maximises shared memory: 28 KB of L1 left) costs 30 %; 164 KB of shared memory = 4 resident blocks and 92 KB of L1.
+    // 48 registers (the 5-block launch bound) leave room for the other stream's kernels on the same SM.
+    static bool configured[64] = {};
+    if (!configured[dev]) { cudaFuncSetAttribute(k_describe<5, kDescSlots>, cudaFuncAttributePreferredSharedMemoryCarveout, 72); configured[dev] = true; }
+    k_describe<5, kDescSlots><<<grd, kDescWarps * 32, 0, s>>>(g, b.pyr, b.blur, b.kept, b.nkept, d_kps, d_desc, d_counts, g_desc_tab[dev].pattern, g_desc_tab[dev].moments);
 }
 
 // ---------------------------------------------------------------------------------------------
