@@ -15,7 +15,7 @@
 
 namespace orbx {
 
-constexpr int kDefaultCsa = 2;                // carry-save stages in front of the POPCs (see hamming_row)
+constexpr int kDefaultCsa = 13;               // carry-save stages in front of the POPCs (see hamming_row / hamming_key; 13 = explicit 3-stage form)
 constexpr int kKnnThreads = 256;
 constexpr int kQPT = 4;                       // queries per thread
 constexpr int kQPB = kKnnThreads * kQPT;      // queries per block
@@ -51,6 +51,35 @@ __device__ __forceinline__ int hamming_row(const uint32_t (&q)[8], const uint4 d
         return __popc(s2) + __popc(x7) + 2 * (__popc(c0) + __popc(c1) + __popc(c2));
     const uint32_t s3 = c0 ^ c1 ^ c2, c3 = (c0 & c1) | (c2 & (c0 | c1));
     return __popc(s2) + __popc(x7) + 2 * __popc(s3) + 4 * __popc(c3);
+}
+
+// Explicit-PTX form of the 3- and 4-stage variants (CSA 13 / 14).  Left to itself the compiler folds the eight XORs into
+// the carry-save LOP3s and ends up with ~17 logic instructions per pair instead of 8 + 6, which made the 3-stage form
+// ALU-pipe bound (SASS).  Here every XOR / sum / majority is one lop3 the compiler cannot re-associate, and the
+// weighted sum of the POPCs is folded into the packed key with one mad each (FMA pipe): key = row + 2^22 * distance.
+__device__ __forceinline__ uint32_t lop_xor(uint32_t a, uint32_t b) { uint32_t r; asm volatile("lop3.b32 %0, %1, %2, 0, 0x3c;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t lop_sum(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ uint32_t lop_maj(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("lop3.b32 %0, %1, %2, %3, 0xe8;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+__device__ __forceinline__ uint32_t mad_u32(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+template <int CSA>
+__device__ __forceinline__ uint32_t hamming_key(const uint32_t (&q)[8], const uint4 d0, const uint4 d1, uint32_t row)
+{
+    const uint32_t x0 = lop_xor(q[0], d0.x), x1 = lop_xor(q[1], d0.y), x2 = lop_xor(q[2], d0.z), x3 = lop_xor(q[3], d0.w);
+    const uint32_t x4 = lop_xor(q[4], d1.x), x5 = lop_xor(q[5], d1.y), x6 = lop_xor(q[6], d1.z), x7 = lop_xor(q[7], d1.w);
+    const uint32_t s0 = lop_sum(x0, x1, x2), c0 = lop_maj(x0, x1, x2);
+    const uint32_t s1 = lop_sum(x3, x4, x5), c1 = lop_maj(x3, x4, x5);
+    const uint32_t s2 = lop_sum(s0, s1, x6), c2 = lop_maj(s0, s1, x6);
+    constexpr uint32_t W1 = 1u << kIdxBits, W2 = 2u << kIdxBits, W4 = 4u << kIdxBits;
+    uint32_t key = mad_u32(__popc(s2), W1, row);
+    key = mad_u32(__popc(x7), W1, key);
+    if (CSA == 13) {
+        key = mad_u32(__popc(c0), W2, key);
+        key = mad_u32(__popc(c1), W2, key);
+        return mad_u32(__popc(c2), W2, key);
+    }
+    const uint32_t s3 = lop_sum(c0, c1, c2), c3 = lop_maj(c0, c1, c2);
+    key = mad_u32(__popc(s3), W2, key);
+    return mad_u32(__popc(c3), W4, key);
 }
 
 template <int CSA>
@@ -98,16 +127,39 @@ k_knn2(const uint4 *__restrict__ query, int nq, const uint4 *__restrict__ db, in
         __syncthreads();
         const int trows = min(rows - t * kTileRows, kTileRows);
         const uint32_t rbase = (uint32_t)(t * kTileRows);
-#pragma unroll 2
-        for (int r = 0; r < trows; ++r) {
-            const uint4 d0 = tile[cur][2 * r], d1 = tile[cur][2 * r + 1];
+        if (CSA >= 10) {
+            // two rows per step: five min/max fold both keys into the running best-2 (six when taken one at a time);
+            // a padding row past the tile's end gets the no-key sentinel
+            for (int r = 0; r < trows; r += 2) {
+                uint32_t ka[kQPT];
+                {
+                    const uint4 d0 = tile[cur][2 * r], d1 = tile[cur][2 * r + 1];
 #pragma unroll
-            for (int i = 0; i < kQPT; ++i) {
-                const int dist = hamming_row<CSA>(q[i], d0, d1);
-                const uint32_t key = ((uint32_t)dist << kIdxBits) | (rbase + (uint32_t)r);
-                const uint32_t hi = max(k1[i], key);
-                k1[i] = min(k1[i], key);
-                k2[i] = min(k2[i], hi);
+                    for (int i = 0; i < kQPT; ++i) ka[i] = hamming_key<CSA>(q[i], d0, d1, rbase + (uint32_t)r);
+                }
+                const uint4 d0 = tile[cur][2 * r + 2], d1 = tile[cur][2 * r + 3];
+                const bool two = r + 1 < trows;
+#pragma unroll
+                for (int i = 0; i < kQPT; ++i) {
+                    const uint32_t kb = two ? hamming_key<CSA>(q[i], d0, d1, rbase + (uint32_t)r + 1u) : kNoKey;
+                    const uint32_t lo = min(ka[i], kb), hi = max(ka[i], kb);
+                    const uint32_t t1 = max(k1[i], lo);
+                    k1[i] = min(k1[i], lo);
+                    k2[i] = min(min(k2[i], t1), hi);
+                }
+            }
+        } else {
+#pragma unroll 2
+            for (int r = 0; r < trows; ++r) {
+                const uint4 d0 = tile[cur][2 * r], d1 = tile[cur][2 * r + 1];
+#pragma unroll
+                for (int i = 0; i < kQPT; ++i) {
+                    const int dist = hamming_row<CSA>(q[i], d0, d1);
+                    const uint32_t key = ((uint32_t)dist << kIdxBits) | (rbase + (uint32_t)r);
+                    const uint32_t hi = max(k1[i], key);
+                    k1[i] = min(k1[i], key);
+                    k2[i] = min(k2[i], hi);
+                }
             }
         }
         __syncthreads();
@@ -305,6 +357,8 @@ void launch_knn2(const uint8_t *d_query, int nq, const uint8_t *d_db, int ndb, i
     if (csa == 0) k_knn2<0><<<grd, kKnnThreads, 0, s>>>((const uint4 *)d_query, nq, (const uint4 *)d_db, ndb, seg_rows, partial);
     else if (csa == 2) k_knn2<2><<<grd, kKnnThreads, 0, s>>>((const uint4 *)d_query, nq, (const uint4 *)d_db, ndb, seg_rows, partial);
     else if (csa == 3) k_knn2<3><<<grd, kKnnThreads, 0, s>>>((const uint4 *)d_query, nq, (const uint4 *)d_db, ndb, seg_rows, partial);
+    else if (csa == 13) k_knn2<13><<<grd, kKnnThreads, 0, s>>>((const uint4 *)d_query, nq, (const uint4 *)d_db, ndb, seg_rows, partial);
+    else if (csa == 14) k_knn2<14><<<grd, kKnnThreads, 0, s>>>((const uint4 *)d_query, nq, (const uint4 *)d_db, ndb, seg_rows, partial);
     else k_knn2<4><<<grd, kKnnThreads, 0, s>>>((const uint4 *)d_query, nq, (const uint4 *)d_db, ndb, seg_rows, partial);
     if (ev) cudaEventRecord(ev[1], s);
     k_knn2_merge<<<(nq + 255) / 256, 256, 0, s>>>(partial, nq, nseg, seg_rows, index_base, d1, idx1, d2);
