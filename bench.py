@@ -41,6 +41,25 @@ WORKLOAD_DESC = ""
 STAGES = ["level0", "resize", "fast", "octree", "blur", "describe"]
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner when the box
+    sets NCCL_DEBUG), so fd 1 is pointed at stderr for the whole run and the JSON line goes to the saved descriptor."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, data)
+
+
 def level_sizes():
     inv = [1.0]
     s = np.float32(1.0)
@@ -198,7 +217,7 @@ def run_reference(args):
                        "note": "each step is a bounded sample of this workload on the host cores (see cpu_baseline.sample)"},
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------
@@ -469,7 +488,7 @@ def run_ours(args):
             line["search_init"] = search_init
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -571,6 +590,7 @@ def main():
                     help="vga = the headline config (default); kitti / 4k = the other BASELINE configs (run by hand, results in profiles/)")
     ap.add_argument("--frames", type=int, default=0, help="override frames per GPU")
     args = ap.parse_args()
+    claim_stdout()
     global W, H, NFEAT, BATCH, ALGO_BYTES_PER_FRAME, WORKLOAD_DESC
     W, H, NFEAT, BATCH, WORKLOAD_DESC = WORKLOADS[args.workload]
     if args.frames:
