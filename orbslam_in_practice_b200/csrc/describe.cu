@@ -31,6 +31,10 @@ __device__ __forceinline__ int reflect101d(int i, int n)
 // ---------------------------------------------------------------------------------------------
 constexpr int kBlurRows = 35;                 // a multiple of the 7-row unrolled window: no rows computed and thrown away
 constexpr int kBlurWarps = 4;
+#ifndef ORBX_BLUR_PREFETCH
+#define ORBX_BLUR_PREFETCH 4
+#endif
+constexpr int kBlurPrefetch = ORBX_BLUR_PREFETCH;   // source rows in flight per lane ahead of the one being consumed
 struct BlurRows { int first[ORBX_MAX_LEVELS + 1]; };   // first blockIdx.y of every level
 // DP2A weight words (low byte x low 16-bit lane, next byte x high lane).  Passed as a kernel parameter so that they
 // are constant-bank operands; as literals the compiler re-materialised all of them in registers in every row iteration.
@@ -70,8 +74,9 @@ k_blur(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, uint8_t *
     }
     // two-deep software prefetch of the next source rows (ncu: 53 % of the stall samples sat on this load).
     // Rows up to h+3 are read; the buffer has 19 rows below the level, so the reads stay inside it.
-    uint32_t wn0 = __ldg(reinterpret_cast<const uint32_t *>(rp)); rp += L.pitch;
-    uint32_t wn1 = __ldg(reinterpret_cast<const uint32_t *>(rp)); rp += L.pitch;
+    uint32_t wn[kBlurPrefetch];
+#pragma unroll
+    for (int i = 0; i < kBlurPrefetch; ++i) { wn[i] = __ldg(reinterpret_cast<const uint32_t *>(rp)); rp += L.pitch; }
     uint8_t *dp = dst + (size_t)y0 * L.blur_pitch;
     for (int yb = y0; yb < y1; yb += 7) {
 #pragma unroll
@@ -81,9 +86,10 @@ k_blur(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, uint8_t *
             // stored, which keeps the shuffles convergent (the compiler bracketed them with WARPSYNC otherwise)
             {
                 // window slot (j + 6) % 7 receives source row y + 3; rows y-3 .. y+3 are slots j .. j+6 (mod 7)
-                const uint32_t w = wn0;
-                wn0 = wn1;
-                wn1 = __ldg(reinterpret_cast<const uint32_t *>(rp)); rp += L.pitch;
+                const uint32_t w = wn[0];
+#pragma unroll
+                for (int i = 0; i + 1 < kBlurPrefetch; ++i) wn[i] = wn[i + 1];
+                wn[kBlurPrefetch - 1] = __ldg(reinterpret_cast<const uint32_t *>(rp)); rp += L.pitch;
                 lo[(j + 6) % 7] = w & 0x00ff00ffu; hi[(j + 6) % 7] = (w >> 8) & 0x00ff00ffu;
                 // vertical 7-tap, two 16-bit lanes per register: V_lo = (V[4c], V[4c+2]), V_hi = (V[4c+1], V[4c+3])
                 const uint32_t vlo = K0 * (lo[j % 7] + lo[(j + 6) % 7]) + K1 * (lo[(j + 1) % 7] + lo[(j + 5) % 7]) +
