@@ -213,6 +213,11 @@ k_resize_gather(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr_s
 // four pixels instead of ~50.  Border pixels need no special case: the padded tables hold their reflected
 // source coordinates and PRMT does not care about the order of the bytes it picks.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+
 __global__ void __launch_bounds__(128, 8)
 k_resize(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr_src, uint8_t *__restrict__ pyr_dst,
          const int2 *__restrict__ tables, int level)
@@ -246,7 +251,7 @@ k_resize(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr_src, uin
         const uint32_t inv = __float2uint_rz(__fdividef(4294967296.f, (float)nvec)) + 1024u;
         for (int i = threadIdx.x; i < total; i += blockDim.x) {
             const int row = nvec == 1 ? i : (int)__umulhi((uint32_t)i, inv), v = i - row * nvec;
-            *reinterpret_cast<uint4 *>(rs_tile + row * TP + v * 16) = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)row * S.pitch) + v);
+            cp_async16(rs_tile + row * TP + v * 16, reinterpret_cast<const uint4 *>(src + (size_t)row * S.pitch) + v);
         }
     }
     // horizontal parameters of the thread's four pixels (padded table: no reflect / clamp here)
@@ -265,6 +270,7 @@ k_resize(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr_src, uin
             psel[j] = da | ((da + 1) << 4) | (db << 8) | ((db + 1) << 12);
         }
     }
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
     __syncthreads();
     if (!active) return;
 
