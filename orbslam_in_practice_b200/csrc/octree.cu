@@ -127,9 +127,11 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
         }
         if (tid == 0) { S.n = carry; ncand_out[f * g.nlevels + level] = carry; }
         __syncthreads();
-        for (int c = warp; c < nCells; c += kOctWarps) {
+        // eight lanes per cell (a cell holds ~4 candidates): four cells per warp pass instead of one, so a warp walks
+        // a quarter as many dependent count -> slot load chains
+        for (int c = tid >> 3; c < nCells; c += kOctThreads >> 3) {
             const int cnt = ccount[c], off = celloff[c];
-            for (int i = lane; i < cnt; i += 32) kB[off + i] = cslots[(size_t)c * L.cell_cap + i];
+            for (int i = tid & 7; i < cnt; i += 8) kB[off + i] = cslots[(size_t)c * L.cell_cap + i];
         }
         __syncthreads();
     }
