@@ -15,7 +15,7 @@
 
 namespace orbx {
 
-constexpr int kDefaultCsa = 13;               // carry-save stages in front of the POPCs (see hamming_row / hamming_key; 13 = explicit 3-stage form)
+constexpr int kDefaultCsa = 15;               // carry-save form (see hamming_row / hamming_key): 13 / 14 = explicit 3- / 4-stage, 15 = alternating rows
 constexpr int kKnnThreads = 256;
 constexpr int kQPT = 4;                       // queries per thread
 constexpr int kQPB = kKnnThreads * kQPT;      // queries per block
@@ -135,13 +135,13 @@ k_knn2(const uint4 *__restrict__ query, int nq, const uint4 *__restrict__ db, in
                 {
                     const uint4 d0 = tile[cur][2 * r], d1 = tile[cur][2 * r + 1];
 #pragma unroll
-                    for (int i = 0; i < kQPT; ++i) ka[i] = hamming_key<CSA>(q[i], d0, d1, rbase + (uint32_t)r);
+                    for (int i = 0; i < kQPT; ++i) ka[i] = hamming_key<CSA == 15 ? 13 : CSA>(q[i], d0, d1, rbase + (uint32_t)r);
                 }
                 const uint4 d0 = tile[cur][2 * r + 2], d1 = tile[cur][2 * r + 3];
                 const bool two = r + 1 < trows;
 #pragma unroll
                 for (int i = 0; i < kQPT; ++i) {
-                    const uint32_t kb = two ? hamming_key<CSA>(q[i], d0, d1, rbase + (uint32_t)r + 1u) : kNoKey;
+                    const uint32_t kb = two ? hamming_key<CSA == 15 ? 14 : CSA>(q[i], d0, d1, rbase + (uint32_t)r + 1u) : kNoKey;
                     const uint32_t lo = min(ka[i], kb), hi = max(ka[i], kb);
                     const uint32_t t1 = max(k1[i], lo);
                     k1[i] = min(k1[i], lo);
@@ -358,6 +358,7 @@ void launch_knn2(const uint8_t *d_query, int nq, const uint8_t *d_db, int ndb, i
     else if (csa == 2) k_knn2<2><<<grd, kKnnThreads, 0, s>>>((const uint4 *)d_query, nq, (const uint4 *)d_db, ndb, seg_rows, partial);
     else if (csa == 3) k_knn2<3><<<grd, kKnnThreads, 0, s>>>((const uint4 *)d_query, nq, (const uint4 *)d_db, ndb, seg_rows, partial);
     else if (csa == 13) k_knn2<13><<<grd, kKnnThreads, 0, s>>>((const uint4 *)d_query, nq, (const uint4 *)d_db, ndb, seg_rows, partial);
+    else if (csa == 15) k_knn2<15><<<grd, kKnnThreads, 0, s>>>((const uint4 *)d_query, nq, (const uint4 *)d_db, ndb, seg_rows, partial);
     else if (csa == 14) k_knn2<14><<<grd, kKnnThreads, 0, s>>>((const uint4 *)d_query, nq, (const uint4 *)d_db, ndb, seg_rows, partial);
     else k_knn2<4><<<grd, kKnnThreads, 0, s>>>((const uint4 *)d_query, nq, (const uint4 *)d_db, ndb, seg_rows, partial);
     if (ev) cudaEventRecord(ev[1], s);

@@ -17,5 +17,5 @@ if len(sys.argv) > 1:
         torch.cuda.synchronize(); best = min(best, m.knn2_times()[0])
     print("CSA", os.environ.get("ORBX_KNN_CSA"), "scan ms %.2f" % best, "Gpairs/s %.1f" % (ndb * nq / best / 1e6), "checksum", int(out.sum(dtype=torch.int64)))
 else:
-    for c in ("0", "2", "3", "4", "13", "14"):
+    for c in (os.environ.get("CSA_LIST", "0,2,3,4,13,14,15").split(",")):
         subprocess.run([sys.executable, __file__, "x"], env=dict(os.environ, ORBX_KNN_CSA=c))
