@@ -2,6 +2,7 @@
 // (:27-54, :422-429), computeOrbDescriptor (:57-97) and the operator() epilogue (:1036-1064).
 #include "orbx_internal.cuh"
 
+#include <cuda_fp16.h>
 #include <mutex>
 
 namespace orbx {
@@ -217,13 +218,14 @@ k_describe(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, const
     // lane i owns descriptor byte i = pattern points 16i .. 16i+15.  The pattern lives in shared memory as floats, one
     // float4 (x0, y0, x1, y1 of a test pair) per (pair k, lane): consecutive lanes read consecutive 16 bytes.  Held in
     // registers (8 packed words + the floats the compiler hoisted out of the slot loop) it cost 96 bytes of spills.
-    __shared__ float4 pat[8][32];
+    __shared__ uint2 pat[8][32];                            // two half2 per entry: 8 bytes per lane, half the L1 wavefronts of float4
     __shared__ uint2 mtab[4 * kMomentPasses * 32];          // IC_Angle weights, see kMomentPasses
     if (threadIdx.x < 256) {
         const int k = threadIdx.x >> 5, l = threadIdx.x & 31;
         const uint32_t w = __ldg(pattern_words + l * 8 + k);
-        pat[k][l] = make_float4((float)(int)(signed char)(w), (float)(int)(signed char)(w >> 8),
-                                (float)(int)(signed char)(w >> 16), (float)(int)(signed char)(w >> 24));
+        const __half2 p0 = __floats2half2_rn((float)(int)(signed char)(w), (float)(int)(signed char)(w >> 8));
+        const __half2 p1 = __floats2half2_rn((float)(int)(signed char)(w >> 16), (float)(int)(signed char)(w >> 24));
+        pat[k][l] = make_uint2(*reinterpret_cast<const uint32_t *>(&p0), *reinterpret_cast<const uint32_t *>(&p1));
     }
     for (int i = threadIdx.x; i < 4 * kMomentPasses * 32; i += kDescWarps * 32) mtab[i] = __ldg(moment_tab + i);
     __syncthreads();
@@ -325,8 +327,9 @@ k_describe(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, const
         int val = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const float4 pp = pat[k][lane];
-            const float x0 = pp.x, y0 = pp.y, x1 = pp.z, y1 = pp.w;
+            const uint2 pp = pat[k][lane];                   // pattern offsets are integers in [-13, 13]: exact in half
+            const float2 q0 = __half22float2(*reinterpret_cast<const __half2 *>(&pp.x)), q1 = __half22float2(*reinterpret_cast<const __half2 *>(&pp.y));
+            const float x0 = q0.x, y0 = q0.y, x1 = q1.x, y1 = q1.y;
             const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
             const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
             const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));

@@ -2,14 +2,15 @@
 //
 // One WARP per (cell, frame); eight cells per block, each warp with a private shared-memory region, so
 // there are no block barriers and no idle warps.  ncu history, round 1 (lane-instructions per pixel):
-// thread-per-pixel 406 (ALU pipe 79 %), block-per-cell with work queues 224, warp-per-cell ~100, this ~80.
-// The warp stages the cell's (wCell+6) x (hCell+6) u8 tile with aligned 16-byte loads, then runs the
+// thread-per-pixel 406 (ALU pipe 79 %), block-per-cell with work queues 224, warp-per-cell ~100, this ~50
+// (3.76e8 warp instructions for 256 VGA frames = 243 M tested pixels).
+// The warp stages the cell's (wCell+6) x (hCell+6) u8 tile with aligned 16-byte cp.async, then runs the
 // reference's two attempts literally -- cv::FAST(cell, iniThFAST) and, only if that returned nothing,
 // cv::FAST(cell, minThFAST) (:766-773).  One attempt at threshold t:
 //   A  every interior pixel, lane = column, verdicts collected in per-lane bitmasks: compass pre-test.
 //      Every 9-arc of the 16-ring holds one pixel of each opposite pair, so a corner needs
 //      min(max(N,S),max(E,W)) > v+t (bright) or max(min(N,S),min(E,W)) < v-t (dark).  Survivors are
-//      compacted into a queue with their polarity.
+//      compacted into a queue sorted by polarity (bright from the front, dark from the back).
 //   B  queue, all lanes busy: the cornerScore of the candidate polarity as a sliding-window min over the
 //      circular ring with 3-input min/max (VIMNMX3).  A 9-arc of each polarity cannot coexist (18 > 16
 //      ring pixels), so score = max_arcs(min_arc(s*d)) - 1, and the pixel is a corner iff that max > t.
