@@ -25,7 +25,7 @@ namespace orbx {
 constexpr int kFastWarps = 8;
 constexpr int kFastThreads = kFastWarps * 32;
 // per-warp shared-memory layout, sized at launch from the largest cell of the geometry
-struct FastSmem { int tp, sp, tile_rows, npix_max, off_score, off_queue, off_bm, per_warp; };
+struct FastSmem { int tp, sp, tile_rows, npix_max, off_score, off_queue, off_bm, per_warp, zero_vecs; };
 
 __device__ __forceinline__ int min3(int a, int b, int c) { return __vimin3_s32(a, b, c); }
 __device__ __forceinline__ int max3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
@@ -118,10 +118,9 @@ k_fast_cells(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr,
     for (int attempt = 0; attempt < 2 && !found; ++attempt) {
         const int th = attempt == 0 ? iniTh : minTh;
         {
-            uint32_t *s32 = reinterpret_cast<uint32_t *>(score);
-            const int nwords = ((ih + 2) * kSP + 3) >> 2;
-            for (int i = lane; i < nwords; i += 32) s32[i] = 0;
-            for (int i = lane; i < nbm; i += 32) bm[i] = 0;
+            // score array and NMS bitmap are adjacent: one 16-byte store loop clears both
+            uint4 *z = reinterpret_cast<uint4 *>(score);
+            for (int i = lane; i < sm.zero_vecs; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
         }
         cp_async_wait_all();                               // the tile (first attempt; nothing pending on the second)
         __syncwarp();
@@ -268,9 +267,10 @@ void launch_fast(const Geo &g, const DevBuffers &b, int nframes, cudaStream_t s)
     sm.tp = (mw + 6 + 15 + 15) / 16 * 16; sm.sp = (mw + 2 + 3) / 4 * 4; sm.tile_rows = mh + 6;
     sm.npix_max = (mw * mh + 1) / 2 * 2;
     sm.off_score = up16(sm.tile_rows * sm.tp);
-    sm.off_queue = sm.off_score + up16((mh + 2) * sm.sp);
-    sm.off_bm = sm.off_queue + up16(sm.npix_max * 2);
-    sm.per_warp = sm.off_bm + up16(mh * 2 * 4);
+    sm.off_bm = sm.off_score + up16((mh + 2) * sm.sp);
+    sm.off_queue = sm.off_bm + up16(mh * 2 * 4);
+    sm.per_warp = sm.off_queue + up16(sm.npix_max * 2);
+    sm.zero_vecs = (sm.off_queue - sm.off_score) / 16;
     // phase A walks its rows in groups of eight: the rows past the cell are masked off, but they are read, so the
     // warp's region must reach (mh rounded up to 8) + 6 rows plus the column slack of one more row
     const int walk = ((mh + 7) / 8 * 8 + 7) * sm.tp;
