@@ -22,7 +22,7 @@
 
 namespace orbx {
 
-constexpr int kFastWarps = 8;
+constexpr int kFastWarps = 4;
 constexpr int kFastThreads = kFastWarps * 32;
 // per-warp shared-memory layout, sized at launch from the largest cell of the geometry
 struct FastSmem { int tp, sp, tile_rows, npix_max, off_score, off_queue, off_bm, per_warp, zero_vecs; };
