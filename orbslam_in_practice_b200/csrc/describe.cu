@@ -199,12 +199,12 @@ __device__ __forceinline__ void stage_patch(uint32_t *patch, const uint8_t *blur
     cp_async_commit();
 }
 
-// One warp per four keypoints.  ncu, round 1: the direct-gather version needed ~20 L1 wavefronts for each
-// of the 16 scattered descriptor loads per lane; the 37x37 blurred patch is therefore staged in
-// shared memory (cp.async, double buffered: the next keypoint's patch lands while this one's descriptor is
-// computed) and gathered from there (<= 4-way bank conflicts).  Three phases per warp: (1) the moments of its
-// four keypoints, (2) fastAtan2 + the double-precision sincos ONCE, lane s working on keypoint s, (3) per keypoint
-// the rotated BRIEF tests and the output row.
+// One warp per kSlotsPerWarp (eight) keypoints.  ncu, round 1: the direct-gather version needed ~20 L1 wavefronts for
+// each of the 16 scattered descriptor loads per lane; the 37x37 blurred patch is therefore staged in shared memory
+// (cp.async, double buffered: the next keypoint's patch lands while this one's descriptor is computed) and gathered
+// from there (<= 4-way bank conflicts).  Three phases per warp: (1) the moments of its keypoints, (2) fastAtan2 + the
+// double-precision sincos ONCE, lane s working on keypoint s, (3) per keypoint the rotated BRIEF tests and the output
+// row.  The kernel runs at 86 % of the L1 data-pipe wavefront peak, not at the issue limit.
 template <int MINB, int kSlotsPerWarp>
 __global__ void __launch_bounds__(kDescWarps * 32, MINB)
 k_describe(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, const uint8_t *__restrict__ blur,
