@@ -261,6 +261,11 @@ typedef struct {
     int32_t update_centers;
     int32_t width, height;
     int32_t literal_gridid_bug;
+    /* Grid bounds of the frames (Frame::FindimageBound, src/Frame.cpp:111-142).  use_bounds == 0: the zero-distortion case
+     * [0, width) x [0, height) (:113-118).  use_bounds != 0: the explicit float bounds below -- what FindimageBound
+     * computes from the undistorted image corners when the lens is distorted (:121-141). */
+    int32_t use_bounds;
+    float min_x, max_x, min_y, max_y;
 } orbm_window_params;
 
 int orbm_search_window_device(orbm_matcher *m, const orbx_keypoint *d_kps, const uint8_t *d_desc, const int32_t *d_counts,

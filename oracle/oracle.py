@@ -297,11 +297,13 @@ class WindowParams(C.Structure):
                 ("query_level_min", C.c_int32), ("query_level_max", C.c_int32),
                 ("level_below", C.c_int32), ("level_above", C.c_int32), ("gate", C.c_int32), ("th_dist", C.c_int32),
                 ("nnratio", C.c_float), ("check_orientation", C.c_int32), ("update_centers", C.c_int32),
-                ("width", C.c_int32), ("height", C.c_int32), ("literal_gridid_bug", C.c_int32)]
+                ("width", C.c_int32), ("height", C.c_int32), ("literal_gridid_bug", C.c_int32),
+                ("use_bounds", C.c_int32), ("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float)]
 
 
 def window_params(radius, level_scale=None, query_levels=(0, 15), level_below=1, level_above=1, gate=1, th_dist=100,
-                  nnratio=0.0, check_orientation=True, update_centers=False, width=640, height=480, literal_bug=False):
+                  nnratio=0.0, check_orientation=True, update_centers=False, width=640, height=480, literal_bug=False,
+                  bounds=None):
     p = WindowParams()
     p.radius = radius
     ls = list(level_scale) if level_scale is not None else []
@@ -311,6 +313,9 @@ def window_params(radius, level_scale=None, query_levels=(0, 15), level_below=1,
     p.level_below, p.level_above, p.gate, p.th_dist, p.nnratio = level_below, level_above, gate, th_dist, nnratio
     p.check_orientation, p.update_centers = int(check_orientation), int(update_centers)
     p.width, p.height, p.literal_gridid_bug = width, height, int(literal_bug)
+    if bounds is not None:                      # (min_x, max_x, min_y, max_y): Frame::FindimageBound for a distorted lens
+        p.use_bounds = 1
+        p.min_x, p.max_x, p.min_y, p.max_y = [float(v) for v in bounds]
     return p
 
 

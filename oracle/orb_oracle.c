@@ -1027,7 +1027,8 @@ int orbo_search_window(const orbo_keypoint *kp1, const uint8_t *desc1, int n1,
                        const orbo_keypoint *kp2, const uint8_t *desc2, int n2,
                        float *centers, int32_t *m12, const orbo_window_params *P)
 {
-    const float minX = 0, maxX = (float)P->width, minY = 0, maxY = (float)P->height;
+    const float minX = P->use_bounds ? P->min_x : 0, maxX = P->use_bounds ? P->max_x : (float)P->width;   /* Frame.cpp:111-142 */
+    const float minY = P->use_bounds ? P->min_y : 0, maxY = P->use_bounds ? P->max_y : (float)P->height;
     const float wInv = (float)FRAME_GRID_COLS / (maxX - minX), hInv = (float)FRAME_GRID_ROWS / (maxY - minY);
     gcell *grid = (gcell *)calloc(FRAME_GRID_COLS * FRAME_GRID_ROWS, sizeof(gcell));
     for (int i = 0; i < n2; ++i) {

@@ -143,6 +143,8 @@ typedef struct {
     int32_t update_centers;
     int32_t width, height;
     int32_t literal_gridid_bug;
+    int32_t use_bounds;                 /* 0: grid bounds [0,width) x [0,height) (Frame.cpp:113-118); else the four floats (:121-141) */
+    float min_x, max_x, min_y, max_y;
 } orbo_window_params;
 int orbo_search_window(const orbo_keypoint *kp1, const uint8_t *desc1, int n1,
                        const orbo_keypoint *kp2, const uint8_t *desc2, int n2,

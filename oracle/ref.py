@@ -65,8 +65,9 @@ def build_match():
 
 
 def run_search_for_initialization(kp1, desc1, kp2, desc2, prev_matched, window=100, nnratio=0.9, check_orientation=True,
-                                  width=640, height=480, literal_bug=False):
-    """The reference's own ORBmatcher::SearchForInitialization (src/ORBmatcher.cpp:9-126, compiled unmodified)."""
+                                  width=640, height=480, literal_bug=False, bounds=None, raw_output=False):
+    """The reference's own ORBmatcher::SearchForInitialization (src/ORBmatcher.cpp:9-126, compiled unmodified).
+    bounds = (minX, maxX, minY, maxY) of the Frame grid (default: the zero-distortion bounds of width x height)."""
     kp1 = np.ascontiguousarray(kp1, KEYPOINT_DTYPE); kp2 = np.ascontiguousarray(kp2, KEYPOINT_DTYPE)
     desc1 = np.ascontiguousarray(desc1, np.uint8); desc2 = np.ascontiguousarray(desc2, np.uint8)
     prev = np.ascontiguousarray(prev_matched, np.float32)
@@ -76,8 +77,10 @@ def run_search_for_initialization(kp1, desc1, kp2, desc2, prev_matched, window=1
         with open(fin, "wb") as f:
             f.write(struct.pack("<7if", n1, n2, width, height, window, int(check_orientation), int(literal_bug), nnratio))
             f.write(kp1.tobytes()); f.write(desc1.tobytes()); f.write(kp2.tobytes()); f.write(desc2.tobytes()); f.write(prev.tobytes())
-        subprocess.check_call([MATCH_BIN, fin, fout])
+        subprocess.check_call([MATCH_BIN, fin, fout] + ([repr(float(np.float32(b))) for b in bounds] if bounds is not None else []))
         raw = open(fout, "rb").read()
+    if raw_output:
+        return raw
     n = struct.unpack_from("<i", raw, 0)[0]
     m12 = np.frombuffer(raw, np.int32, n1, 4).copy()
     prev_out = np.frombuffer(raw, np.float32, 2 * n1, 4 + 4 * n1).reshape(n1, 2).copy()

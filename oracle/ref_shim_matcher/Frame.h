@@ -25,10 +25,12 @@ class MapPoint;
 
 class Frame {
 public:
-    Frame(const std::vector<cv::KeyPoint> &kps, const cv::Mat &desc, int width, int height, bool literalBug)
+    /* bounds = {minX, maxX, minY, maxY}: what FindimageBound leaves in the statics -- {0, cols, 0, rows} without
+     * distortion (Frame.cpp:113-118), the undistorted corners otherwise (:121-141) */
+    Frame(const std::vector<cv::KeyPoint> &kps, const cv::Mat &desc, const float *bounds, bool literalBug)
         : mvUnKeypts(kps), mcvDescriptors(desc), mbLiteralBug(literalBug)
     {
-        miMinX = 0; miMaxX = (float)width; miMinY = 0; miMaxY = (float)height;              /* Frame.cpp:113-118 */
+        miMinX = bounds[0]; miMaxX = bounds[1]; miMinY = bounds[2]; miMaxY = bounds[3];
         mfGridElementWidthInv = static_cast<float>(FRAME_GRID_COLS) / (miMaxX - miMinX);     /* Frame.cpp:59-60 */
         mfGridElementHeightInv = static_cast<float>(FRAME_GRID_ROWS) / (miMaxY - miMinY);
         AssignFeaturesToGrid();

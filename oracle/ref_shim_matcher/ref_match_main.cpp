@@ -6,8 +6,10 @@
  * in.bin : int32 {n1, n2, width, height, window, checkOri, literalBug}, float nnratio,
  *          n1 x 28 B keypoints, n1 x 32 B descriptors, n2 x 28 B keypoints, n2 x 32 B descriptors, n1 x 2 float prevMatched
  * out.bin: int32 nmatches, n1 x int32 matches12, n1 x 2 float prevMatched (updated)
+ * optional argv[3..6]: minX maxX minY maxY (grid bounds of a distorted lens); default {0, width, 0, height}
  */
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -38,7 +40,9 @@ int main(int argc, char **argv)
     std::vector<cv::Point2f> prev(h[0]);
     for (int i = 0; i < h[0]; ++i) { float xy[2]; if (fread(xy, 4, 2, f) != 2) return 3; prev[i] = cv::Point2f(xy[0], xy[1]); }
     fclose(f);
-    ORBSlam::Frame F1(k1, d1, h[2], h[3], h[6] != 0), F2(k2, d2, h[2], h[3], h[6] != 0);
+    float bounds[4] = { 0.f, (float)h[2], 0.f, (float)h[3] };
+    if (argc >= 7) for (int i = 0; i < 4; ++i) bounds[i] = (float)atof(argv[3 + i]);
+    ORBSlam::Frame F1(k1, d1, bounds, h[6] != 0), F2(k2, d2, bounds, h[6] != 0);
     ORBSlam::ORBmatcher matcher(ratio, h[5] != 0);
     std::vector<int> m12;
     int n = matcher.SearchForInitialization(F1, F2, prev, m12, h[4]);

@@ -51,7 +51,8 @@ class WindowParams(C.Structure):
                 ("query_level_min", C.c_int32), ("query_level_max", C.c_int32),
                 ("level_below", C.c_int32), ("level_above", C.c_int32), ("gate", C.c_int32), ("th_dist", C.c_int32),
                 ("nnratio", C.c_float), ("check_orientation", C.c_int32), ("update_centers", C.c_int32),
-                ("width", C.c_int32), ("height", C.c_int32), ("literal_gridid_bug", C.c_int32)]
+                ("width", C.c_int32), ("height", C.c_int32), ("literal_gridid_bug", C.c_int32),
+                ("use_bounds", C.c_int32), ("min_x", C.c_float), ("max_x", C.c_float), ("min_y", C.c_float), ("max_y", C.c_float)]
 
     @classmethod
     def projection(cls, th, scale_factors, width, height, th_dist=100, check_orientation=True, level_below=1, level_above=1):

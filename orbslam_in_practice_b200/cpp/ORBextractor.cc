@@ -18,7 +18,7 @@ static void check(int rc, const char *what)
 
 ORBextractor::ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int _iniThFAST, int _minThFAST)
     : nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels), iniThFAST(_iniThFAST), minThFAST(_minThFAST),
-      mHandle(nullptr), mDevice(0), mMaxW(0), mMaxH(0), mMaxBatch(0), mbDownloadPyramid(true)
+      mHandle(nullptr), mDevice(0), mMaxW(0), mMaxH(0), mMaxBatch(0), mbDownloadPyramid(false)
 {
     // the tables come from the library (it restates ORBextractor.cpp:360-420); a 64x64 handle is enough
     // to query them and verifies early that a device exists (no CPU fallback)
@@ -48,34 +48,43 @@ void ORBextractor::operator()(cv::InputArray _image, cv::InputArray /*mask*/, st
     cv::Mat image = _image.getMat();
     if (image.type() != CV_8UC1) throw std::runtime_error("ORBextractor: image must be CV_8UC1");
     EnsureHandle(image.cols, image.rows, 1);
-    const int cap = orbx_capacity(mHandle);
-    std::vector<orbx_keypoint> kps((size_t)cap);
-    std::vector<unsigned char> desc((size_t)cap * 32);
+    const size_t cap = (size_t)orbx_capacity(mHandle);
+    if (mKpsBuf.size() < cap * sizeof(orbx_keypoint)) { mKpsBuf.resize(cap * sizeof(orbx_keypoint)); mDescBuf.resize(cap * 32); }
     int count = 0;
     check(orbx_extract_host(mHandle, image.data, image.step, image.step * (size_t)image.rows, image.cols, image.rows, 1,
-                            kps.data(), desc.data(), &count), "extract");
-    if (count == 0) _descriptors.release();
+                            (orbx_keypoint *)mKpsBuf.data(), mDescBuf.data(), &count), "extract");
+    if (count == 0) _descriptors.release();                       // src/ORBextractor.cpp:1024-1030
     else {
         _descriptors.create(count, 32, CV_8U);
         cv::Mat d = _descriptors.getMat();
-        for (int i = 0; i < count; ++i) std::memcpy(d.ptr(i), &desc[(size_t)i * 32], 32);
+        if (d.isContinuous()) std::memcpy(d.ptr(0), mDescBuf.data(), (size_t)count * 32);
+        else for (int i = 0; i < count; ++i) std::memcpy(d.ptr(i), &mDescBuf[(size_t)i * 32], 32);
     }
-    _keypoints.clear();
-    _keypoints.resize((size_t)count);
+    _keypoints.resize((size_t)count);                             // :1032-1033 (clear + reserve, then filled)
     static_assert(sizeof(cv::KeyPoint) == sizeof(orbx_keypoint), "KeyPoint layout");
-    if (count) std::memcpy((void *)_keypoints.data(), kps.data(), (size_t)count * sizeof(orbx_keypoint));
+    if (count) std::memcpy((void *)_keypoints.data(), mKpsBuf.data(), (size_t)count * sizeof(orbx_keypoint));
+    if (mbDownloadPyramid) DownloadPyramid();
+}
 
-    if (mbDownloadPyramid) {
-        mvBordered.resize(nlevels);
-        for (int l = 0; l < nlevels; ++l) {
-            int w = 0, h = 0;
-            check(orbx_level_dims(mHandle, l, &w, &h), "level_dims");
-            const int B = ORBX_EDGE_THRESHOLD;
-            mvBordered[l].create(h + 2 * B, w + 2 * B, CV_8UC1);
-            check(orbx_download_level(mHandle, 0, l, 0, B, mvBordered[l].data, mvBordered[l].step), "download_level");
-            mvImagePyramid[l] = mvBordered[l](cv::Rect(B, B, w, h));
-        }
+void ORBextractor::DownloadPyramid()
+{
+    if (!mHandle) return;
+    mvBordered.resize(nlevels);
+    for (int l = 0; l < nlevels; ++l) {
+        int w = 0, h = 0;
+        check(orbx_level_dims(mHandle, l, &w, &h), "level_dims");
+        const int B = ORBX_EDGE_THRESHOLD;
+        mvBordered[l].create(h + 2 * B, w + 2 * B, CV_8UC1);
+        check(orbx_download_level(mHandle, 0, l, 0, B, mvBordered[l].data, mvBordered[l].step), "download_level");
+        mvImagePyramid[l] = mvBordered[l](cv::Rect(B, B, w, h));
     }
+}
+
+void ORBextractor::SetDevice(int device)
+{
+    if (device == mDevice) return;
+    if (mHandle) { orbx_destroy(mHandle); mHandle = nullptr; mMaxW = mMaxH = mMaxBatch = 0; }   // re-created on the new device by the next call
+    mDevice = device;
 }
 
 void ORBextractor::ExtractBatch(const unsigned char *imgs, int width, int height, size_t rowPitch, size_t frameStride, int nframes,

@@ -5,8 +5,9 @@
 // mask, keypoints, descriptors) with the mask ignored, Get* accessors returning by value, and the
 // public mvImagePyramid member.  Everything per-pixel happens on the GPU through the C ABI in
 // include/orbx.h; there is no CPU fallback (construction throws std::runtime_error without a B200).
-// Additions (not in the reference): ExtractBatch() for many same-sized frames per call, and
-// SetPyramidDownload(false) to skip copying the pyramid back to the host when nobody reads it.
+// mvImagePyramid has no reader anywhere in the reference, so the pyramid stays on the device and the
+// member is materialised on request: DownloadPyramid() after a call, or SetPyramidDownload(true) for every call.
+// Additions (not in the reference): ExtractBatch() for many same-sized frames per call, SetDevice().
 #pragma once
 
 #include <vector>
@@ -38,15 +39,18 @@ public:
     std::vector<float> GetScaleSigmaSquares() { return mvLevelSigma2; }
     std::vector<float> GetInverseScaleSigmaSquares() { return mvInvLevelSigma2; }
 
-    // level l is a view of (cols x rows) pixels inside a buffer carrying the 19-px reflect-101 border
+    // level l is a view of (cols x rows) pixels inside a buffer carrying the 19-px reflect-101 border.  Filled by
+    // DownloadPyramid() (the last operator() call's pyramid stays on the device until the next call) or, with
+    // SetPyramidDownload(true), by every operator() call as in the reference.
     std::vector<cv::Mat> mvImagePyramid;
+    void DownloadPyramid();
 
     // ---- extensions ----
     // nframes same-sized frames: frame f, row y at imgs + f*frameStride + y*rowPitch
     void ExtractBatch(const unsigned char *imgs, int width, int height, size_t rowPitch, size_t frameStride, int nframes,
                       std::vector<std::vector<cv::KeyPoint> > &keypoints, std::vector<cv::Mat> &descriptors);
     void SetPyramidDownload(bool on) { mbDownloadPyramid = on; }
-    void SetDevice(int device) { mDevice = device; }
+    void SetDevice(int device);
 
 protected:
     void EnsureHandle(int width, int height, int batch);
@@ -64,6 +68,8 @@ protected:
     int mDevice, mMaxW, mMaxH, mMaxBatch;
     bool mbDownloadPyramid;
     std::vector<cv::Mat> mvBordered;   // owners of the bordered level buffers
+    // host staging of one call's outputs, sized once per handle: no allocation on the per-frame path
+    std::vector<unsigned char> mKpsBuf, mDescBuf;
 };
 
 } // namespace ORBSlam

@@ -23,6 +23,8 @@ struct NvtxRange {
 namespace orbx {
 // knn.cu
 int knn_segments(int nq, int ndb, int sm_count, int *seg_rows_out);
+size_t knn_partial_elems(int max_q, int max_db, int sm_count);
+void launch_knn2_empty(int nq, int *d1, int *idx1, int *d2, cudaStream_t s);
 void launch_knn2(const uint8_t *d_query, int nq, const uint8_t *d_db, int ndb, int index_base, int nseg, int seg_rows,
                  uint2 *partial, int *d1, int *idx1, int *d2, cudaStream_t s, cudaEvent_t *ev);
 void launch_hamming_pairs(const uint8_t *a, const uint8_t *b, int n, int *dist, cudaStream_t s);
@@ -837,9 +839,7 @@ extern "C" int orbm_create(int max_queries, int max_db, int device, orbm_matcher
     m->device = device; m->max_q = max_queries; m->max_db = max_db;
     CK(cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, device));
     CK(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
-    int seg_rows = 0;
-    const int nseg = knn_segments(max_queries, std::max(max_db, 1), m->sm_count, &seg_rows);
-    m->partial_elems = (size_t)(nseg + 1) * max_queries;
+    m->partial_elems = knn_partial_elems(max_queries, max_db, m->sm_count);   // worst case over every nq <= max_queries
     if (cudaMalloc(&m->partial, m->partial_elems * sizeof(uint2)) != cudaSuccess) { cuda_fail(cudaGetLastError(), "cudaMalloc"); orbm_destroy(m); return ORBX_E_NOMEM; }
     *out = m;
     return ORBX_OK;
@@ -1024,14 +1024,17 @@ extern "C" int orbm_knn2_sharded_device(orbm_matcher *m, const uint8_t *d_query,
     const int par = (int)(epoch & 1u), W = m->x_world;
     int *mine = (int *)m->x_buf + (size_t)par * 3 * m->x_qmax;       // this epoch's triple, arrays strided by x_qmax
     int rc = orbm_knn2_device(m, d_query, nq, d_db_shard, ndb_shard, index_base, mine, mine + m->x_qmax, mine + 2 * (size_t)m->x_qmax, s);
-    if (rc) return rc;
+    // A local failure must not leave the peers spinning until their timeout: publish an EMPTY shard for this epoch
+    // (idx = -1 rows are skipped by the merge) and the flag, run the merge like everybody else, then report the error.
+    const int scan_rc = rc;
+    if (rc) launch_knn2_empty(nq, mine, mine + m->x_qmax, mine + 2 * (size_t)m->x_qmax, s);
     launch_exchange_signal(m->x_flag_tab, m->x_rank, W, epoch, s);
     unsigned char *own = m->x_buf;
     launch_merge_peers((const int *const *)(m->x_tri_tab + (size_t)par * W), (const uint32_t *)(own + x_tri_bytes(m)), W, nq, (size_t)m->x_qmax,
                        epoch, d_d1, d_idx1, d_d2, th_low, ratio, d_match, (int *)(own + x_tri_bytes(m) + 64 * sizeof(uint32_t)), s);
     m->launches += 2;
     CK(cudaGetLastError());
-    return ORBX_OK;
+    return scan_rc;
 }
 
 extern "C" int orbm_exchange_status(orbm_matcher *m)
@@ -1052,7 +1055,8 @@ extern "C" size_t orbm_search_init_workspace_bytes(int capacity, int npairs)
 
 static int window_params_ok(const orbm_window_params *p)
 {
-    return p && p->width >= 1 && p->height >= 1 && p->radius >= 0.f && (p->gate == 0 || p->gate == 1) &&
+    const bool bounds_ok = p && (p->use_bounds ? (p->max_x > p->min_x && p->max_y > p->min_y) : (p->width >= 1 && p->height >= 1));
+    return p && bounds_ok && p->radius >= 0.f && (p->gate == 0 || p->gate == 1) &&
            p->query_level_min >= 0 && p->query_level_max < 16 && p->query_level_min <= p->query_level_max;
 }
 
@@ -1079,7 +1083,13 @@ extern "C" int orbm_search_window_device(orbm_matcher *m, const orbx_keypoint *d
     a.workspace = (uint32_t *)d_workspace; a.ws_words_per_pair = workspace_bytes / sizeof(uint32_t) / (size_t)npairs;
     int sn = 32; while (sn < capacity) sn <<= 1;
     a.sort_n = sn;
-    if (launch_search_init(a, stream ? (cudaStream_t)stream : m->stream)) return cuda_fail(cudaGetLastError(), "search_init smem");
+    if (const int lrc = launch_search_init(a, stream ? (cudaStream_t)stream : m->stream)) {
+        if (lrc == -2) {
+            std::snprintf(g_cuda_err, sizeof(g_cuda_err), "keypoint capacity %d too large for the search kernel's shared-memory tables (limit about 11 600)", capacity);
+            return ORBX_E_UNSUPPORTED;
+        }
+        return cuda_fail(cudaGetLastError(), "search_init smem");
+    }
     m->launches += 1;
     CK(cudaGetLastError());
     return ORBX_OK;
@@ -1106,7 +1116,13 @@ extern "C" int orbm_search_groups_device(orbm_matcher *m, const orbx_keypoint *d
     a.workspace = (uint32_t *)d_workspace; a.ws_words_per_pair = workspace_bytes / sizeof(uint32_t) / (size_t)npairs;
     int sn = 32; while (sn < capacity) sn <<= 1;
     a.sort_n = sn;
-    if (launch_search_init(a, stream ? (cudaStream_t)stream : m->stream)) return cuda_fail(cudaGetLastError(), "search_init smem");
+    if (const int lrc = launch_search_init(a, stream ? (cudaStream_t)stream : m->stream)) {
+        if (lrc == -2) {
+            std::snprintf(g_cuda_err, sizeof(g_cuda_err), "keypoint capacity %d too large for the search kernel's shared-memory tables (limit about 11 600)", capacity);
+            return ORBX_E_UNSUPPORTED;
+        }
+        return cuda_fail(cudaGetLastError(), "search_init smem");
+    }
     m->launches += 1;
     CK(cudaGetLastError());
     return ORBX_OK;

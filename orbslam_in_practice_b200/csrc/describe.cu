@@ -236,10 +236,6 @@ k_describe(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, const
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
     const int total = __shfl_sync(0xffffffffu, incl, 31);
     if (blockIdx.x == 0 && threadIdx.x == 0) out_counts[f] = total;
-    // (unused since the per-lane level lookup; left in because removing it changes ptxas' register naming, and the
-    //  object code shipped is the one the round-1 GPU parity run validated -- drop it with the next validated change)
-    const uint32_t lvl_mask = g.nlevels >= 32 ? 0xffffffffu : ((1u << g.nlevels) - 1u);
-
     const int slot0 = (blockIdx.x * kDescWarps + warp) * kSlotsPerWarp;   // first output row of this warp inside the frame
     const int nslot = min(kSlotsPerWarp, total - slot0);
     if (nslot <= 0) return;

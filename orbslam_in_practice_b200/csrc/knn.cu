@@ -277,7 +277,12 @@ k_merge_peers(const int *const *__restrict__ peer_tri, const volatile uint32_t *
     }
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nq || !s_ok) return;
+    if (i >= nq) return;
+    if (!s_ok) {                                                  // a shard never arrived: no stale results of an earlier call survive
+        od1[i] = INT_MAX; oidx1[i] = -1; od2[i] = INT_MAX;
+        if (match) match[i] = -1;
+        return;
+    }
     int best = INT_MAX, best2 = INT_MAX, bidx = -1;
     for (int r = 0; r < world; ++r) {                             // ranks own ascending index ranges
         const int *t = peer_tri[r];
@@ -291,6 +296,10 @@ k_merge_peers(const int *const *__restrict__ peer_tri, const volatile uint32_t *
     if (match) match[i] = (bidx >= 0 && best <= th_low && (float)best < __fmul_rn((float)best2, ratio)) ? bidx : -1;
 }
 
+void launch_knn2_empty(int nq, int *d1, int *idx1, int *d2, cudaStream_t s)
+{
+    if (nq > 0) k_knn2_empty<<<(nq + 255) / 256, 256, 0, s>>>(nq, d1, idx1, d2);
+}
 void launch_exchange_signal(uint32_t *const *peer_flags, int rank, int world, uint32_t epoch, cudaStream_t s)
 {
     k_exchange_signal<<<1, 32, 0, s>>>(peer_flags, rank, world, epoch);
@@ -343,6 +352,22 @@ int knn_segments(int nq, int ndb, int sm_count, int *seg_rows_out)
     nseg = (ndb + seg_rows - 1) / seg_rows;
     *seg_rows_out = seg_rows;
     return nseg;
+}
+
+// Worst case of nseg * nq over every query count a handle created for (max_q, max_db) accepts.  The segment count GROWS
+// when the query count shrinks (fewer blocks in x -> more database segments to fill the SMs), so sizing for nq = max_q
+// alone rejects valid smaller calls.  nseg is non-decreasing in ndb, so ndb = max_db is the worst database.
+size_t knn_partial_elems(int max_q, int max_db, int sm_count)
+{
+    size_t worst = 0;
+    const int gx_max = (max_q + kQPB - 1) / kQPB;
+    for (int gx = 1; gx <= gx_max; ++gx) {
+        const int nq = gx * kQPB < max_q ? gx * kQPB : max_q;      // the largest query count with this many blocks in x
+        int seg_rows = 0;
+        const size_t need = (size_t)knn_segments(nq, max_db > 0 ? max_db : 1, sm_count, &seg_rows) * (size_t)nq;
+        worst = need > worst ? need : worst;
+    }
+    return worst;
 }
 
 void launch_knn2(const uint8_t *d_query, int nq, const uint8_t *d_db, int ndb, int index_base, int nseg, int seg_rows,

@@ -64,7 +64,7 @@ k_search_init(const __grid_constant__ SearchInitArgs A)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int pair = blockIdx.x;
     const int fa = A.pair_a[pair], fb = A.pair_b[pair];
-    const int n1 = A.counts[fa], n2 = A.counts[fb];
+    const int n1 = min(max(A.counts[fa], 0), A.cap), n2 = min(max(A.counts[fb], 0), A.cap);   // never trust a count beyond the row capacity
     const orbx_keypoint *kp1 = A.kps + (size_t)fa * A.cap, *kp2 = A.kps + (size_t)fb * A.cap;
     const uint4 *d1 = reinterpret_cast<const uint4 *>(A.desc + (size_t)fa * A.cap * 32);
     const uint4 *d2 = reinterpret_cast<const uint4 *>(A.desc + (size_t)fb * A.cap * 32);
@@ -76,7 +76,8 @@ k_search_init(const __grid_constant__ SearchInitArgs A)
 
     // image bounds for zero distortion (Frame.cpp:113-118) and grid cell sizes (:59-60)
     const orbm_window_params &W = A.w;
-    const float minX = 0.f, minY = 0.f, maxX = (float)W.width, maxY = (float)W.height;
+    const float minX = W.use_bounds ? W.min_x : 0.f, maxX = W.use_bounds ? W.max_x : (float)W.width;
+    const float minY = W.use_bounds ? W.min_y : 0.f, maxY = W.use_bounds ? W.max_y : (float)W.height;
     const float wInv = (float)kGridCols / (maxX - minX), hInv = (float)kGridRows / (maxY - minY);
 
     // ---- 1: grid keys of F2; only the octaves some query can ask for (SearchForInitialization: octave 0 alone,
@@ -335,6 +336,7 @@ size_t search_init_smem_bytes(int cap, int sort_n)
 int launch_search_init(const SearchInitArgs &a, cudaStream_t s)
 {
     const size_t smem = search_init_smem_bytes(a.cap, a.sort_n);
+    if (smem > 227 * 1024) return -2;                     // per-pair tables do not fit one SM's shared memory (capacity beyond ~11 600)
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(k_search_init, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
     k_search_init<<<a.npairs, kSiThreads, smem, s>>>(a);

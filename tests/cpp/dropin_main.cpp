@@ -34,7 +34,9 @@ int main(int argc, char **argv)
         if (n) lastDesc = desc;
         allKps.push_back(kps); allDesc.push_back(desc.clone());
     }
-    // trailer: pyramid checks + matcher checks on the last frame
+    // trailer: pyramid checks + matcher checks on the last frame.  mvImagePyramid is materialised on request (it has no
+    // reader in the reference): the last call's pyramid is still on the device
+    ex->DownloadPyramid();
     int levels = ex->GetLevels();
     std::fwrite(&levels, 4, 1, fo);
     for (int l = 0; l < levels; ++l) {

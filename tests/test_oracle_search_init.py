@@ -87,3 +87,24 @@ def test_group_search_properties(oracle):
     n1, m1 = oracle.search_groups(k1[:1], d1[:1], one[:1], k2, d2, two, 256, 10.0, False)
     dist = np.unpackbits(d1[:1] ^ d2, axis=1).sum(1)
     assert n1 == 1 and m1[0] == int(np.argmin(dist))
+
+
+BOUNDS = (40.5, 600.25, 30.75, 440.5)        # FindimageBound of a distorted lens (src/Frame.cpp:121-141): min over the undistorted corners, can cut into the image
+
+
+@pytest.mark.parametrize("seed,shift,ratio,ori", [(0, (5, 3), 0.9, True), (7, (-9, 14), 0.7, False)])
+def test_explicit_grid_bounds_equal_reference_matcher_tu(oracle, seed, shift, ratio, ori):
+    """Float grid bounds (a distorted lens): the windowed oracle with explicit bounds against the reference's own
+    ORBmatcher.cpp over a Frame whose statics hold those bounds; and bounds = {0, w, 0, h} is the default case."""
+    k1, d1, k2, d2 = _pair(oracle, seed, shift)
+    prev = np.stack([k1["x"], k1["y"]], 1)
+    mk = lambda b: oracle.window_params(100.0, None, (0, 0), 0, 0, gate=0, th_dist=50, nnratio=ratio, check_orientation=ori,
+                                        update_centers=True, width=640, height=480, bounds=b)
+    n_b, m_b, p_b = oracle.search_window(k1, d1, k2, d2, prev, mk(BOUNDS))
+    n_r, m_r, p_r = R.run_search_for_initialization(k1, d1, k2, d2, prev, 100, ratio, ori, 640, 480, False, bounds=BOUNDS)
+    assert n_b == n_r and np.array_equal(m_b, m_r) and np.array_equal(p_b, p_r)
+    assert n_r > 50
+    n_0, m_0, p_0 = oracle.search_window(k1, d1, k2, d2, prev, mk(None))
+    n_1, m_1, p_1 = oracle.search_window(k1, d1, k2, d2, prev, mk((0.0, 640.0, 0.0, 480.0)))
+    assert n_0 == n_1 and np.array_equal(m_0, m_1) and np.array_equal(p_0, p_1)
+    assert not np.array_equal(m_0, m_b)          # the bounds do change the grid (otherwise this test pins nothing)
