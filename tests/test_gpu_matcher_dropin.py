@@ -108,8 +108,9 @@ def test_typed_bow_and_projection_call_sites(orbx, oracle, tmp_path):
     bad = has_mp & ((np.arange(len(k1)) % 17) == 0)
     fx, fy, cx, cy = 500.0, 500.0, 320.0, 240.0
     z = 2.0
-    X = (k1["x"].astype(np.float64) - np.float32(cx)) / np.float32(fx) * z
-    Y = (k1["y"].astype(np.float64) - np.float32(cy)) / np.float32(fy) * z
+    # same arithmetic as the driver: float subtraction and division, then double
+    X = ((k1["x"] - np.float32(cx)) / np.float32(fx)).astype(np.float64) * z
+    Y = ((k1["y"] - np.float32(cy)) / np.float32(fy)).astype(np.float64) * z
     u = (np.float32(fx) * X / z + np.float32(cx)).astype(np.float32)
     v = (np.float32(fy) * Y / z + np.float32(cy)).astype(np.float32)
     cen = np.stack([u, v], 1)
