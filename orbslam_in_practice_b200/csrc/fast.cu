@@ -4,16 +4,23 @@
 // there are no block barriers and no idle warps.  ncu history, round 1 (lane-instructions per pixel):
 // thread-per-pixel 406 (ALU pipe 79 %), block-per-cell with work queues 224, warp-per-cell ~100, this ~50
 // (3.76e8 warp instructions for 256 VGA frames = 243 M tested pixels).
-// The warp stages the cell's (wCell+6) x (hCell+6) u8 tile with aligned 16-byte cp.async, then runs the
+// The warp stages the cell's (wCell+6) x (hCell+6) u8 tile with aligned 8-byte cp.async into a tile whose pitch is
+// an ODD multiple of 8 bytes (56, 72, ...: 14, 18, ... words), so that 16 consecutive rows of one column fall into 16
+// different banks.  ncu, round 2: with the 64-byte pitch of round 1 a column's rows alternate between TWO banks, the
+// candidates of a phase-B chunk come column by column, and every ring load cost 4.8 wavefronts -- the kernel sat at
+// 82 % of the shared-memory wavefront peak (46 % of the wavefronts in phase B), not at the issue limit.  It then runs the
 // reference's two attempts literally -- cv::FAST(cell, iniThFAST) and, only if that returned nothing,
 // cv::FAST(cell, minThFAST) (:766-773).  One attempt at threshold t:
 //   A  every interior pixel, lane = column, verdicts collected in per-lane bitmasks: compass pre-test.
 //      Every 9-arc of the 16-ring holds one pixel of each opposite pair, so a corner needs
-//      min(max(N,S),max(E,W)) > v+t (bright) or max(min(N,S),min(E,W)) < v-t (dark).  Survivors are
-//      compacted into a queue sorted by polarity (bright from the front, dark from the back).
-//   B  queue, all lanes busy: the cornerScore of the candidate polarity as a sliding-window min over the
-//      circular ring with 3-input min/max (VIMNMX3).  A 9-arc of each polarity cannot coexist (18 > 16
-//      ring pixels), so score = max_arcs(min_arc(s*d)) - 1, and the pixel is a corner iff that max > t.
+//      min(max(N,S),max(E,W)) > v+t (bright) or max(min(N,S),min(E,W)) < v-t (dark).  Survivors of either
+//      polarity are compacted into one queue.
+//   B  queue, all lanes busy: cornerScore as a sliding-window min over the circular ring with 3-input
+//      min/max, BOTH polarities in one pass: a ring pixel e is held as the 16-bit pair (e, 255 - e), so
+//      one VIMNMX3.U16x2 takes the arc minimum of e (bright) in the low half and 255 - (arc maximum of e)
+//      (dark) in the high half.  score = max(max_arcs(min_arc e) - v, v - min_arcs(max_arc e)) - 1, and the
+//      pixel is a corner iff that maximum > t.  ncu, round 2: the two scalar passes (one per polarity, ~150
+//      instructions per 32 candidates, nearly every chunk mixed) were 24 % of the kernel's instructions.
 //   C  corners only: strict 3x3 non-max suppression *inside the cell* (non-corners and pixels outside the
 //      cell read 0) -> bitmap
 //   D  emit set bits in row-major order into the cell's slot array.
@@ -30,38 +37,33 @@ struct FastSmem { int tp, sp, tile_rows, npix_max, off_score, off_queue, off_bm,
 __device__ __forceinline__ int min3(int a, int b, int c) { return __vimin3_s32(a, b, c); }
 __device__ __forceinline__ int max3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
 
-// max over the 16 arcs of 9 contiguous ring values of their minimum (cornerScore<16>'s core, bright arcs)
-__device__ __forceinline__ int arc9_maxmin(const int (&e)[16])
+// ring pixel e (0..255) as the 16-bit pair (e, 255 - e): e * (1 - 2^16) + (255 << 16), one IMAD
+__device__ __forceinline__ uint32_t pack_pm(int e) { return (uint32_t)e * 0xffff0001u + 0x00ff0000u; }
+__device__ __forceinline__ uint32_t min3x2(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u16x2(a, b, c); }
+__device__ __forceinline__ uint32_t max3x2(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_u16x2(a, b, c); }
+
+// cornerScore<16>'s core for both polarities at once on packed ring values (see pack_pm):
+//   low half:  max over the 16 arcs of 9 contiguous ring values of their minimum           (bright arcs)
+//   high half: max over the arcs of min(255 - e) = 255 - (min over the arcs of their maximum) (dark arcs)
+__device__ __forceinline__ uint32_t arc9_both(const uint32_t (&e)[16])
 {
-    int m3[16], m9[16];
+    uint32_t m3[16], m9[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) m3[k] = min3(e[k], e[(k + 1) & 15], e[(k + 2) & 15]);
+    for (int k = 0; k < 16; ++k) m3[k] = min3x2(e[k], e[(k + 1) & 15], e[(k + 2) & 15]);
 #pragma unroll
-    for (int k = 0; k < 16; ++k) m9[k] = min3(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
-    int b0 = max3(m9[0], m9[1], m9[2]), b1 = max3(m9[3], m9[4], m9[5]), b2 = max3(m9[6], m9[7], m9[8]);
-    int b3 = max3(m9[9], m9[10], m9[11]), b4 = max3(m9[12], m9[13], m9[14]);
-    return max3(max3(b0, b1, b2), b3, max3(b4, m9[15], m9[15]));
-}
-// min over the 16 arcs of their maximum (dark arcs)
-__device__ __forceinline__ int arc9_minmax(const int (&e)[16])
-{
-    int m3[16], m9[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) m3[k] = max3(e[k], e[(k + 1) & 15], e[(k + 2) & 15]);
-#pragma unroll
-    for (int k = 0; k < 16; ++k) m9[k] = max3(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
-    int b0 = min3(m9[0], m9[1], m9[2]), b1 = min3(m9[3], m9[4], m9[5]), b2 = min3(m9[6], m9[7], m9[8]);
-    int b3 = min3(m9[9], m9[10], m9[11]), b4 = min3(m9[12], m9[13], m9[14]);
-    return min3(min3(b0, b1, b2), b3, min3(b4, m9[15], m9[15]));
+    for (int k = 0; k < 16; ++k) m9[k] = min3x2(m3[k], m3[(k + 3) & 15], m3[(k + 6) & 15]);
+    const uint32_t b0 = max3x2(m9[0], m9[1], m9[2]), b1 = max3x2(m9[3], m9[4], m9[5]), b2 = max3x2(m9[6], m9[7], m9[8]);
+    const uint32_t b3 = max3x2(m9[9], m9[10], m9[11]), b4 = max3x2(m9[12], m9[13], m9[14]);
+    return max3x2(max3x2(b0, b1, b2), b3, max3x2(b4, m9[15], m9[15]));
 }
 
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
 {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
-// TP: tile pitch as a compile-time constant (64 covers every cell up to 28 + 36 = 43 px wide incl. the alignment
+// TP: tile pitch as a compile-time constant (56 covers every cell up to 56 - 7 - 6 = 43 px wide incl. the alignment
 // slack, i.e. all VGA / KITTI / 4K geometries), 0 = the runtime pitch sm.tp.
 template <int TP>
 __global__ void __launch_bounds__(kFastThreads)
@@ -75,9 +77,8 @@ k_fast_cells(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr,
     unsigned char *mine = fast_smem + warp * sm.per_warp;
     uint8_t *tile = mine;                                                     // [tile_rows][tp]
     uint8_t *score = mine + sm.off_score;                                     // [tile_rows - 4][sp]
-    uint16_t *queue = reinterpret_cast<uint16_t *>(mine + sm.off_queue);      // phase A survivors: bright from the front, dark from the back
+    uint16_t *queue = reinterpret_cast<uint16_t *>(mine + sm.off_queue);      // phase A survivors (x | y << 6), either polarity
     const int kTP = TP ? TP : sm.tp, kSP = sm.sp;
-    const int qlast = sm.npix_max - 1;
 
     // cell rectangle, ORBextractor.cpp:745-762, precomputed on the host (build_cell_table): one 16-byte load
     const int4 ct = __ldg(cell_tab + cell);
@@ -88,19 +89,20 @@ k_fast_cells(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr,
     if (cw == 0) { if (lane == 0) *count_out = 0; return; }
     const int iw = cw - 6, ih = ch - 6;                // pixels FAST actually tests
 
-    // ---- phase 0: stage the tile with 16-byte cp.async (no registers, every row of the lane in flight at once):
-    //      tile column 0 is the 16-byte aligned pixel at or left of iniX (rows are 64-byte aligned, the interior
-    //      starts at byte 32), so cell column c lives at tile column c + xoff.  4 rows per warp pass. ----
-    const int xoff = iniX & 15;
+    // ---- phase 0: stage the tile with 8-byte cp.async (no registers, every row of the lane in flight at once):
+    //      tile column 0 is the 8-byte aligned pixel at or left of iniX (rows are 64-byte aligned, the interior
+    //      starts at byte 32), so cell column c lives at tile column c + xoff.  4 rows per warp pass (2 for wide cells). ----
+    const int xoff = iniX & 7;
     {
         const uint8_t *img = pyr + L.base + (size_t)f * L.frame_stride + (size_t)(kPadY + iniY) * L.pitch + kPadX + (iniX - xoff);
-        const int vpr = (cw + xoff + 15) >> 4;              // 16-byte vectors per tile row (<= kTP / 16)
-        const int sub = lane & 7, rr = lane >> 3;           // up to 8 vectors per row, 4 rows per pass
+        const int vpr = (cw + xoff + 7) >> 3;               // 8-byte vectors per tile row (<= kTP / 8)
+        const int lsh = vpr <= 8 ? 3 : 4;                   // lanes per row: 8 (4 rows per pass) or 16 (2 rows per pass)
+        const int sub = lane & ((1 << lsh) - 1), rr = lane >> lsh, rstep = 32 >> lsh;
         if (sub < vpr) {
-            const uint8_t *src = img + (size_t)rr * L.pitch + sub * 16;
-            uint8_t *dst = tile + rr * kTP + sub * 16;
-            const size_t sstep = (size_t)4 * L.pitch;
-            for (int r = rr; r < ch; r += 4, src += sstep, dst += 4 * kTP) cp_async16(dst, src);
+            const uint8_t *src = img + (size_t)rr * L.pitch + sub * 8;
+            uint8_t *dst = tile + rr * kTP + sub * 8;
+            const size_t sstep = (size_t)rstep * L.pitch;
+            for (int r = rr; r < ch; r += rstep, src += sstep, dst += rstep * kTP) cp_async8(dst, src);
         }
     }
     // NMS bitmap: one 32- or 64-bit row of bits per pixel row (bit = column), so bit order is row-major and the
@@ -127,9 +129,9 @@ k_fast_cells(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr,
 
         // ---- phase A: compass pre-test, lane = column, walking down the rows with the column's last six pixels in
         //      registers (N of row y is the centre of row y+3 and S of row y+6): three loads per pixel.  The two
-        //      verdicts are sign bits, (v + t) - min(max(N,S),max(E,W)) < 0 and max(min(N,S),min(E,W)) + t - v < 0,
-        //      shifted into per-lane masks with one funnel shift each (row y ends up at bit nr-1-y). ----
-        int nb = 0, nd = 0;                                // queue fill: bright [0, nb), dark (qlast - nd, qlast]
+        //      verdicts are sign bits, (v + t) - min(max(N,S),max(E,W)) < 0 and max(min(N,S),min(E,W)) + t - v < 0;
+        //      their OR is shifted into a per-lane mask with one funnel shift (row y ends up at bit nr-1-y). ----
+        int nq = 0;                                        // queue fill
         for (int x0 = 0; x0 < iw; x0 += 32) {
             const int x = x0 + lane;
             const bool inx = x < iw;
@@ -138,7 +140,7 @@ k_fast_cells(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr,
                 const int nr = (rows + 7) & ~7;            // rows walked (the extra ones are masked off below)
                 const uint8_t *p = tile + (yb + 3) * kTP + 3 + xoff + (inx ? x : 0);
                 int c0 = p[-3 * kTP], c1 = p[-2 * kTP], c2 = p[-kTP], c3 = p[0], c4 = p[kTP], c5 = p[2 * kTP];
-                uint32_t mb = 0, md = 0;
+                uint32_t m = 0;
 #pragma unroll 1
                 for (int y0 = 0; y0 < nr; y0 += 8, p += 8 * kTP) {
 #pragma unroll
@@ -146,66 +148,46 @@ k_fast_cells(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr,
                         const int n = p[(k + 3) * kTP], e = p[k * kTP + 3], w = p[k * kTP - 3];
                         const int hi = min(max(n, c0), max(e, w));
                         const int lo = max(min(n, c0), min(e, w));
-                        mb = __funnelshift_l((uint32_t)(c3 + th - hi), mb, 1);
-                        md = __funnelshift_l((uint32_t)(lo + th - c3), md, 1);
+                        m = __funnelshift_l((uint32_t)((c3 + th - hi) | (lo + th - c3)), m, 1);
                         c0 = c1; c1 = c2; c2 = c3; c3 = c4; c4 = c5; c5 = n;
                     }
                 }
                 const uint32_t valid = inx ? (0xffffffffu >> (32 - nr)) & (0xffffffffu << (nr - rows)) : 0u;
-                mb &= valid; md &= valid;
-                uint32_t both = mb & md;
-                mb &= ~both; md &= ~both;                  // bright only / dark only / (rare) both
-                // one scan for both queue ends: bright (incl. both) in the low half, dark in the high half
-                const int cnt = (__popc(mb) + __popc(both)) | (__popc(md) << 16);
+                m &= valid;
+                const int cnt = __popc(m);
                 int inc = cnt;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-                const int excl = inc - cnt;
-                // queue entry: x | y << 6 | both << 12   (x, y < 64); bit b of a mask is row yb + nr - 1 - b
+                // queue entry: x | y << 6   (x, y < 64); bit b of the mask is row yb + nr - 1 - b
                 const int ebase = x | ((yb + nr - 1) << 6);
-                uint16_t *qb = queue + nb + (excl & 0xffff);
-                while (mb) {
-                    const int b = 31 - __clz(mb);
-                    mb ^= 1u << b;
-                    *qb++ = (uint16_t)(ebase - (b << 6));
+                uint16_t *q = queue + nq + (inc - cnt);
+                while (m) {
+                    const int b = 31 - __clz(m);
+                    m ^= 1u << b;
+                    *q++ = (uint16_t)(ebase - (b << 6));
                 }
-                while (both) {
-                    const int b = 31 - __clz(both);
-                    both ^= 1u << b;
-                    *qb++ = (uint16_t)((ebase - (b << 6)) | 0x1000);
-                }
-                uint16_t *qd = queue + qlast - nd - (excl >> 16);
-                while (md) {
-                    const int b = 31 - __clz(md);
-                    md ^= 1u << b;
-                    *qd-- = (uint16_t)(ebase - (b << 6));
-                }
-                const int tot = __shfl_sync(0xffffffffu, inc, 31);
-                nb += tot & 0xffff; nd += tot >> 16;
+                nq += __shfl_sync(0xffffffffu, inc, 31);
             }
         }
         __syncwarp();
-        const int nq = nb + nd;
 
-        // ---- phase B: exact score.  The queue is sorted by polarity, so all chunks but one run a single path on the
-        //      raw ring bytes: bright = max over arcs of the arc's minimum - v, dark = v - min over arcs of the arc's
-        //      maximum (cornerScore's two halves; an arc of each polarity cannot coexist, 18 > 16 ring pixels). ----
+        // ---- phase B: exact score of both polarities in one packed pass (see arc9_both): bright = max over arcs of
+        //      the arc's minimum - v, dark = v - min over arcs of the arc's maximum (cornerScore's two halves). ----
         for (int i0 = 0; i0 < nq; i0 += 32) {
             const int i = i0 + lane;
             if (i < nq) {
-                const bool dark = i >= nb;
-                const uint32_t ent = queue[dark ? qlast - (i - nb) : i];
-                const int x = ent & 63, y = (ent >> 6) & 63;
+                const uint32_t ent = queue[i];
+                const int x = ent & 63, y = ent >> 6;
                 const uint8_t *p = tile + (y + 3) * kTP + (x + 3 + xoff);
                 const int v = p[0];
-                int e[16];
-                e[0] = p[3 * kTP];      e[1] = p[3 * kTP + 1];   e[2] = p[2 * kTP + 2];    e[3] = p[kTP + 3];
-                e[4] = p[3];            e[5] = p[-kTP + 3];      e[6] = p[-2 * kTP + 2];   e[7] = p[-3 * kTP + 1];
-                e[8] = p[-3 * kTP];     e[9] = p[-3 * kTP - 1];  e[10] = p[-2 * kTP - 2];  e[11] = p[-kTP - 3];
-                e[12] = p[-3];          e[13] = p[kTP - 3];      e[14] = p[2 * kTP - 2];   e[15] = p[3 * kTP - 1];
-                int best = -512;
-                if (!dark) best = arc9_maxmin(e) - v;
-                if (dark || (ent & 0x1000u)) best = max(best, v - arc9_minmax(e));
+                uint32_t e[16];
+                e[0] = pack_pm(p[3 * kTP]);      e[1] = pack_pm(p[3 * kTP + 1]);   e[2] = pack_pm(p[2 * kTP + 2]);    e[3] = pack_pm(p[kTP + 3]);
+                e[4] = pack_pm(p[3]);            e[5] = pack_pm(p[-kTP + 3]);      e[6] = pack_pm(p[-2 * kTP + 2]);   e[7] = pack_pm(p[-3 * kTP + 1]);
+                e[8] = pack_pm(p[-3 * kTP]);     e[9] = pack_pm(p[-3 * kTP - 1]);  e[10] = pack_pm(p[-2 * kTP - 2]);  e[11] = pack_pm(p[-kTP - 3]);
+                e[12] = pack_pm(p[-3]);          e[13] = pack_pm(p[kTP - 3]);      e[14] = pack_pm(p[2 * kTP - 2]);   e[15] = pack_pm(p[3 * kTP - 1]);
+                const uint32_t both = arc9_both(e);
+                // low half: max_arcs(min_arc e);  high half: 255 - min_arcs(max_arc e)
+                const int best = max((int)(both & 0xffffu) - v, (int)(both >> 16) + v - 255);
                 if (best > th)                            // corner at th; cornerScore = best - 1 >= th
                     score[(y + 1) * kSP + (x + 1)] = (uint8_t)(best - 1);
             }
@@ -215,8 +197,8 @@ k_fast_cells(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr,
         // ---- phase C: strict 3x3 NMS inside the cell; walks the same queue (non-corners have score 0) ----
         bool mine_any = false;
         for (int i = lane; i < nq; i += 32) {
-            const uint32_t ent = queue[i >= nb ? qlast - (i - nb) : i];
-            const int x = ent & 63, y = (ent >> 6) & 63;
+            const uint32_t ent = queue[i];
+            const int x = ent & 63, y = ent >> 6;
             const uint8_t *q = score + (y + 1) * kSP + (x + 1);
             const int s = q[0];
             if (s == 0) continue;                         // every stored score is >= th >= 1
@@ -264,7 +246,10 @@ void launch_fast(const Geo &g, const DevBuffers &b, int nframes, cudaStream_t s)
     for (int l = 0; l < g.nlevels; ++l) if (g.lv[l].nCols > 0) { mw = mw > g.lv[l].wCell ? mw : g.lv[l].wCell; mh = mh > g.lv[l].hCell ? mh : g.lv[l].hCell; }
     auto up16 = [](int v) { return (v + 15) / 16 * 16; };
     FastSmem sm;
-    sm.tp = (mw + 6 + 15 + 15) / 16 * 16; sm.sp = (mw + 2 + 3) / 4 * 4; sm.tile_rows = mh + 6;
+    sm.tp = (mw + 6 + 7 + 7) / 8 * 8;                     // cell + 7 bytes of alignment slack, in 8-byte vectors ...
+    if ((sm.tp & 15) == 0) sm.tp += 8;                   // ... and an odd number of them (bank spread, see the file header)
+    if (sm.tp < 56) sm.tp = 56;
+    sm.sp = (mw + 2 + 3) / 4 * 4; sm.tile_rows = mh + 6;
     sm.npix_max = (mw * mh + 1) / 2 * 2;
     sm.off_score = up16(sm.tile_rows * sm.tp);
     sm.off_bm = sm.off_score + up16((mh + 2) * sm.sp);
@@ -278,9 +263,9 @@ void launch_fast(const Geo &g, const DevBuffers &b, int nframes, cudaStream_t s)
     const size_t bytes = (size_t)sm.per_warp * kFastWarps;
     dim3 grd((g.total_cells + kFastWarps - 1) / kFastWarps, nframes);
     // per-device function attribute; a handful of nanoseconds, so no process-wide caching (one handle per device each)
-    if (sm.tp == 64) {
-        if (bytes > 48 * 1024) cudaFuncSetAttribute(k_fast_cells<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        k_fast_cells<64><<<grd, kFastThreads, bytes, s>>>(g, b.pyr, b.cell_count, b.cell_slots, b.cell_tab, sm);
+    if (sm.tp == 56) {
+        if (bytes > 48 * 1024) cudaFuncSetAttribute(k_fast_cells<56>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        k_fast_cells<56><<<grd, kFastThreads, bytes, s>>>(g, b.pyr, b.cell_count, b.cell_slots, b.cell_tab, sm);
     } else {
         if (bytes > 48 * 1024) cudaFuncSetAttribute(k_fast_cells<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         k_fast_cells<0><<<grd, kFastThreads, bytes, s>>>(g, b.pyr, b.cell_count, b.cell_slots, b.cell_tab, sm);
