@@ -72,6 +72,9 @@ typedef struct orbm_matcher orbm_matcher;
 const char *orbx_strerror(int code);
 const char *orbx_last_cuda_error(void);
 int orbx_version(void);
+/* 16 hex digits identifying the kernel sources this library was built from (sha256 of csrc + orbx.h); profiles record it so
+ * that bench.py only quotes ncu counters captured on the same object code */
+const char *orbx_build_id(void);
 /* number of visible CUDA devices with compute capability 10.x (0 if none / no driver) */
 int orbx_device_count(void);
 

@@ -30,6 +30,17 @@ def build(force=False):
     return _SO
 
 
+def build_variant(out_dir, tag, flags):
+    """The same restatement compiled with other optimisation flags ON THE BOX THAT RUNS IT (bench.py's cpu_baseline leg:
+    -O2 as the reference's default build would, and -O3 -march=native) -- a timing aid, never a checker."""
+    so = os.path.join(out_dir, "liborb_oracle_%s.so" % tag)
+    subprocess.check_call(["gcc"] + list(flags) + ["-fno-math-errno", "-ffp-contract=off", "-fPIC", "-std=gnu11", "-shared",
+                                                   "-o", so, os.path.join(_HERE, "orb_oracle.c"), "-lm", "-lpthread"], cwd=_HERE)
+    L = C.CDLL(so)
+    L.orbo_knn2_mt.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    return L
+
+
 _lib = None
 
 

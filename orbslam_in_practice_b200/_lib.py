@@ -19,7 +19,7 @@ CAND_DTYPE = np.dtype([("x", "<i2"), ("y", "<i2"), ("score", "<i4")])
 
 # every symbol include/orbx.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
-    "orbx_strerror", "orbx_last_cuda_error", "orbx_version", "orbx_device_count",
+    "orbx_strerror", "orbx_last_cuda_error", "orbx_version", "orbx_build_id", "orbx_device_count",
     "orbx_create", "orbx_destroy", "orbx_nlevels", "orbx_capacity", "orbx_tables",
     "orbx_extract_host", "orbx_extract_host_begin", "orbx_extract_host_end", "orbx_extract_device", "orbx_set_pyramid_border", "orbx_set_device_split", "orbx_set_input_format", "orbx_undistort_keypoints_device",
     "orbx_level_dims", "orbx_download_level", "orbx_level_device_ptr",
@@ -81,6 +81,7 @@ def load():
     L.orbx_strerror.restype = C.c_char_p
     L.orbx_strerror.argtypes = [i32]
     L.orbx_last_cuda_error.restype = C.c_char_p
+    L.orbx_build_id.restype = C.c_char_p
     L.orbx_create.argtypes = [C.POINTER(Params), i32, i32, i32, i32, C.POINTER(vp)]
     L.orbx_destroy.argtypes = [vp]
     L.orbx_nlevels.argtypes = [vp]
@@ -130,6 +131,10 @@ def load():
     L.orbm_search_init_device.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, vp, i32, f32, i32, i32, i32, i32, vp, sz, vp]
     _lib = L
     return L
+
+
+def build_id():
+    return load().orbx_build_id().decode()
 
 
 def check(rc):

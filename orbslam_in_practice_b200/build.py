@@ -19,11 +19,21 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def source_id():
+    """sha256 over the kernel sources and the ABI header: the library reports it as orbx_build_id()."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(os.listdir(CSRC)) + [os.path.join("..", "..", "include", "orbx.h")]:
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(f.encode()); h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
+    cmd = [nvcc] + NVCC_FLAGS + ['-DORBX_BUILD_ID="%s"' % source_id()] + (["-Xptxas", "-v"] if verbose else []) + \
           ["-o", SO] + [os.path.join(CSRC, f) for f in SOURCES]
     subprocess.check_call(cmd, cwd=HERE)
     return SO
@@ -38,11 +48,23 @@ def build_cpp(force=False):
     srcs = [os.path.join(CPP_DIR, f) for f in ("ORBextractor.cc", "ORBmatcher.cc")]
     deps = srcs + [os.path.join(CPP_DIR, f) for f in ("ORBextractor.h", "ORBmatcher.h", "cv_compat.h")] + [SO]
     if not force and os.path.exists(FRONTEND_SO) and all(os.path.getmtime(FRONTEND_SO) >= os.path.getmtime(d) for d in deps):
+        if not os.path.exists(os.path.join(os.path.dirname(HERE), "tools", "_build", "cpp_latency")):
+            build_tools()
         return FRONTEND_SO
     cmd = ["g++", "-std=c++14", "-O2", "-fPIC", "-shared", "-Wall", "-I", CPP_DIR, "-o", FRONTEND_SO] + srcs + \
           ["-L", HERE, "-lorbx", "-Wl,-rpath,$ORIGIN"]
     subprocess.check_call(cmd, cwd=HERE)
+    build_tools()
     return FRONTEND_SO
+
+
+def build_tools():
+    """tools/_build/cpp_latency: the C++ class timed one frame per call (bench.py's `latency.cpp_operator_call`)."""
+    root = os.path.dirname(HERE)
+    out = os.path.join(root, "tools", "_build")
+    os.makedirs(out, exist_ok=True)
+    subprocess.check_call(["g++", "-std=c++14", "-O2", "-I", CPP_DIR, "-o", os.path.join(out, "cpp_latency"),
+                           os.path.join(root, "tools", "cpp_latency.cpp"), "-L", HERE, "-lorbslam_frontend", "-lorbx", "-Wl,-rpath," + HERE])
 
 
 if __name__ == "__main__":

@@ -95,6 +95,10 @@ extern "C" const char *orbx_strerror(int code)
 }
 extern "C" const char *orbx_last_cuda_error(void) { return g_cuda_err; }
 extern "C" int orbx_version(void) { return 100; }
+#ifndef ORBX_BUILD_ID
+#define ORBX_BUILD_ID "unknown"
+#endif
+extern "C" const char *orbx_build_id(void) { return ORBX_BUILD_ID; }
 
 extern "C" int orbx_device_count(void)
 {

@@ -33,7 +33,7 @@ def step():
 for _ in range(a.warm + 1):
     step()
 torch.cuda.synchronize()
-print("keypoints:", int(d_c.sum().item()), "launches:", ex.launches)
+print("keypoints:", int(d_c.sum().item()), "launches:", ex.launches, "build_id:", _lib.build_id())
 if a.steps:
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

@@ -1,6 +1,6 @@
 """Regenerate the tracked profile artefacts from scratch captures.
 
-  profile_artifacts.py traffic <full.ncu-rep> <out.json> [frames_in_capture frames_per_step]
+  profile_artifacts.py traffic <full.ncu-rep> <out.json> [frames_in_capture frames_per_step] [--build-id=ID]
       per-stage DRAM bytes and warp instructions of one step (bench.py reads this for roofline.traffic).  When the
       capture covers only part of a step (the device path runs a batch as two halves), pass the frame counts and the
       sums are scaled to a full step.
@@ -18,7 +18,7 @@ def stage_of(name):
     return STAGE.get(base)
 
 
-def traffic(rep, out, scale=1.0):
+def traffic(rep, out, scale=1.0, build_id=None):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
@@ -37,6 +37,7 @@ def traffic(rep, out, scale=1.0):
         w[st] += float(r[ci["smsp__inst_executed.sum"]].replace(",", ""))
     doc = {"source": "%s (ncu --set full --clock-control none); dram__bytes_read.sum + dram__bytes_write.sum and "
                      "smsp__inst_executed.sum summed over the stage's launches, scaled x%.3g to one full step" % (rep, scale),
+           "build_id": build_id,   # orbx_build_id() of the library that was profiled (printed by tools/prof_step.py)
            "bytes_per_step": {k: v * scale for k, v in b.items()},
            "launches": {k: int(v) for k, v in n.items()},
            "warp_instructions_per_step": {k: v * scale for k, v in w.items()}}
@@ -73,7 +74,9 @@ def launches(csv_path, out, cmd):
 
 if __name__ == "__main__":
     if sys.argv[1] == "traffic":
-        sc = float(sys.argv[5]) / float(sys.argv[4]) if len(sys.argv) > 5 else 1.0
-        traffic(sys.argv[2], sys.argv[3], sc)
+        args = [a for a in sys.argv[2:] if not a.startswith("--build-id=")]
+        bid = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--build-id=")), None)
+        sc = float(args[3]) / float(args[2]) if len(args) > 3 else 1.0
+        traffic(args[0], args[1], sc, bid)
     else:
         launches(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "")
