@@ -309,6 +309,8 @@ static int build_geometry(const orbx_extractor *ex, int w, int h, Geo &g, std::v
         }
     }
     g.total_cells = cell_off;
+    g.oct_node_cap_max = 0;
+    for (int l = 0; l < g.nlevels; ++l) g.oct_node_cap_max = std::max(g.oct_node_cap_max, g.lv[l].node_cap);
     g.capacity = kept_off; g.kept_total = kept_off;
     g.slots_per_frame = slot_off; g.keys_per_frame = key_off;
     g.pyr_frame_total = pyr_off; g.blur_frame_total = blur_off;

@@ -21,10 +21,14 @@
 // "equal sizes: later-created node first" (= the reference under a monotonic allocator).
 #include "orbx_internal.cuh"
 
+#include <cstdlib>
+
 namespace orbx {
 
 constexpr int kOctMaxThreads = 1024;          // block size is chosen per geometry: 256 (VGA-sized problems) or 1024 (4K)
 constexpr int kOctMaxWarps = kOctMaxThreads / 32;
+constexpr int kOctKeyBytes = 4 + 4 + 4 + 2 + 2 + 1;   // per key in shared memory: two key arrays, own-quadrant rank, two node arrays, quadrant
+int octree_smem_keys(const Geo &g);
 
 struct __align__(16) Node {
     short x0, y0, x1, y1;
@@ -34,7 +38,7 @@ struct __align__(16) Node {
 struct OctShared {
     int warp_i[kOctMaxWarps + 1];
     uint4 warp_v[kOctMaxWarps + 1];
-    int size, n, nsplit, C, U, nToExpand, J, pending;
+    int n, nsplit, C, U, nToExpand, J, pending;
 };
 
 __device__ __forceinline__ int warp_incl_scan(int v)
@@ -74,10 +78,10 @@ __device__ __forceinline__ int quadrant(uint32_t key, const Node &nd)
 __device__ __forceinline__ uint32_t comp(const uint4 &v, int q) { return q == 0 ? v.x : q == 1 ? v.y : q == 2 ? v.z : v.w; }
 
 template <int kOctThreads>
-__global__ void __launch_bounds__(kOctThreads, kOctThreads == 256 ? 6 : 1)   // latency-bound: favour resident blocks over registers
+__global__ void __launch_bounds__(kOctThreads, kOctThreads == 256 ? 5 : 1)   // latency-bound: favour resident blocks over registers
 k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, const uint32_t *__restrict__ cell_slots,
          uint32_t *keysA_all, uint32_t *keysB_all, uint16_t *nodeA_all, uint16_t *nodeB_all, uint4 *scanE_all,
-         int *__restrict__ ncand_out, uint32_t *__restrict__ kept_out, int *__restrict__ nkept_out)
+         int *__restrict__ ncand_out, uint32_t *__restrict__ kept_out, int *__restrict__ nkept_out, const int smem_keys)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ OctShared S;
@@ -97,6 +101,11 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
     int *ubase = arr + NC;                                  // [NC]
     unsigned char *nonEmpty = reinterpret_cast<unsigned char *>(ubase + NC); // [NC]
     unsigned char *split = nonEmpty + NC;                   // [NC]
+    // key arrays of problems with at most smem_keys candidates live in shared memory (ncu, round 2: every sweep of a pass is a
+    // dependent round trip to L2 on 1 000 keys -- long-scoreboard stalls behind 4.75 barrier stalls per issue); larger
+    // problems keep them in global memory.  The carve-up is sized with the LAUNCH's largest node_cap (see octree_smem_bytes).
+    unsigned char *key_smem = smem_raw + (size_t)g.oct_node_cap_max * (2 * sizeof(Node) + 4 * 4 * 2 + 16 + 3 * 4 + 2);
+    key_smem += (16 - ((size_t)key_smem & 15)) & 15;
 
     uint32_t *kA = keysA_all + (size_t)f * g.keys_per_frame + L.key_base;
     uint32_t *kB = keysB_all + (size_t)f * g.keys_per_frame + L.key_base;
@@ -127,6 +136,11 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
         }
         if (tid == 0) { S.n = carry; ncand_out[f * g.nlevels + level] = carry; }
         __syncthreads();
+        if (S.n <= smem_keys) {
+            kA = reinterpret_cast<uint32_t *>(key_smem); kB = kA + smem_keys; E32 = kB + smem_keys;
+            nA = reinterpret_cast<uint16_t *>(E32 + smem_keys); nB = nA + smem_keys;
+            qbuf = reinterpret_cast<unsigned char *>(nB + smem_keys);
+        }
         // eight lanes per cell (a cell holds ~4 candidates): four cells per warp pass instead of one, so a warp walks
         // a quarter as many dependent count -> slot load chains
         for (int c = tid >> 3; c < nCells; c += kOctThreads >> 3) {
@@ -144,6 +158,7 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
     // counters, so a sweep over all keys costs two block barriers instead of two per 256 keys
     const int seg = (((n + kOctWarps - 1) / kOctWarps) + 31) & ~31;
     const int s0 = min(n, warp * seg), s1 = min(n, s0 + seg);
+    int cur_size = 0;                                      // nodes in the list (lNodes.size()), kept in a register by every thread
     {
         const float hX = L.hX;
         int placed = 0, nroots = 0;
@@ -191,14 +206,13 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
             placed = off3 + tot.w;
             __syncthreads();
         }
-        if (tid == 0) S.size = nroots;
-        __syncthreads();
+        cur_size = nroots;                                 // block-uniform: every thread derived it from the same totals
     }
 
     bool phase2 = false;
 #pragma unroll 1
     for (;;) {
-        const int size = S.size;
+        const int size = cur_size;
         const int prevSize = size;
 
         // ---- A: stable rank of every key inside its future child (warp-streaming scan, see above) ----
@@ -216,8 +230,9 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
                 c2 += __popc(__ballot_sync(0xffffffffu, q == 2)); c3 += __popc(__ballot_sync(0xffffffffu, q == 3));
             }
             if (lane == 0) S.warp_v[warp] = make_uint4(c0, c1, c2, c3);
-            if (tid == 0) { S.nToExpand = 0; S.J = 0x7fffffff; S.pending = 0; }
+            if (tid == 0) { S.J = 0x7fffffff; S.pending = 0; }
             __syncthreads();
+            if (tid == 0) S.nToExpand = 0;                 // behind a barrier: the previous pass's tail may still be reading it
             uint4 run = make_uint4(0, 0, 0, 0);
             for (int w = 0; w < warp; ++w) run = add4(run, S.warp_v[w]);
             for (int p0 = s0; p0 < s1; p0 += 32) {
@@ -304,26 +319,20 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
         for (int gi = tid; gi < size; gi += kOctThreads) if (split[gi]) arr[rank[gi]] = nonEmpty[gi];
         __syncthreads();
         {
+            // one packed scan gives both: low half = children created before processing rank i, high half = untouched
+            // nodes in front of list position i (sums stay below 2^16: node_cap < 65536, checked at geometry build)
             int carry = 0;
-            for (int base = 0; base < nsplit; base += kOctThreads) {
-                const int r = base + tid;
-                const int v = r < nsplit ? arr[r] : 0;
+            const int span = nsplit > size ? nsplit : size;
+            for (int base = 0; base < span; base += kOctThreads) {
+                const int i = base + tid;
+                const int v = (i < nsplit ? arr[i] : 0) | ((i < size ? !split[i] : 0) << 16);
                 int tot;
-                const int ex = block_excl_scan<kOctWarps>(v, S, tot);
-                if (r < nsplit) arr[r] = carry + ex;
+                const int ex = carry + block_excl_scan<kOctWarps>(v, S, tot);
+                if (i < nsplit) arr[i] = ex & 0xffff;
+                if (i < size) ubase[i] = ex >> 16;
                 carry += tot;
             }
-            if (tid == 0) S.C = carry;
-            int ucarry = 0;
-            for (int base = 0; base < size; base += kOctThreads) {
-                const int gi = base + tid;
-                const int fl = gi < size ? !split[gi] : 0;
-                int tot;
-                const int ex = block_excl_scan<kOctWarps>(fl, S, tot);
-                if (gi < size) ubase[gi] = ucarry + ex;
-                ucarry += tot;
-            }
-            if (tid == 0) S.U = ucarry;
+            if (tid == 0) { S.C = carry & 0xffff; S.U = carry >> 16; }
             __syncthreads();
         }
         const int C = S.C, U = S.U;
@@ -379,16 +388,14 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
         __syncthreads();
         { uint32_t *t = kA; kA = kB; kB = t; uint16_t *u = nA; nA = nB; nB = u; Node *v = nodes; nodes = nodesN; nodesN = v; }
         const int newSize = C + U;
-        const int nToExpand = S.nToExpand;
-        __syncthreads();
-        if (tid == 0) S.size = newSize;
-        __syncthreads();
+        const int nToExpand = S.nToExpand;                 // reset only behind the next pass's first barrier
+        cur_size = newSize;
         if (newSize >= N || newSize == prevSize) break;                 // :621-624 / :688
         if (!phase2 && newSize + nToExpand * 3 > N) phase2 = true;      // :626
     }
 
     // ---- :697-715 keep the best key of every node (first maximum wins), list order ----
-    const int size = S.size;
+    const int size = cur_size;
     uint32_t *kept = kept_out + (size_t)f * g.kept_total + L.kept_base;
     for (int gi = tid; gi < size && gi < L.kept_cap; gi += kOctThreads) {
         const Node nd = nodes[gi];
@@ -406,8 +413,29 @@ int octree_smem_bytes(const Geo &g)
 {
     int nc = 0;
     for (int l = 0; l < g.nlevels; ++l) nc = nc > g.lv[l].node_cap ? nc : g.lv[l].node_cap;
-    // 2 node tables + childCnt + newIdx (4 ints each) + rank + arr + ubase + 2 byte flags
-    return nc * (2 * (int)sizeof(Node) + 4 * 4 * 2 + 3 * 4 + 16 + 2) + 64;
+    // 2 node tables + childCnt + newIdx (4 ints each) + rank + arr + ubase + 2 byte flags, then the shared-memory key arrays
+    return nc * (2 * (int)sizeof(Node) + 4 * 4 * 2 + 3 * 4 + 16 + 2) + 64 + 16 + octree_smem_keys(g) * kOctKeyBytes;
+}
+
+// Candidates per problem that get shared-memory key arrays: about six candidates per kept feature of the largest level
+// (FAST delivers 4-6x the quota on textured frames), capped so that a few blocks still fit one SM.  Larger problems run
+// from global memory, so this is a performance knob, never a capacity limit.
+int octree_smem_keys(const Geo &g)
+{
+    int nmax = 0, big = 0;
+    for (int l = 0; l < g.nlevels; ++l) {
+        nmax = nmax > g.lv[l].N ? nmax : g.lv[l].N;
+        big = big > g.lv[l].regionW * g.lv[l].regionH ? big : g.lv[l].regionW * g.lv[l].regionH;
+    }
+    if (big > 1500000) return 0;                            // 4K-sized levels: tens of thousands of candidates, 1024-thread blocks
+    int k = (6 * nmax + 31) & ~31;
+    if (const char *e = std::getenv("ORBX_OCT_SMEM_KEYS")) k = std::atoi(e) & ~31;
+    k = k < 0 ? 0 : (k > 2048 ? 2048 : k);
+    // node tables that already fill most of an SM (one huge level) leave no room: such problems run from global memory
+    int nc = 0;
+    for (int l = 0; l < g.nlevels; ++l) nc = nc > g.lv[l].node_cap ? nc : g.lv[l].node_cap;
+    if ((size_t)nc * 94 + 80 + (size_t)k * kOctKeyBytes > 112 * 1024) k = 0;
+    return k;
 }
 
 int octree_configure(int smem_bytes)
@@ -425,10 +453,10 @@ void launch_octree(const Geo &g, const DevBuffers &b, int nframes, int smem_byte
     for (int l = 0; l < g.nlevels; ++l) big = big > g.lv[l].regionW * g.lv[l].regionH ? big : g.lv[l].regionW * g.lv[l].regionH;
     if (big > 1500000)
         k_octree<1024><<<grd, 1024, smem_bytes, s>>>(g, b.cell_count, b.cell_slots, b.keysA, b.keysB, b.nodeA, b.nodeB,
-                                                     b.scanE, b.ncand, b.kept, b.nkept);
+                                                     b.scanE, b.ncand, b.kept, b.nkept, 0);
     else
         k_octree<256><<<grd, 256, smem_bytes, s>>>(g, b.cell_count, b.cell_slots, b.keysA, b.keysB, b.nodeA, b.nodeB,
-                                                   b.scanE, b.ncand, b.kept, b.nkept);
+                                                   b.scanE, b.ncand, b.kept, b.nkept, octree_smem_keys(g));
 }
 
 } // namespace orbx

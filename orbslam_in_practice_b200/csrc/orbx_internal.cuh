@@ -64,6 +64,7 @@ struct Geo {
     int total_cells;          // cells per frame, all levels
     int capacity;             // output keypoint slots per frame
     int kept_total;           // kept slots per frame (= capacity)
+    int oct_node_cap_max;     // largest node_cap over the levels (sizes the octree's shared-memory carve-up)
     unsigned long long pyr_frame_total, blur_frame_total; // allocation sizes (bytes, all frames) of the pyramid / blur buffers
     unsigned long long slots_per_frame, keys_per_frame;
     LevelGeom lv[ORBX_MAX_LEVELS];
