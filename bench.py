@@ -643,7 +643,10 @@ def measure_latency(_lib, torch, frame, local, calls=300):
     exe = os.path.join(ROOT, "tools", "_build", "cpp_latency")
     if os.path.exists(exe):
         try:
-            r = subprocess.run([exe, str(W), str(H), str(NFEAT), str(calls), str(local)], capture_output=True, text=True, timeout=120)
+            import tempfile
+            with tempfile.NamedTemporaryFile(suffix=".raw") as tf:
+                tf.write(np.ascontiguousarray(frame).tobytes()); tf.flush()
+                r = subprocess.run([exe, str(W), str(H), str(NFEAT), str(calls), str(local), tf.name], capture_output=True, text=True, timeout=120)
             out["cpp_operator_call"] = json.loads(r.stdout.strip().splitlines()[-1])
         except Exception as e:
             out["cpp_operator_call"] = {"error": str(e)[:120]}

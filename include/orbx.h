@@ -113,6 +113,12 @@ int orbx_extract_device(orbx_extractor *ex, const uint8_t *d_imgs, size_t row_pi
                         int width, int height, int nframes,
                         orbx_keypoint *d_kps, uint8_t *d_desc, int32_t *d_counts, void *stream);
 
+/* Small batches (<= 8 frames; the reference's caller passes ONE frame per call, src/Frame.cpp:75-78) take a low-latency
+ * path by default: the call's kernels are replayed as a CUDA graph whose nodes follow the real dependencies (FAST + octree
+ * of level l start as soon as level l of the resize chain exists), and the host entry points use one stream, pinned
+ * staging for pageable caller buffers and one download.  Results are identical.  enabled = 0 restores the stream path. */
+int orbx_set_low_latency(orbx_extractor *ex, int enabled);
+
 /* Input pixel format of the following extract calls: channels = 1 (gray, default), 3 or 4 interleaved 8-bit
  * channels; rgb_order = 0 for BGR(A), 1 for RGB(A).  Colour input is converted to gray inside the level-0 kernel with
  * OpenCV's 8U fixed point (R*9798 + G*19235 + B*3735 + 16384) >> 15, replacing the cv::cvtColor call in front of the

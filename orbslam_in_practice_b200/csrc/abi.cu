@@ -78,7 +78,22 @@ struct orbx_extractor {
     static const int kProfCalls = 64;            // event sets kept (ring) while profiling
     cudaEvent_t ev[kProfCalls][ORBX_NUM_STAGES + 1];
     int prof_calls;                              // calls recorded since profiling was enabled
+    // ---- low-latency path for small batches (the reference's call pattern is ONE frame per call, src/Frame.cpp:75-78) ----
+    // The kernels of a call are replayed as a CUDA graph whose nodes follow the real dependencies: FAST + octree of level l
+    // hang off level l of the resize chain (not off its end), the blur off the chain's end, describe joins everything.
+    struct LatGraph {
+        cudaGraphExec_t exec; int launches;
+        const void *imgs, *kps, *desc, *counts; size_t pitch, fstride; int w, h, n, ch, rgb, border;
+    };
+    LatGraph lat[2];                             // [0] host entry points (handle-owned staging / outputs), [1] orbx_extract_device
+    int low_latency, lat_warm;
+    cudaStream_t s_cap;                          // capture origin (the graph is replayed on the call's stream)
+    cudaStream_t s_branch[ORBX_MAX_LEVELS];
+    cudaEvent_t ev_lvl[ORBX_MAX_LEVELS], ev_lvl_done[ORBX_MAX_LEVELS];
+    uint8_t *pin_in, *pin_out; size_t pin_in_bytes, pin_out_bytes;   // pinned staging for pageable caller buffers / the single D2H
+    struct { int active, n; orbx_keypoint *kps; uint8_t *desc; int32_t *counts; } lat_pending;   // copy-out owed by _end
 };
+static const int kLatMaxFrames = 8;
 
 extern "C" const char *orbx_strerror(int code)
 {
@@ -379,6 +394,11 @@ extern "C" int orbx_create(const orbx_params *p, int max_width, int max_height, 
     ex->launches = 0; ex->last_frames = 0; ex->border_on = 0; ex->in_channels = 1; ex->in_rgb = 0;
     ex->staging_color = nullptr; ex->staging_color_bytes = 0; ex->profiling = 0; ex->prof_calls = 0;
     for (auto &set : ex->ev) for (auto &e : set) e = nullptr;
+    std::memset(ex->lat, 0, sizeof(ex->lat)); ex->low_latency = 1; ex->lat_warm = 0; ex->s_cap = nullptr;
+    if (const char *e = std::getenv("ORBX_LOW_LATENCY")) ex->low_latency = std::atoi(e) != 0;
+    for (int i = 0; i < ORBX_MAX_LEVELS; ++i) { ex->s_branch[i] = nullptr; ex->ev_lvl[i] = nullptr; ex->ev_lvl_done[i] = nullptr; }
+    ex->pin_in = ex->pin_out = nullptr; ex->pin_in_bytes = ex->pin_out_bytes = 0;
+    std::memset(&ex->lat_pending, 0, sizeof(ex->lat_pending));
     std::memset(&ex->buf, 0, sizeof(ex->buf));
     ex->stream = ex->stream2 = ex->s_h2d = ex->s_d2h = nullptr; ex->s_aux[0] = ex->s_aux[1] = nullptr; ex->fork_slot = 0;
     for (int i = 0; i < orbx_extractor::kMaxChunks; ++i) { ex->ev_h2d[i] = nullptr; ex->ev_done[i] = nullptr; ex->ev_fork[i] = nullptr; ex->ev_join[i] = nullptr; }
@@ -425,9 +445,13 @@ extern "C" int orbx_create(const orbx_params *p, int max_width, int max_height, 
     TRY(dev_alloc(ex, &b.kept, F * g.kept_total));
     TRY(dev_alloc(ex, &b.nkept, F * g.nlevels));
     TRY(dev_alloc(ex, &b.staging, F * (size_t)max_width * max_height));
-    TRY(dev_alloc(ex, &b.out_kps, F * g.capacity));
-    TRY(dev_alloc(ex, &b.out_desc, F * g.capacity * 32));
-    TRY(dev_alloc(ex, &b.out_counts, F));
+    {   // outputs of the host path as ONE block [kps | desc | counts]: a full batch goes back in a single D2H copy
+        uint8_t *blk = nullptr;
+        TRY(dev_alloc(ex, &blk, F * g.capacity * (sizeof(orbx_keypoint) + 32) + F * sizeof(int)));
+        b.out_kps = reinterpret_cast<orbx_keypoint *>(blk);
+        b.out_desc = blk + F * g.capacity * sizeof(orbx_keypoint);
+        b.out_counts = reinterpret_cast<int *>(b.out_desc + F * g.capacity * 32);
+    }
 #undef TRY
     rc = upload_geometry(ex, max_width, max_height);
     if (rc) { orbx_destroy(ex); return rc; }
@@ -446,6 +470,15 @@ extern "C" int orbx_destroy(orbx_extractor *ex)
     if (ex->s_d2h) cudaStreamDestroy(ex->s_d2h);
     for (int i = 0; i < orbx_extractor::kMaxChunks; ++i) { if (ex->ev_h2d[i]) cudaEventDestroy(ex->ev_h2d[i]); if (ex->ev_done[i]) cudaEventDestroy(ex->ev_done[i]);
         if (ex->ev_fork[i]) cudaEventDestroy(ex->ev_fork[i]); if (ex->ev_join[i]) cudaEventDestroy(ex->ev_join[i]); }
+    for (auto &lg : ex->lat) if (lg.exec) cudaGraphExecDestroy(lg.exec);
+    for (int i = 0; i < ORBX_MAX_LEVELS; ++i) {
+        if (ex->s_branch[i]) cudaStreamDestroy(ex->s_branch[i]);
+        if (ex->ev_lvl[i]) cudaEventDestroy(ex->ev_lvl[i]);
+        if (ex->ev_lvl_done[i]) cudaEventDestroy(ex->ev_lvl_done[i]);
+    }
+    if (ex->s_cap) cudaStreamDestroy(ex->s_cap);
+    if (ex->pin_in) cudaFreeHost(ex->pin_in);
+    if (ex->pin_out) cudaFreeHost(ex->pin_out);
     for (void *p : ex->allocs) cudaFree(p);
     if (ex->staging_color) cudaFree(ex->staging_color);
     if (ex->ev_split_fork) cudaEventDestroy(ex->ev_split_fork);
@@ -559,6 +592,90 @@ static int run_pipeline(orbx_extractor *ex, const uint8_t *d_imgs, size_t pitch,
     return ORBX_OK;
 }
 
+// The same kernels as run_pipeline with the dependencies a single small batch really has: level l's FAST + octree start as
+// soon as level l exists.  Issued on `s` and the handle's branch streams; meant to be stream-captured into a graph (the
+// event record / wait pairs become graph edges).  Critical path of one VGA frame: level0 -> resize chain -> FAST_7 ->
+// octree_7 -> describe, with the large levels' octrees (the longest kernels) running beside the chain.
+static int run_pipeline_dag(orbx_extractor *ex, const uint8_t *d_imgs, size_t pitch, size_t fstride, int nframes,
+                            orbx_keypoint *d_kps, uint8_t *d_desc, int *d_counts, cudaStream_t s, int *nlaunch)
+{
+    Geo g = ex->geo;
+    g.frame0 = 0; g.in_channels = ex->in_channels; g.in_rgb = ex->in_rgb;
+    int launches = 0;
+    launch_level0(g, ex->buf, d_imgs, pitch, fstride, nframes, s); ++launches;
+    for (int l = 0; l < g.nlevels; ++l) {
+        if (l) { launch_resize(g, ex->buf, l, nframes, s); ++launches; }
+        cudaStream_t br = ex->s_branch[l];
+        CK(cudaEventRecord(ex->ev_lvl[l], s));
+        CK(cudaStreamWaitEvent(br, ex->ev_lvl[l], 0));
+        if (g.lv[l].nCols * g.lv[l].nRows > 0) { launch_fast(g, ex->buf, nframes, br, l, l + 1); ++launches; }
+        launch_octree(g, ex->buf, nframes, ex->oct_smem, br, l, l + 1); ++launches;
+        CK(cudaEventRecord(ex->ev_lvl_done[l], br));
+    }
+    launch_blur(g, ex->buf, nframes, s); ++launches;
+    for (int l = 0; l < g.nlevels; ++l) CK(cudaStreamWaitEvent(s, ex->ev_lvl_done[l], 0));
+    launch_describe(g, ex->buf, nframes, d_kps, d_desc, d_counts, s); ++launches;
+    CK(cudaGetLastError());
+    *nlaunch = launches;
+    return ORBX_OK;
+}
+
+static int lat_resources(orbx_extractor *ex)
+{
+    for (int i = 0; i < ex->params.nlevels; ++i) {
+        if (!ex->s_branch[i]) CK(cudaStreamCreateWithFlags(&ex->s_branch[i], cudaStreamNonBlocking));
+        if (!ex->ev_lvl[i]) CK(cudaEventCreateWithFlags(&ex->ev_lvl[i], cudaEventDisableTiming));
+        if (!ex->ev_lvl_done[i]) CK(cudaEventCreateWithFlags(&ex->ev_lvl_done[i], cudaEventDisableTiming));
+    }
+    if (!ex->s_cap) CK(cudaStreamCreateWithFlags(&ex->s_cap, cudaStreamNonBlocking));
+    return ORBX_OK;
+}
+
+// Graph of one call's kernels for exactly these buffers and this geometry; rebuilt when anything in the key changes.
+// Returns ORBX_OK with slot.exec == nullptr if graphs are unusable here (the caller then takes the stream path).
+static int lat_graph_ensure(orbx_extractor *ex, int which, const uint8_t *d_imgs, size_t pitch, size_t fstride, int w, int h, int n,
+                            orbx_keypoint *d_kps, uint8_t *d_desc, int *d_counts, cudaStream_t user_stream)
+{
+    orbx_extractor::LatGraph &lg = ex->lat[which];
+    if (lg.exec && lg.imgs == d_imgs && lg.kps == d_kps && lg.desc == d_desc && lg.counts == d_counts && lg.pitch == pitch &&
+        lg.fstride == fstride && lg.w == w && lg.h == h && lg.n == n && lg.ch == ex->in_channels && lg.rgb == ex->in_rgb && lg.border == ex->border_on)
+        return ORBX_OK;
+    if (lg.exec) { cudaGraphExecDestroy(lg.exec); lg.exec = nullptr; }
+    int rc = lat_resources(ex);
+    if (rc) return rc;
+    if (!ex->lat_warm) {
+        // one plain pass first: the launchers' one-time initialisation (table uploads, function attributes) must not
+        // happen inside a capture.  It runs on the caller's stream (ordered behind whatever produces the inputs or still
+        // uses the handle) and computes the same outputs the graph will overwrite.
+        rc = run_pipeline(ex, d_imgs, pitch, fstride, w, h, 0, n, d_kps, d_desc, d_counts, user_stream);
+        if (rc) return rc;
+        CK(cudaStreamSynchronize(user_stream));
+        CK(cudaStreamSynchronize(ex->s_aux[0])); CK(cudaStreamSynchronize(ex->s_aux[1]));
+        ex->lat_warm = 1;
+    }
+    cudaGraph_t graph = nullptr;
+    int nl = 0;
+    if (cudaStreamBeginCapture(ex->s_cap, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); ex->low_latency = 0; return ORBX_OK; }
+    rc = run_pipeline_dag(ex, d_imgs, pitch, fstride, n, d_kps, d_desc, d_counts, ex->s_cap, &nl);
+    const cudaError_t ce = cudaStreamEndCapture(ex->s_cap, &graph);
+    if (rc || ce != cudaSuccess || !graph) { cudaGetLastError(); if (graph) cudaGraphDestroy(graph); ex->low_latency = 0; return ORBX_OK; }
+    cudaGraphExec_t exec = nullptr;
+    const cudaError_t ie = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { cudaGetLastError(); ex->low_latency = 0; return ORBX_OK; }
+    lg.exec = exec; lg.launches = nl;
+    lg.imgs = d_imgs; lg.kps = d_kps; lg.desc = d_desc; lg.counts = d_counts; lg.pitch = pitch; lg.fstride = fstride;
+    lg.w = w; lg.h = h; lg.n = n; lg.ch = ex->in_channels; lg.rgb = ex->in_rgb; lg.border = ex->border_on;
+    return ORBX_OK;
+}
+
+extern "C" int orbx_set_low_latency(orbx_extractor *ex, int enabled)
+{
+    if (!ex) return ORBX_E_INVALID;
+    ex->low_latency = enabled ? 1 : 0;
+    return ORBX_OK;
+}
+
 extern "C" int orbx_extract_device(orbx_extractor *ex, const uint8_t *d_imgs, size_t row_pitch, size_t frame_stride,
                                    int width, int height, int nframes,
                                    orbx_keypoint *d_kps, uint8_t *d_desc, int32_t *d_counts, void *stream)
@@ -577,6 +694,17 @@ extern "C" int orbx_extract_device(orbx_extractor *ex, const uint8_t *d_imgs, si
     // instruction-issue bound at 65-77 % issue utilisation, and the halves' different kernels (and their tail waves)
     // fill each other's idle issue slots.  Profiling keeps one serial pass so that stage times stay attributable.
     int nsplit = (!ex->profiling && nframes >= 32) ? ex->device_split : 1;
+    if (ex->low_latency && !ex->profiling && nframes <= kLatMaxFrames) {
+        int rc = ensure_geometry(ex, width, height);
+        if (rc) return rc;
+        rc = lat_graph_ensure(ex, 1, d_imgs, row_pitch, frame_stride, width, height, nframes, d_kps, d_desc, d_counts, s);
+        if (rc) return rc;
+        if (ex->lat[1].exec) {
+            CK(cudaGraphLaunch(ex->lat[1].exec, s));
+            ex->launches += ex->lat[1].launches; ex->last_frames = nframes;
+            return ORBX_OK;
+        }
+    }
     if (nsplit <= 1) return run_pipeline(ex, d_imgs, row_pitch, frame_stride, width, height, 0, nframes, d_kps, d_desc, d_counts, s);
     CK(cudaEventRecord(ex->ev_split_fork, s));
     CK(cudaStreamWaitEvent(ex->stream2, ex->ev_split_fork, 0));
@@ -594,9 +722,85 @@ extern "C" int orbx_extract_host_end(orbx_extractor *ex)
 {
     if (!ex) return ORBX_E_INVALID;
     CK(cudaSetDevice(ex->device));
+    if (ex->lat_pending.active) {
+        // low-latency path: everything ran on ex->stream; hand the caller exactly counts[f] rows per frame
+        ex->lat_pending.active = 0;
+        CK(cudaStreamSynchronize(ex->stream));
+        const size_t cap = (size_t)ex->full.capacity; const int n = ex->lat_pending.n;
+        const orbx_keypoint *pk = reinterpret_cast<const orbx_keypoint *>(ex->pin_out);
+        const uint8_t *pd = ex->pin_out + (size_t)n * cap * sizeof(orbx_keypoint);
+        const int *pc = reinterpret_cast<const int *>(pd + (size_t)n * cap * 32);
+        for (int f = 0; f < n; ++f) {
+            int c = pc[f]; if (c < 0) c = 0; if ((size_t)c > cap) c = (int)cap;
+            ex->lat_pending.counts[f] = c;
+            std::memcpy(ex->lat_pending.kps + f * cap, pk + f * cap, (size_t)c * sizeof(orbx_keypoint));
+            std::memcpy(ex->lat_pending.desc + f * cap * 32, pd + f * cap * 32, (size_t)c * 32);
+        }
+        return ORBX_OK;
+    }
     CK(cudaStreamSynchronize(ex->s_d2h));
     CK(cudaStreamSynchronize(ex->stream));
     CK(cudaStreamSynchronize(ex->stream2));
+    return ORBX_OK;
+}
+
+static bool host_pinned(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+static int pin_ensure(uint8_t **buf, size_t *have, size_t need)
+{
+    if (*have >= need) return ORBX_OK;
+    if (*buf) { cudaFreeHost(*buf); *buf = nullptr; *have = 0; }
+    if (cudaHostAlloc((void **)buf, need, cudaHostAllocDefault) != cudaSuccess) { cuda_fail(cudaGetLastError(), "cudaHostAlloc"); return ORBX_E_NOMEM; }
+    *have = need;
+    return ORBX_OK;
+}
+
+// Small batches (<= kLatMaxFrames frames; the reference's caller passes ONE): a single stream, the upload, the kernel graph
+// and ONE download into handle-owned pinned memory.  Pageable caller images are first copied into pinned staging (a
+// cudaMemcpyAsync from pageable memory stages through the driver anyway, and synchronously).  Measured and rejected:
+// describe storing its rows straight into pinned host memory (no download node) -- 5 us slower for one frame, 40 % for eight.
+static int extract_host_small(orbx_extractor *ex, const uint8_t *imgs, size_t row_pitch, size_t frame_stride, int width, int height, int n,
+                              uint8_t *staging, orbx_keypoint *kps, uint8_t *desc, int32_t *counts, bool *taken)
+{
+    *taken = false;
+    const size_t C = (size_t)ex->in_channels, rbytes = (size_t)width * C, fbytes = rbytes * height, cap = (size_t)ex->full.capacity;
+    int rc = lat_graph_ensure(ex, 0, staging, rbytes, fbytes, width, height, n, ex->buf.out_kps, ex->buf.out_desc, ex->buf.out_counts, ex->stream);
+    if (rc) return rc;
+    if (!ex->lat[0].exec) return ORBX_OK;           // graphs unavailable: the caller falls through to the stream path
+    cudaStream_t s = ex->stream;
+    const uint8_t *src = imgs; size_t sp = row_pitch, sf = frame_stride;
+    if (!host_pinned(imgs)) {
+        rc = pin_ensure(&ex->pin_in, &ex->pin_in_bytes, (size_t)n * fbytes);
+        if (rc) return rc;
+        for (int f = 0; f < n; ++f) {
+            const uint8_t *fs = imgs + (size_t)f * frame_stride; uint8_t *fd = ex->pin_in + (size_t)f * fbytes;
+            if (row_pitch == rbytes) std::memcpy(fd, fs, fbytes);
+            else for (int y = 0; y < height; ++y) std::memcpy(fd + (size_t)y * rbytes, fs + (size_t)y * row_pitch, rbytes);
+        }
+        src = ex->pin_in; sp = rbytes; sf = fbytes;
+    }
+    if (sp == rbytes && (sf == fbytes || n == 1)) CK(cudaMemcpyAsync(staging, src, (size_t)n * fbytes, cudaMemcpyHostToDevice, s));
+    else for (int f = 0; f < n; ++f)
+        CK(cudaMemcpy2DAsync(staging + (size_t)f * fbytes, rbytes, src + (size_t)f * sf, sp, rbytes, (size_t)height, cudaMemcpyHostToDevice, s));
+    CK(cudaGraphLaunch(ex->lat[0].exec, s));
+    ex->launches += ex->lat[0].launches; ex->last_frames = n;
+    const size_t kb = (size_t)n * cap * sizeof(orbx_keypoint), db = (size_t)n * cap * 32, cb = (size_t)n * sizeof(int);
+    rc = pin_ensure(&ex->pin_out, &ex->pin_out_bytes, kb + db + cb);
+    if (rc) return rc;
+    if (n == ex->max_batch) {
+        CK(cudaMemcpyAsync(ex->pin_out, ex->buf.out_kps, kb + db + cb, cudaMemcpyDeviceToHost, s));    // the block is contiguous for a full batch
+    } else {
+        CK(cudaMemcpyAsync(ex->pin_out, ex->buf.out_kps, kb, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(ex->pin_out + kb, ex->buf.out_desc, db, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(ex->pin_out + kb + db, ex->buf.out_counts, cb, cudaMemcpyDeviceToHost, s));
+    }
+    ex->lat_pending.active = 1; ex->lat_pending.n = n; ex->lat_pending.kps = kps; ex->lat_pending.desc = desc; ex->lat_pending.counts = counts;
+    *taken = true;
     return ORBX_OK;
 }
 
@@ -635,6 +839,11 @@ extern "C" int orbx_extract_host_begin(orbx_extractor *ex, const uint8_t *imgs, 
     }
     int rc = ensure_geometry(ex, width, height);
     if (rc) return rc;
+    if (ex->low_latency && !ex->profiling && nframes <= kLatMaxFrames) {
+        bool taken = false;
+        rc = extract_host_small(ex, imgs, row_pitch, frame_stride, width, height, nframes, staging, kps, desc, counts, &taken);
+        if (rc || taken) return rc;
+    }
     // Chunked three-stream pipeline: the H2D copy of chunk c+1 and the D2H copy of chunk c-1 overlap
     // the kernels of chunk c (PCIe is full duplex; frames are independent).
     int nchunks = nframes >= 64 ? 4 : (nframes >= 8 ? 2 : 1);

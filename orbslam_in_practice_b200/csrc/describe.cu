@@ -393,14 +393,24 @@ void launch_describe(const Geo &g, const DevBuffers &b, int nframes, orbx_keypoi
         cudaMemcpy(m, h_tab, sizeof(h_tab), cudaMemcpyHostToDevice);
         g_desc_tab[dev].pattern = p; g_desc_tab[dev].moments = m;
     }
-    const int per_block = kDescWarps * kDescSlots;
+    // small batches (the low-latency path): two keypoints per warp instead of eight -- four times the warps, a quarter of
+    // the serial depth; the amortisation of the pattern load and the sincos only matters when the GPU is full anyway
+    const bool small = nframes <= 4;
+    const int per_block = kDescWarps * (small ? 2 : kDescSlots);
     dim3 grd((g.capacity + per_block - 1) / per_block, nframes);
     // measured on a B200 (256 VGA frames): the kernel is bound by the L1 data pipe, and a small L1 (the default carve-out
     // maximises shared memory: 28 KB of L1 left) costs 30 %; 164 KB of shared memory = 4 resident blocks and 92 KB of L1.
     // 48 registers (the 5-block launch bound) leave room for the other stream's kernels on the same SM.
     static bool configured[64] = {};
-    if (!configured[dev]) { cudaFuncSetAttribute(k_describe<5, kDescSlots>, cudaFuncAttributePreferredSharedMemoryCarveout, 72); configured[dev] = true; }
-    k_describe<5, kDescSlots><<<grd, kDescWarps * 32, 0, s>>>(g, b.pyr, b.blur, b.kept, b.nkept, d_kps, d_desc, d_counts, g_desc_tab[dev].pattern, g_desc_tab[dev].moments);
+    if (!configured[dev]) {
+        cudaFuncSetAttribute(k_describe<5, kDescSlots>, cudaFuncAttributePreferredSharedMemoryCarveout, 72);
+        cudaFuncSetAttribute(k_describe<5, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 72);
+        configured[dev] = true;
+    }
+    if (small)
+        k_describe<5, 2><<<grd, kDescWarps * 32, 0, s>>>(g, b.pyr, b.blur, b.kept, b.nkept, d_kps, d_desc, d_counts, g_desc_tab[dev].pattern, g_desc_tab[dev].moments);
+    else
+        k_describe<5, kDescSlots><<<grd, kDescWarps * 32, 0, s>>>(g, b.pyr, b.blur, b.kept, b.nkept, d_kps, d_desc, d_counts, g_desc_tab[dev].pattern, g_desc_tab[dev].moments);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -68,12 +68,13 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 template <int TP>
 __global__ void __launch_bounds__(kFastThreads)
 k_fast_cells(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr,
-             int *__restrict__ cell_count, uint32_t *__restrict__ cell_slots, const int4 *__restrict__ cell_tab, const FastSmem sm)
+             int *__restrict__ cell_count, uint32_t *__restrict__ cell_slots, const int4 *__restrict__ cell_tab, const FastSmem sm,
+             const int cell_lo, const int cell_hi)
 {
     extern __shared__ __align__(16) unsigned char fast_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int cell = blockIdx.x * kFastWarps + warp, f = blockIdx.y + g.frame0;
-    if (cell >= g.total_cells) return;
+    const int cell = cell_lo + blockIdx.x * kFastWarps + warp, f = blockIdx.y + g.frame0;   // [cell_lo, cell_hi): all cells, or one level's
+    if (cell >= cell_hi) return;
     unsigned char *mine = fast_smem + warp * sm.per_warp;
     uint8_t *tile = mine;                                                     // [tile_rows][tp]
     uint8_t *score = mine + sm.off_score;                                     // [tile_rows - 4][sp]
@@ -240,8 +241,13 @@ k_fast_cells(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr,
     if (lane == 0) *count_out = base;
 }
 
-void launch_fast(const Geo &g, const DevBuffers &b, int nframes, cudaStream_t s)
+void launch_fast(const Geo &g, const DevBuffers &b, int nframes, cudaStream_t s, int level_lo, int level_hi)
 {
+    // cells of levels [level_lo, level_hi); the default covers the whole pyramid in one launch
+    if (level_hi > g.nlevels) level_hi = g.nlevels;
+    const int cell_lo = g.lv[level_lo].cell_base;
+    const int cell_hi = level_hi >= g.nlevels ? g.total_cells : g.lv[level_hi].cell_base;
+    if (cell_hi <= cell_lo) return;
     int mw = 1, mh = 1;
     for (int l = 0; l < g.nlevels; ++l) if (g.lv[l].nCols > 0) { mw = mw > g.lv[l].wCell ? mw : g.lv[l].wCell; mh = mh > g.lv[l].hCell ? mh : g.lv[l].hCell; }
     auto up16 = [](int v) { return (v + 15) / 16 * 16; };
@@ -261,14 +267,14 @@ void launch_fast(const Geo &g, const DevBuffers &b, int nframes, cudaStream_t s)
     const int walk = ((mh + 7) / 8 * 8 + 7) * sm.tp;
     if (sm.per_warp < walk) sm.per_warp = up16(walk);
     const size_t bytes = (size_t)sm.per_warp * kFastWarps;
-    dim3 grd((g.total_cells + kFastWarps - 1) / kFastWarps, nframes);
+    dim3 grd((cell_hi - cell_lo + kFastWarps - 1) / kFastWarps, nframes);
     // per-device function attribute; a handful of nanoseconds, so no process-wide caching (one handle per device each)
     if (sm.tp == 56) {
         if (bytes > 48 * 1024) cudaFuncSetAttribute(k_fast_cells<56>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        k_fast_cells<56><<<grd, kFastThreads, bytes, s>>>(g, b.pyr, b.cell_count, b.cell_slots, b.cell_tab, sm);
+        k_fast_cells<56><<<grd, kFastThreads, bytes, s>>>(g, b.pyr, b.cell_count, b.cell_slots, b.cell_tab, sm, cell_lo, cell_hi);
     } else {
         if (bytes > 48 * 1024) cudaFuncSetAttribute(k_fast_cells<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        k_fast_cells<0><<<grd, kFastThreads, bytes, s>>>(g, b.pyr, b.cell_count, b.cell_slots, b.cell_tab, sm);
+        k_fast_cells<0><<<grd, kFastThreads, bytes, s>>>(g, b.pyr, b.cell_count, b.cell_slots, b.cell_tab, sm, cell_lo, cell_hi);
     }
 }
 

@@ -81,12 +81,12 @@ template <int kOctThreads>
 __global__ void __launch_bounds__(kOctThreads, kOctThreads == 256 ? 5 : 1)   // latency-bound: favour resident blocks over registers
 k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, const uint32_t *__restrict__ cell_slots,
          uint32_t *keysA_all, uint32_t *keysB_all, uint16_t *nodeA_all, uint16_t *nodeB_all, uint4 *scanE_all,
-         int *__restrict__ ncand_out, uint32_t *__restrict__ kept_out, int *__restrict__ nkept_out, const int smem_keys)
+         int *__restrict__ ncand_out, uint32_t *__restrict__ kept_out, int *__restrict__ nkept_out, const int smem_keys, const int level_lo)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ OctShared S;
 
-    const int level = blockIdx.x, f = blockIdx.y + g.frame0, tid = threadIdx.x;
+    const int level = level_lo + blockIdx.x, f = blockIdx.y + g.frame0, tid = threadIdx.x;
     constexpr int kOctWarps = kOctThreads / 32;
     const LevelGeom &L = g.lv[level];
     const int NC = L.node_cap;
@@ -445,18 +445,20 @@ int octree_configure(int smem_bytes)
     return e == cudaSuccess ? 0 : -1;
 }
 
-void launch_octree(const Geo &g, const DevBuffers &b, int nframes, int smem_bytes, cudaStream_t s)
+void launch_octree(const Geo &g, const DevBuffers &b, int nframes, int smem_bytes, cudaStream_t s, int level_lo, int level_hi)
 {
-    dim3 grd(g.nlevels, nframes);
+    if (level_hi > g.nlevels) level_hi = g.nlevels;
+    if (level_hi <= level_lo) return;
+    dim3 grd(level_hi - level_lo, nframes);                 // levels [level_lo, level_hi); default: all
     // candidate counts scale with the level area: large levels (4K) get 1024 threads per problem
     int big = 0;
     for (int l = 0; l < g.nlevels; ++l) big = big > g.lv[l].regionW * g.lv[l].regionH ? big : g.lv[l].regionW * g.lv[l].regionH;
     if (big > 1500000)
         k_octree<1024><<<grd, 1024, smem_bytes, s>>>(g, b.cell_count, b.cell_slots, b.keysA, b.keysB, b.nodeA, b.nodeB,
-                                                     b.scanE, b.ncand, b.kept, b.nkept, 0);
+                                                     b.scanE, b.ncand, b.kept, b.nkept, 0, level_lo);
     else
         k_octree<256><<<grd, 256, smem_bytes, s>>>(g, b.cell_count, b.cell_slots, b.keysA, b.keysB, b.nodeA, b.nodeB,
-                                                   b.scanE, b.ncand, b.kept, b.nkept, octree_smem_keys(g));
+                                                   b.scanE, b.ncand, b.kept, b.nkept, octree_smem_keys(g), level_lo);
 }
 
 } // namespace orbx

@@ -92,8 +92,8 @@ struct DevBuffers {
 void launch_level0(const Geo &g, const DevBuffers &b, const uint8_t *d_imgs, size_t pitch, size_t fstride, int nframes, cudaStream_t s);
 void launch_resize(const Geo &g, const DevBuffers &b, int level, int nframes, cudaStream_t s);
 void launch_fill_border(const Geo &g, const DevBuffers &b, int level, int frame, cudaStream_t s);
-void launch_fast(const Geo &g, const DevBuffers &b, int nframes, cudaStream_t s);
-void launch_octree(const Geo &g, const DevBuffers &b, int nframes, int smem_bytes, cudaStream_t s);
+void launch_fast(const Geo &g, const DevBuffers &b, int nframes, cudaStream_t s, int level_lo = 0, int level_hi = ORBX_MAX_LEVELS);
+void launch_octree(const Geo &g, const DevBuffers &b, int nframes, int smem_bytes, cudaStream_t s, int level_lo = 0, int level_hi = ORBX_MAX_LEVELS);
 void launch_blur(const Geo &g, const DevBuffers &b, int nframes, cudaStream_t s);
 void launch_describe(const Geo &g, const DevBuffers &b, int nframes, orbx_keypoint *d_kps, uint8_t *d_desc, int *d_counts, cudaStream_t s);
 void launch_undistort(const orbx_keypoint *in, orbx_keypoint *out, int n, const float *cam, const float *dist, int literal_bug, cudaStream_t s);

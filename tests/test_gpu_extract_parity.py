@@ -345,3 +345,55 @@ def test_device_entry_sub_batches_give_identical_results(orbx, oracle):
         assert n == len(ko)
         assert np.array_equal(outs[1][0][f, :n, 0].view(np.float32), ko["x"]) and np.array_equal(outs[1][0][f, :n, 1].view(np.float32), ko["y"])
         assert np.unpackbits(outs[1][1][f, :n] ^ do).sum() <= 1e-3 * do.size * 8
+
+
+def test_low_latency_graph_path_equals_stream_path(orbx, oracle):
+    """Small batches replay the kernels as a CUDA graph with per-level FAST/octree branches (orbx_set_low_latency, the default);
+    the stream path is the same kernels in one chain.  Both must give the oracle's result: pageable and pinned caller
+    buffers, a padded row pitch, 1..8 frames per call, repeated calls (graph replay) and a change of batch size (re-capture)."""
+    import torch
+    imgs = synth_batch(range(40, 48))
+    oex = oracle.OracleExtractor()
+    want = [oex(im) for im in imgs]
+    ex = orbx.Extractor(max_width=640, max_height=480, max_batch=8)
+    ref = orbx.Extractor(max_width=640, max_height=480, max_batch=8)
+    ref.set_low_latency(False)
+
+    def check(kps, desc, counts, frames):
+        for i, f in enumerate(frames):
+            ko, do = want[f]
+            n = int(counts[i])
+            assert n == len(ko)
+            for fld in ("x", "y", "size", "response", "octave", "class_id"):
+                assert np.array_equal(kps[i, :n][fld], ko[fld]), fld
+            d = np.abs(kps[i, :n]["angle"] - ko["angle"]); d = np.minimum(d, 360.0 - d)
+            assert d.max() <= ANGLE_TOL_DEG
+            assert np.unpackbits(desc[i, :n] ^ do).sum() <= 1e-3 * do.size * 8
+
+    for n in (1, 1, 3, 8, 2, 1):                          # repeats replay the cached graph; size changes re-capture it
+        fr = list(range(n))
+        out = ex.extract_host(imgs[:n]); check(*out, fr)
+        out2 = ref.extract_host(imgs[:n]); check(*out2, fr)
+        for f in range(n):
+            c = int(out[2][f])
+            assert c == int(out2[2][f]) and out[0][f, :c].tobytes() == out2[0][f, :c].tobytes() and np.array_equal(out[1][f, :c], out2[1][f, :c])
+    # padded row pitch (a cv::Mat ROI), pageable
+    wide = np.zeros((2, 480, 704), np.uint8); wide[:, :, :640] = imgs[4:6]
+    check(*ex.extract_host(wide[:, :, :640]), [4, 5])
+    # pinned caller buffers
+    pinned = torch.from_numpy(imgs[6:8].copy()).pin_memory()
+    check(*ex.extract_host(pinned.numpy()), [6, 7])
+    # the intermediate buffers are the ones the stage accessors read
+    kps, desc, counts = ex.extract_host(imgs[:1])
+    _compare_frame(oracle, ex, oex, imgs[0], 0, kps, desc, counts)
+    # device pointers: the second graph slot
+    dev = torch.device("cuda:0")
+    d_f = torch.from_numpy(imgs[:2].copy()).to(dev); cap = ex.capacity
+    d_k = torch.zeros((2, cap, 7), dtype=torch.float32, device=dev); d_d = torch.zeros((2, cap, 32), dtype=torch.uint8, device=dev)
+    d_c = torch.zeros(2, dtype=torch.int32, device=dev)
+    st = torch.cuda.Stream(device=dev)
+    for _ in range(3):
+        ex.extract_device(d_f.data_ptr(), 640, 640 * 480, 640, 480, 2, d_k.data_ptr(), d_d.data_ptr(), d_c.data_ptr(), st.cuda_stream)
+    st.synchronize()
+    kd = d_k.cpu().numpy().view(np.uint8).reshape(2, cap, 28).copy().view(oracle.KEYPOINT_DTYPE).reshape(2, cap)
+    check(kd, d_d.cpu().numpy(), d_c.cpu().numpy(), [0, 1])

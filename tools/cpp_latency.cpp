@@ -1,6 +1,6 @@
 // cpp_latency.cpp -- wall-clock latency of ORBSlam::ORBextractor::operator() on ONE frame per call, the way the reference's
 // Frame calls it (src/Frame.cpp:75-78): pageable cv::Mat in, std::vector<cv::KeyPoint> + cv::Mat out.
-// usage: cpp_latency W H nfeatures calls device   -> one JSON line {"p50":..,"p99":..,"mean":..,"keypoints":..}
+// usage: cpp_latency W H nfeatures calls device [frame.raw]   -> one JSON line {"p50":..,"p99":..,"mean":..,"keypoints":..}
 #include <algorithm>
 #include <chrono>
 #include <cstdio>
@@ -22,6 +22,11 @@ int main(int argc, char **argv)
             s = s * 1664525u + 1013904223u;
             img[(size_t)y * W + x] = (unsigned char)(((b >> 7) & 0xff) * 3 / 4 + ((s >> 24) & 7));
         }
+    if (argc > 6) {                                     // the bench's own synthetic frame (W*H raw bytes)
+        FILE *fi = std::fopen(argv[6], "rb");
+        if (!fi || std::fread(img.data(), 1, img.size(), fi) != img.size()) return 3;
+        std::fclose(fi);
+    }
     try {
         ORBSlam::ORBextractor ex(NF, 1.2f, 8, 20, 7);
         ex.SetDevice(dev);
