@@ -78,7 +78,7 @@ __device__ __forceinline__ int quadrant(uint32_t key, const Node &nd)
 __device__ __forceinline__ uint32_t comp(const uint4 &v, int q) { return q == 0 ? v.x : q == 1 ? v.y : q == 2 ? v.z : v.w; }
 
 template <int kOctThreads>
-__global__ void __launch_bounds__(kOctThreads, kOctThreads == 256 ? 5 : 1)   // latency-bound: favour resident blocks over registers
+__global__ void __launch_bounds__(kOctThreads, kOctThreads == 256 ? 5 : (kOctThreads == 512 ? 2 : 1))   // latency-bound: favour resident blocks over registers
 k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, const uint32_t *__restrict__ cell_slots,
          uint32_t *keysA_all, uint32_t *keysB_all, uint16_t *nodeA_all, uint16_t *nodeB_all, uint4 *scanE_all,
          int *__restrict__ ncand_out, uint32_t *__restrict__ kept_out, int *__restrict__ nkept_out, const int smem_keys, const int level_lo)
@@ -441,6 +441,7 @@ int octree_smem_keys(const Geo &g)
 int octree_configure(int smem_bytes)
 {
     cudaError_t e = cudaFuncSetAttribute(k_octree<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_octree<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_octree<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     return e == cudaSuccess ? 0 : -1;
 }
@@ -456,6 +457,10 @@ void launch_octree(const Geo &g, const DevBuffers &b, int nframes, int smem_byte
     if (big > 1500000)
         k_octree<1024><<<grd, 1024, smem_bytes, s>>>(g, b.cell_count, b.cell_slots, b.keysA, b.keysB, b.nodeA, b.nodeB,
                                                      b.scanE, b.ncand, b.kept, b.nkept, 0, level_lo);
+    else if (nframes <= 4)
+        // small batches (low-latency path): twice the threads per problem -- half the keys per warp in every sweep
+        k_octree<512><<<grd, 512, smem_bytes, s>>>(g, b.cell_count, b.cell_slots, b.keysA, b.keysB, b.nodeA, b.nodeB,
+                                                   b.scanE, b.ncand, b.kept, b.nkept, octree_smem_keys(g), level_lo);
     else
         k_octree<256><<<grd, 256, smem_bytes, s>>>(g, b.cell_count, b.cell_slots, b.keysA, b.keysB, b.nodeA, b.nodeB,
                                                    b.scanE, b.ncand, b.kept, b.nkept, octree_smem_keys(g), level_lo);
