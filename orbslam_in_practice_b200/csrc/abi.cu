@@ -430,7 +430,7 @@ extern "C" int orbx_create(const orbx_params *p, int max_width, int max_height, 
                                                2 * ((size_t)g.lv[l].pitch / 256 + 2) + 2 * ((size_t)(g.lv[l].h + 2 * kBorder) / kResizeRows + 2);   // plain + padded tables + block ranges
 #define TRY(x) do { rc = (x); if (rc) { orbx_destroy(ex); return rc; } } while (0)
     TRY(dev_alloc(ex, &b.pyr, g.pyr_frame_total));
-    TRY(dev_alloc(ex, &b.blur, g.blur_frame_total));
+    TRY(dev_alloc(ex, &b.blur, g.blur_frame_total + 256));   // the descriptor stage reads 64-byte row segments: up to 26 bytes past a row's end
     ex->tables_cap = ntab + 8 * ORBX_MAX_LEVELS;
     TRY(dev_alloc(ex, &b.tables, ex->tables_cap));
     TRY(dev_alloc(ex, &b.cell_tab, (size_t)g.total_cells));

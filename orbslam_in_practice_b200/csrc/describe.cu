@@ -3,6 +3,7 @@
 #include "orbx_internal.cuh"
 
 #include <cuda_fp16.h>
+#include <cstdlib>
 #include <mutex>
 
 namespace orbx {
@@ -163,6 +164,12 @@ constexpr int kPatchRows = 2 * kPatchR + 1;               // 37
 constexpr int kPatchWords = (2 * kPatchR + 1 + 3 + 3) / 4; // 37 px + up to 3 px of alignment slack = 11 words
 constexpr int kStagePasses = (kPatchRows + 1) / 2;        // two patch rows (22 lanes) per cp.async pass
 constexpr int kPatchAlloc = 2 * kStagePasses * kPatchWords; // words per patch buffer (one spare row for the last pass)
+// Patch staging variants (ORBX_DESC_STAGE): 0 = 4-byte cp.async.ca, rows of 11 words from a 4-byte aligned column;
+// 1 = 16-byte cp.async.cg (L1 bypass), 2 = one cp.async.bulk (TMA engine, mbarrier completion) per row -- both with rows of
+// 64 bytes from a 16-byte aligned column (x - 18 rounded down to 16: the 37 columns end at byte 51 at most).
+__host__ __device__ constexpr int patch_pitch(int stage) { return stage == 0 ? kPatchWords * 4 : 64; }           // bytes per staged patch row
+__host__ __device__ constexpr int patch_buf_words(int stage) { return stage == 0 ? kPatchAlloc : kPatchRows * 16; }  // words per patch buffer
+__host__ __device__ constexpr int patch_align_mask(int stage) { return stage == 0 ? ~3 : ~15; }
 // IC_Angle as dot products: the 31 x 31 window is read as 9 aligned words per row, three rows per warp pass
 // (lane = row-in-pass * 9 + word), and a host-built table holds for every (alignment, pass, lane) the four
 // column weights u and the four row weights v as signed bytes, zero outside the circular patch (umax) and
@@ -182,12 +189,56 @@ __device__ __forceinline__ void cp_async4(void *smem, const void *gmem)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cp_async16_cg(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase)
+{
+    asm volatile("{\n.reg .pred p;\nWAIT_%=: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@!p bra WAIT_%=;\n}" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem)), "l"(gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
 // blurred 37 x 37 patch (word aligned, 11 words per row) -> shared memory: lanes 0..21 copy two rows per pass
-__device__ __forceinline__ void stage_patch(uint32_t *patch, const uint8_t *blur, const LevelGeom &L, int f, int x, int y, int lane)
+template <int kStage>
+__device__ __forceinline__ void stage_patch(uint32_t *patch, const uint8_t *blur, const LevelGeom &L, int f, int x, int y, int lane, uint64_t *bar)
 {
     const int bp = L.blur_pitch;
-    const int xa = (x - kPatchR) & ~3;                    // first staged column (keypoints sit >= 19 px inside)
+    const int xa = (x - kPatchR) & patch_align_mask(kStage);   // first staged column (keypoints sit >= 19 px inside)
+    if (kStage == 1) {
+        // 16 bytes per lane, four lanes per 64-byte row, eight rows per pass: 5 LDGSTS.128 per patch, L1 bypassed
+        const uint8_t *src = blur + L.blur_base + (size_t)f * L.blur_frame_stride + (size_t)(y - kPatchR + (lane >> 2)) * bp + xa + 16 * (lane & 3);
+        uint8_t *dst = reinterpret_cast<uint8_t *>(patch) + lane * 16;
+#pragma unroll
+        for (int it = 0; it < (kPatchRows + 7) / 8; ++it, src += 8 * bp, dst += 8 * 64)
+            if (it * 8 + (lane >> 2) < kPatchRows) cp_async16_cg(dst, src);
+        cp_async_commit();
+        return;
+    }
+    if (kStage == 2) {
+        // the TMA engine copies the rows: one 64-byte bulk copy per row, issued by one lane, completion on the buffer's mbarrier
+        if (lane == 0) {
+            mbar_expect_tx(bar, kPatchRows * 64);
+            const uint8_t *src = blur + L.blur_base + (size_t)f * L.blur_frame_stride + (size_t)(y - kPatchR) * bp + xa;
+            uint8_t *dst = reinterpret_cast<uint8_t *>(patch);
+#pragma unroll 1
+            for (int r = 0; r < kPatchRows; ++r, src += bp, dst += 64) bulk_g2s(dst, src, 64, bar);
+        }
+        return;
+    }
     if (lane < 2 * kPatchWords) {
         const int r = lane >= kPatchWords ? 1 : 0, wx = lane - r * kPatchWords;
         const uint8_t *src = blur + L.blur_base + (size_t)f * L.blur_frame_stride + (size_t)(y - kPatchR + r) * bp + xa + 4 * wx;
@@ -205,14 +256,17 @@ __device__ __forceinline__ void stage_patch(uint32_t *patch, const uint8_t *blur
 // from there (<= 4-way bank conflicts).  Three phases per warp: (1) the moments of its keypoints, (2) fastAtan2 + the
 // double-precision sincos ONCE, lane s working on keypoint s, (3) per keypoint the rotated BRIEF tests and the output
 // row.  The kernel runs at 86 % of the L1 data-pipe wavefront peak, not at the issue limit.
-template <int MINB, int kSlotsPerWarp>
+template <int MINB, int kSlotsPerWarp, int kStage>
 __global__ void __launch_bounds__(kDescWarps * 32, MINB)
 k_describe(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, const uint8_t *__restrict__ blur,
            const uint32_t *__restrict__ kept, const int *__restrict__ nkept,
            orbx_keypoint *__restrict__ out_kps, uint8_t *__restrict__ out_desc, int *__restrict__ out_counts,
            const uint32_t *__restrict__ pattern_words, const uint2 *__restrict__ moment_tab)
 {
-    __shared__ uint32_t patch_all[kDescWarps][2][kPatchAlloc];
+    constexpr int kPatchPitch = patch_pitch(kStage);
+    extern __shared__ __align__(128) uint32_t patch_dyn[];      // [kDescWarps][2][patch_buf_words]: dynamic, the 64-byte-row variants pass 48 KB of static data
+    uint32_t (*patch_all)[2][patch_buf_words(kStage)] = reinterpret_cast<uint32_t (*)[2][patch_buf_words(kStage)]>(patch_dyn);
+    __shared__ __align__(8) uint64_t patch_bar[kDescWarps][2];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int f = blockIdx.y + g.frame0;
     // lane i owns descriptor byte i = pattern points 16i .. 16i+15.  The pattern lives in shared memory as floats, one
@@ -228,6 +282,10 @@ k_describe(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, const
         pat[k][l] = make_uint2(*reinterpret_cast<const uint32_t *>(&p0), *reinterpret_cast<const uint32_t *>(&p1));
     }
     for (int i = threadIdx.x; i < 4 * kMomentPasses * 32; i += kDescWarps * 32) mtab[i] = __ldg(moment_tab + i);
+    if (kStage == 2 && threadIdx.x < 2 * kDescWarps) {
+        mbar_init(&patch_bar[0][0] + threadIdx.x, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
     // per-level keypoint counts -> inclusive prefix in lanes 0..nlevels-1 (level-major concatenation, :1036-1063)
     const int myc = lane < g.nlevels ? nkept[f * g.nlevels + lane] : 0;
@@ -263,7 +321,7 @@ k_describe(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, const
         const int level = __shfl_sync(0xffffffffu, my_level, si);
         const LevelGeom &L = g.lv[level];
         const int x = cand_x(key) + kMinBorder, y = cand_y(key) + kMinBorder;   // :801-802
-        if (stage) stage_patch(patch_all[warp][0], blur, L, f, x, y, lane);
+        if (stage) stage_patch<kStage>(patch_all[warp][0], blur, L, f, x, y, lane, &patch_bar[warp][0]);
         const int pitch = L.pitch;
         al_out = (x - kHalfPatch + kPadX) & 3;             // bytes between the aligned first word and column x-15
         const uint8_t *src = pyr + L.base + (size_t)f * L.frame_stride + (size_t)(kPadY + y - kHalfPatch + mrow) * pitch
@@ -314,14 +372,15 @@ k_describe(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, const
         if (si + 1 < nslot) {                                // next keypoint's patch into the other buffer
             const uint32_t nkey = __shfl_sync(0xffffffffu, my_key, si + 1);
             const int nlevel = __shfl_sync(0xffffffffu, my_level, si + 1);
-            stage_patch(patch_all[warp][(si + 1) & 1], blur, g.lv[nlevel], f, cand_x(nkey) + kMinBorder, cand_y(nkey) + kMinBorder, lane);
-            cp_async_wait<1>();
+            stage_patch<kStage>(patch_all[warp][(si + 1) & 1], blur, g.lv[nlevel], f, cand_x(nkey) + kMinBorder, cand_y(nkey) + kMinBorder, lane, &patch_bar[warp][(si + 1) & 1]);
+            if (kStage != 2) cp_async_wait<1>();
         } else {
-            cp_async_wait<0>();
+            if (kStage != 2) cp_async_wait<0>();
         }
+        if (kStage == 2) mbar_wait(&patch_bar[warp][si & 1], (si >> 1) & 1);   // buffer b is filled for keypoints b, b+2, ...: parity of its use count
         __syncwarp();
-        const int xa = (x - kPatchR) & ~3;
-        const uint8_t *pc = reinterpret_cast<const uint8_t *>(patch_all[warp][si & 1]) + kPatchR * (kPatchWords * 4) + (x - xa);   // patch centre
+        const int xa = (x - kPatchR) & patch_align_mask(kStage);
+        const uint8_t *pc = reinterpret_cast<const uint8_t *>(patch_all[warp][si & 1]) + kPatchR * kPatchPitch + (x - xa);   // patch centre
         int val = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -332,7 +391,7 @@ k_describe(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, const
             const int c0 = __float2int_rn(__fsub_rn(__fmul_rn(x0, a), __fmul_rn(y0, b)));
             const int r1 = __float2int_rn(__fadd_rn(__fmul_rn(x1, b), __fmul_rn(y1, a)));
             const int c1 = __float2int_rn(__fsub_rn(__fmul_rn(x1, a), __fmul_rn(y1, b)));
-            const int t0 = pc[r0 * (kPatchWords * 4) + c0], t1 = pc[r1 * (kPatchWords * 4) + c1];
+            const int t0 = pc[r0 * kPatchPitch + c0], t1 = pc[r1 * kPatchPitch + c1];
             val |= (t0 < t1) << k;
         }
         out_desc[((size_t)f * g.capacity + slot) * 32 + lane] = (uint8_t)val;
@@ -402,15 +461,25 @@ void launch_describe(const Geo &g, const DevBuffers &b, int nframes, orbx_keypoi
     // maximises shared memory: 28 KB of L1 left) costs 30 %; 164 KB of shared memory = 4 resident blocks and 92 KB of L1.
     // 48 registers (the 5-block launch bound) leave room for the other stream's kernels on the same SM.
     static bool configured[64] = {};
+    static int stage = 0, carve = 72;
     if (!configured[dev]) {
-        cudaFuncSetAttribute(k_describe<5, kDescSlots>, cudaFuncAttributePreferredSharedMemoryCarveout, 72);
-        cudaFuncSetAttribute(k_describe<5, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 72);
+        if (const char *e = std::getenv("ORBX_DESC_STAGE")) stage = std::atoi(e);
+        if (const char *e = std::getenv("ORBX_DESC_CARVEOUT")) carve = std::atoi(e);
+        cudaFuncSetAttribute(k_describe<5, kDescSlots, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(k_describe<5, kDescSlots, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(k_describe<5, kDescSlots, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(k_describe<5, 2, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 72);
+        cudaFuncSetAttribute(k_describe<5, kDescSlots, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDescWarps * 2 * patch_buf_words(1) * 4);
+        cudaFuncSetAttribute(k_describe<5, kDescSlots, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDescWarps * 2 * patch_buf_words(2) * 4);
         configured[dev] = true;
     }
-    if (small)
-        k_describe<5, 2><<<grd, kDescWarps * 32, 0, s>>>(g, b.pyr, b.blur, b.kept, b.nkept, d_kps, d_desc, d_counts, g_desc_tab[dev].pattern, g_desc_tab[dev].moments);
-    else
-        k_describe<5, kDescSlots><<<grd, kDescWarps * 32, 0, s>>>(g, b.pyr, b.blur, b.kept, b.nkept, d_kps, d_desc, d_counts, g_desc_tab[dev].pattern, g_desc_tab[dev].moments);
+#define DESC_ARGS g, b.pyr, b.blur, b.kept, b.nkept, d_kps, d_desc, d_counts, g_desc_tab[dev].pattern, g_desc_tab[dev].moments
+    const int dyn0 = kDescWarps * 2 * patch_buf_words(0) * 4, dyn1 = kDescWarps * 2 * patch_buf_words(1) * 4;
+    if (small) k_describe<5, 2, 0><<<grd, kDescWarps * 32, dyn0, s>>>(DESC_ARGS);
+    else if (stage == 1) k_describe<5, kDescSlots, 1><<<grd, kDescWarps * 32, dyn1, s>>>(DESC_ARGS);
+    else if (stage == 2) k_describe<5, kDescSlots, 2><<<grd, kDescWarps * 32, dyn1, s>>>(DESC_ARGS);
+    else k_describe<5, kDescSlots, 0><<<grd, kDescWarps * 32, dyn0, s>>>(DESC_ARGS);
+#undef DESC_ARGS
 }
 
 // ---------------------------------------------------------------------------------------------
