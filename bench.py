@@ -491,6 +491,27 @@ def run_ours(args):
     h2d_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
     barrier()
     h2d_ceiling_gbs = world * h2d * K / (h2d_ms * 1e-3) / 1e9
+    # the same uploads with each step's result download (the step's real d2h bytes) running beside them on other streams: the
+    # host side of an 8-GPU box is shared, so the downloads take their part of what it can deliver
+    dstreams = [torch.cuda.Stream(device=dev) for _ in range(DEPTH)]
+    d_outs = [torch.empty(d2h, dtype=torch.uint8, device=dev) for _ in range(DEPTH)]
+    h_outs = [torch.empty(d2h, dtype=torch.uint8).pin_memory() for _ in range(DEPTH)]
+
+    def bare_both(n):
+        for i in range(n):
+            with torch.cuda.stream(cstreams[i % DEPTH]):
+                d_sinks[i % DEPTH].copy_(slots[i % DEPTH][1], non_blocking=True)
+            with torch.cuda.stream(dstreams[i % DEPTH]):
+                h_outs[i % DEPTH].copy_(d_outs[i % DEPTH], non_blocking=True)
+
+    bare_both(DEPTH); barrier()
+    t0 = time.perf_counter()
+    bare_both(K)
+    torch.cuda.synchronize()
+    both_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
+    barrier()
+    h2d_ceiling_duplex_gbs = world * h2d * K / (both_ms * 1e-3) / 1e9
+    del d_outs, h_outs
     del d_sinks
 
     # ---------------- latency of ONE frame per call: the reference's real call pattern (src/Frame.cpp:75-78) ----------------
@@ -599,8 +620,11 @@ def run_ours(args):
                         "ms_per_step": e2e_ms / K,
                         "h2d_ceiling_gbs": h2d_ceiling_gbs, "h2d_achieved_gbs": e2e_value * W * H / 1e9,
                         "frac_of_ceiling": e2e_value * W * H / 1e9 / h2d_ceiling_gbs,
+                        "h2d_ceiling_with_downloads_gbs": h2d_ceiling_duplex_gbs,
+                        "frac_of_ceiling_with_downloads": e2e_value * W * H / 1e9 / h2d_ceiling_duplex_gbs,
                         "h2d_ceiling": "the same K x %d-byte pinned uploads with no kernels and no downloads, %d in flight, all %d rank(s) "
-                                       "at once, wall clock max over ranks: what the box's host side can deliver" % (h2d, DEPTH, world),
+                                       "at once, wall clock max over ranks: what the box's host side can deliver; _with_downloads: the same uploads next to bare downloads "
+                                       "of the step's %d result bytes" % (h2d, DEPTH, world, d2h),
                         "api": "orbx_extract_host_begin/_end (C ABI) on %d handles, pinned host buffers: consecutive steps overlap "
                                "(uploads of the next steps during the kernels of step k); every step uploads its frames and downloads its results" % DEPTH,
                         "single_blocking_call": {"value": e2e_sync_value, "ms_per_step": e2e_sync_ms / K, "api": "orbx_extract_host"}},
