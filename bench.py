@@ -664,7 +664,7 @@ def measure_latency(_lib, torch, frame, local, calls=300):
     ts *= 1e6
     out = {"unit": "us per call", "frame": "%dx%d, nfeatures=%d" % (W, H, NFEAT), "calls": calls, "keypoints": int(hc[0]),
            "orbx_extract_host": {"p50": float(np.percentile(ts, 50)), "p99": float(np.percentile(ts, 99)), "mean": float(ts.mean()),
-                                 "api": "C ABI, pinned host buffers, blocking (H2D + 12 launches + D2H)"}}
+                                 "api": "C ABI, pinned host buffers, blocking (upload, the call's kernels as one CUDA graph, one download)"}}
     del ex1
     # the C++ class the reference's caller sees: (*mpORBextractor)(img, cv::Mat(), keypoints, descriptors) with pageable cv::Mat
     exe = os.path.join(ROOT, "tools", "_build", "cpp_latency")
