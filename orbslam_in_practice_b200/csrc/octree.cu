@@ -77,8 +77,11 @@ __device__ __forceinline__ int quadrant(uint32_t key, const Node &nd)
 
 __device__ __forceinline__ uint32_t comp(const uint4 &v, int q) { return q == 0 ? v.x : q == 1 ? v.y : q == 2 ? v.z : v.w; }
 
-template <int kOctThreads>
-__global__ void __launch_bounds__(kOctThreads, kOctThreads == 256 ? 5 : (kOctThreads == 512 ? 2 : 1))   // latency-bound: favour resident blocks over registers
+// kU: key groups a warp loads before it processes them.  Problems whose keys live in global memory (4K-sized levels: tens of
+// thousands of candidates, one block per SM because of the node tables) are bound by the latency of the dependent L2 round
+// trips of every sweep (ncu, round 2: st_long 9.4 per issue at 39 % issue-active); kU = 4 puts four groups' loads in flight.
+template <int kOctThreads, int kU>
+__global__ void __launch_bounds__(kOctThreads, kOctThreads == 256 ? 5 : ((kOctThreads == 512 && kU == 1) ? 2 : 1))   // latency-bound: favour resident blocks over registers
 k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, const uint32_t *__restrict__ cell_slots,
          uint32_t *keysA_all, uint32_t *keysB_all, uint16_t *nodeA_all, uint16_t *nodeB_all, uint4 *scanE_all,
          int *__restrict__ ncand_out, uint32_t *__restrict__ kept_out, int *__restrict__ nkept_out, const int smem_keys, const int level_lo)
@@ -218,16 +221,26 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
         // ---- A: stable rank of every key inside its future child (warp-streaming scan, see above) ----
         {
             uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-            for (int p0 = s0; p0 < s1; p0 += 32) {
-                const int p = p0 + lane;
-                int q = 4;
-                if (p < s1) {
-                    const Node nd = nodes[nA[p]];
-                    if (nd.count > 1) q = quadrant(kA[p], nd);
-                    qbuf[p] = (unsigned char)q;
+            for (int p0 = s0; p0 < s1; p0 += 32 * kU) {
+                int gis[kU]; uint32_t keys[kU];
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const int p = p0 + 32 * u + lane;
+                    gis[u] = 0; keys[u] = 0;
+                    if (p < s1) { gis[u] = nA[p]; keys[u] = kA[p]; }
                 }
-                c0 += __popc(__ballot_sync(0xffffffffu, q == 0)); c1 += __popc(__ballot_sync(0xffffffffu, q == 1));
-                c2 += __popc(__ballot_sync(0xffffffffu, q == 2)); c3 += __popc(__ballot_sync(0xffffffffu, q == 3));
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const int p = p0 + 32 * u + lane;
+                    int q = 4;
+                    if (p < s1) {
+                        const Node nd = nodes[gis[u]];
+                        if (nd.count > 1) q = quadrant(keys[u], nd);
+                        qbuf[p] = (unsigned char)q;
+                    }
+                    c0 += __popc(__ballot_sync(0xffffffffu, q == 0)); c1 += __popc(__ballot_sync(0xffffffffu, q == 1));
+                    c2 += __popc(__ballot_sync(0xffffffffu, q == 2)); c3 += __popc(__ballot_sync(0xffffffffu, q == 3));
+                }
             }
             if (lane == 0) S.warp_v[warp] = make_uint4(c0, c1, c2, c3);
             if (tid == 0) { S.J = 0x7fffffff; S.pending = 0; }
@@ -235,21 +248,31 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
             if (tid == 0) S.nToExpand = 0;                 // behind a barrier: the previous pass's tail may still be reading it
             uint4 run = make_uint4(0, 0, 0, 0);
             for (int w = 0; w < warp; ++w) run = add4(run, S.warp_v[w]);
-            for (int p0 = s0; p0 < s1; p0 += 32) {
-                const int p = p0 + lane;
-                const int q = p < s1 ? (int)qbuf[p] : 4;
-                const uint32_t b0 = __ballot_sync(0xffffffffu, q == 0), b1 = __ballot_sync(0xffffffffu, q == 1);
-                const uint32_t b2 = __ballot_sync(0xffffffffu, q == 2), b3 = __ballot_sync(0xffffffffu, q == 3);
-                if (q < 4) {
-                    const uint4 ex = make_uint4(run.x + __popc(b0 & lt), run.y + __popc(b1 & lt), run.z + __popc(b2 & lt), run.w + __popc(b3 & lt));
-                    E32[p] = comp(ex, q);
-                    const int gi = nA[p];
-                    const Node nd = nodes[gi];
-                    if (p == nd.begin) nodeFirst[gi] = ex;
-                    if (p == nd.begin + nd.count - 1)             // counters just behind the node's last key
-                        *reinterpret_cast<uint4 *>(childCnt + 4 * gi) = make_uint4(ex.x + (q == 0), ex.y + (q == 1), ex.z + (q == 2), ex.w + (q == 3));
+            for (int p0 = s0; p0 < s1; p0 += 32 * kU) {
+                int qs[kU], gis[kU];
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const int p = p0 + 32 * u + lane;
+                    qs[u] = 4; gis[u] = 0;
+                    if (p < s1) { qs[u] = (int)qbuf[p]; gis[u] = nA[p]; }
                 }
-                run.x += __popc(b0); run.y += __popc(b1); run.z += __popc(b2); run.w += __popc(b3);
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const int p = p0 + 32 * u + lane;
+                    const int q = qs[u];
+                    const uint32_t b0 = __ballot_sync(0xffffffffu, q == 0), b1 = __ballot_sync(0xffffffffu, q == 1);
+                    const uint32_t b2 = __ballot_sync(0xffffffffu, q == 2), b3 = __ballot_sync(0xffffffffu, q == 3);
+                    if (q < 4) {
+                        const uint4 ex = make_uint4(run.x + __popc(b0 & lt), run.y + __popc(b1 & lt), run.z + __popc(b2 & lt), run.w + __popc(b3 & lt));
+                        E32[p] = comp(ex, q);
+                        const int gi = gis[u];
+                        const Node nd = nodes[gi];
+                        if (p == nd.begin) nodeFirst[gi] = ex;
+                        if (p == nd.begin + nd.count - 1)             // counters just behind the node's last key
+                            *reinterpret_cast<uint4 *>(childCnt + 4 * gi) = make_uint4(ex.x + (q == 0), ex.y + (q == 1), ex.z + (q == 2), ex.w + (q == 3));
+                    }
+                    run.x += __popc(b0); run.y += __popc(b1); run.z += __popc(b2); run.w += __popc(b3);
+                }
             }
             __syncthreads();
         }
@@ -370,19 +393,31 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
             __syncthreads();
         }
         // ---- F: move keys ----
-        for (int p = tid; p < n; p += kOctThreads) {
-            const int gi = nA[p];
-            const uint32_t key = kA[p];
-            if (split[gi]) {
-                const Node nd = nodes[gi];
-                const int q = qbuf[p];
-                int off = 0;
+        for (int pb = tid; pb < n; pb += kOctThreads * kU) {
+            int gis[kU], qs[kU]; uint32_t keys[kU], es[kU];
 #pragma unroll
-                for (int qq = 0; qq < 3; ++qq) if (qq < q) off += childCnt[4 * gi + qq];
-                const int np = nd.begin + off + (int)(E32[p] - comp(nodeFirst[gi], q));
-                kB[np] = key; nB[np] = (uint16_t)newIdx[4 * gi + q];
-            } else {
-                kB[p] = key; nB[p] = (uint16_t)newIdx[4 * gi];
+            for (int u = 0; u < kU; ++u) {
+                const int p = pb + u * kOctThreads;
+                gis[u] = 0; qs[u] = 0; keys[u] = 0; es[u] = 0;
+                if (p < n) { gis[u] = nA[p]; keys[u] = kA[p]; qs[u] = qbuf[p]; es[u] = E32[p]; }   // qbuf / E32 are stale for unsplit nodes and unused there
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+                const int p = pb + u * kOctThreads;
+                if (p >= n) break;
+                const int gi = gis[u];
+                const uint32_t key = keys[u];
+                if (split[gi]) {
+                    const Node nd = nodes[gi];
+                    const int q = qs[u];
+                    int off = 0;
+#pragma unroll
+                    for (int qq = 0; qq < 3; ++qq) if (qq < q) off += childCnt[4 * gi + qq];
+                    const int np = nd.begin + off + (int)(es[u] - comp(nodeFirst[gi], q));
+                    kB[np] = key; nB[np] = (uint16_t)newIdx[4 * gi + q];
+                } else {
+                    kB[p] = key; nB[p] = (uint16_t)newIdx[4 * gi];
+                }
             }
         }
         __syncthreads();
@@ -440,9 +475,12 @@ int octree_smem_keys(const Geo &g)
 
 int octree_configure(int smem_bytes)
 {
-    cudaError_t e = cudaFuncSetAttribute(k_octree<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_octree<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_octree<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    cudaError_t e = cudaFuncSetAttribute(k_octree<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_octree<512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_octree<512, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_octree<1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_octree<1024, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_octree<1024, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     return e == cudaSuccess ? 0 : -1;
 }
 
@@ -454,15 +492,22 @@ void launch_octree(const Geo &g, const DevBuffers &b, int nframes, int smem_byte
     // candidate counts scale with the level area: large levels (4K) get 1024 threads per problem
     int big = 0;
     for (int l = 0; l < g.nlevels; ++l) big = big > g.lv[l].regionW * g.lv[l].regionH ? big : g.lv[l].regionW * g.lv[l].regionH;
-    if (big > 1500000)
-        k_octree<1024><<<grd, 1024, smem_bytes, s>>>(g, b.cell_count, b.cell_slots, b.keysA, b.keysB, b.nodeA, b.nodeB,
-                                                     b.scanE, b.ncand, b.kept, b.nkept, 0, level_lo);
+    if (big > 1500000) {
+        static int variant = -1;                             // ORBX_OCT_BIG: 0 = 1024 threads, 1 / 3 = 1024 threads with 2 / 4 key groups in flight (default 3: 0.864 -> 0.731 -> 0.638 -> 0.608 ms per 32 4K frames), 2 = 512 threads x 4 groups (0.873)
+        if (variant < 0) { const char *e = std::getenv("ORBX_OCT_BIG"); variant = e ? std::atoi(e) : 3; }
+#define OCT_ARGS g, b.cell_count, b.cell_slots, b.keysA, b.keysB, b.nodeA, b.nodeB, b.scanE, b.ncand, b.kept, b.nkept, 0, level_lo
+        if (variant == 0) k_octree<1024, 1><<<grd, 1024, smem_bytes, s>>>(OCT_ARGS);
+        else if (variant == 1) k_octree<1024, 2><<<grd, 1024, smem_bytes, s>>>(OCT_ARGS);
+        else if (variant == 3) k_octree<1024, 4><<<grd, 1024, smem_bytes, s>>>(OCT_ARGS);
+        else k_octree<512, 4><<<grd, 512, smem_bytes, s>>>(OCT_ARGS);
+#undef OCT_ARGS
+    }
     else if (nframes <= 4)
         // small batches (low-latency path): twice the threads per problem -- half the keys per warp in every sweep
-        k_octree<512><<<grd, 512, smem_bytes, s>>>(g, b.cell_count, b.cell_slots, b.keysA, b.keysB, b.nodeA, b.nodeB,
+        k_octree<512, 1><<<grd, 512, smem_bytes, s>>>(g, b.cell_count, b.cell_slots, b.keysA, b.keysB, b.nodeA, b.nodeB,
                                                    b.scanE, b.ncand, b.kept, b.nkept, octree_smem_keys(g), level_lo);
     else
-        k_octree<256><<<grd, 256, smem_bytes, s>>>(g, b.cell_count, b.cell_slots, b.keysA, b.keysB, b.nodeA, b.nodeB,
+        k_octree<256, 1><<<grd, 256, smem_bytes, s>>>(g, b.cell_count, b.cell_slots, b.keysA, b.keysB, b.nodeA, b.nodeB,
                                                    b.scanE, b.ncand, b.kept, b.nkept, octree_smem_keys(g), level_lo);
 }
 
