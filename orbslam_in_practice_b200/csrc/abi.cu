@@ -63,6 +63,7 @@ struct orbx_extractor {
     cudaEvent_t ev_fork[kMaxChunks], ev_join[kMaxChunks];
     unsigned fork_slot;
     int oct_smem;
+    unsigned char *oct_scratch_mem; size_t oct_scratch_bytes;   // global-memory node tables (only for quotas beyond one SM's shared memory)
     size_t tables_cap;                            // int2 entries allocated for buf.tables
     int device_split;                             // orbx_extract_device: independent sub-batches on two streams
     cudaEvent_t ev_split_fork, ev_split_join;
@@ -367,10 +368,19 @@ static int upload_geometry(orbx_extractor *ex, int w, int h)
     CK(cudaStreamSynchronize(ex->stream));   // `tables` is pageable host memory about to go out of scope
     ex->cur_w = w; ex->cur_h = h;
     ex->oct_smem = octree_smem_bytes(ex->geo);
-    // the octree keeps its node tables in shared memory: a level quota beyond ~2 400 features does not fit one SM
+    // the octree keeps its node tables in shared memory; a level quota beyond ~2 400 features does not fit one SM and runs
+    // with the tables in a global scratch buffer instead (one slice per frame and level; slow, but served)
+    ex->buf.oct_scratch = nullptr; ex->buf.oct_scratch_stride = 0;
     if (ex->oct_smem > 227 * 1024) {
-        std::snprintf(g_cuda_err, sizeof(g_cuda_err), "per-level feature quota too large for the octree's shared-memory node tables (%d bytes)", ex->oct_smem);
-        return ORBX_E_UNSUPPORTED;
+        const size_t stride = (size_t)octree_table_bytes(ex->geo), need = stride * (size_t)ex->max_batch * (size_t)ex->geo.nlevels;
+        if (ex->oct_scratch_bytes < need) {
+            if (ex->oct_scratch_mem) CK(cudaFree(ex->oct_scratch_mem));
+            ex->oct_scratch_mem = nullptr; ex->oct_scratch_bytes = 0;
+            if (cudaMalloc(&ex->oct_scratch_mem, need) != cudaSuccess) { cuda_fail(cudaGetLastError(), "cudaMalloc (octree node tables)"); return ORBX_E_NOMEM; }
+            ex->oct_scratch_bytes = need;
+        }
+        ex->buf.oct_scratch = ex->oct_scratch_mem; ex->buf.oct_scratch_stride = stride;
+        ex->oct_smem = 0;
     }
     if (octree_configure(ex->oct_smem)) return cuda_fail(cudaGetLastError(), "octree smem");
     return ORBX_OK;
@@ -400,6 +410,7 @@ extern "C" int orbx_create(const orbx_params *p, int max_width, int max_height, 
     ex->pin_in = ex->pin_out = nullptr; ex->pin_in_bytes = ex->pin_out_bytes = 0;
     std::memset(&ex->lat_pending, 0, sizeof(ex->lat_pending));
     std::memset(&ex->buf, 0, sizeof(ex->buf));
+    ex->oct_scratch_mem = nullptr; ex->oct_scratch_bytes = 0;
     ex->stream = ex->stream2 = ex->s_h2d = ex->s_d2h = nullptr; ex->s_aux[0] = ex->s_aux[1] = nullptr; ex->fork_slot = 0;
     for (int i = 0; i < orbx_extractor::kMaxChunks; ++i) { ex->ev_h2d[i] = nullptr; ex->ev_done[i] = nullptr; ex->ev_fork[i] = nullptr; ex->ev_join[i] = nullptr; }
     build_reference_tables(ex);
@@ -481,6 +492,7 @@ extern "C" int orbx_destroy(orbx_extractor *ex)
     if (ex->pin_out) cudaFreeHost(ex->pin_out);
     for (void *p : ex->allocs) cudaFree(p);
     if (ex->staging_color) cudaFree(ex->staging_color);
+    if (ex->oct_scratch_mem) cudaFree(ex->oct_scratch_mem);
     if (ex->ev_split_fork) cudaEventDestroy(ex->ev_split_fork);
     if (ex->ev_split_join) cudaEventDestroy(ex->ev_split_join);
     for (auto &set : ex->ev) for (auto &e : set) if (e) cudaEventDestroy(e);

@@ -84,9 +84,13 @@ template <int kOctThreads, int kU>
 __global__ void __launch_bounds__(kOctThreads, kOctThreads == 256 ? 5 : ((kOctThreads == 512 && kU == 1) ? 2 : 1))   // latency-bound: favour resident blocks over registers
 k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, const uint32_t *__restrict__ cell_slots,
          uint32_t *keysA_all, uint32_t *keysB_all, uint16_t *nodeA_all, uint16_t *nodeB_all, uint4 *scanE_all,
-         int *__restrict__ ncand_out, uint32_t *__restrict__ kept_out, int *__restrict__ nkept_out, const int smem_keys, const int level_lo)
+         int *__restrict__ ncand_out, uint32_t *__restrict__ kept_out, int *__restrict__ nkept_out, const int smem_keys, const int level_lo,
+         unsigned char *node_scratch, const unsigned long long node_scratch_stride)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_dyn[];
+    // node tables: shared memory, or -- for a level quota whose tables do not fit one SM (more than ~2 400 features on one
+    // level) -- this problem's slice of a global scratch buffer (slow, but the configuration is served instead of refused)
+    unsigned char *smem_raw = node_scratch ? node_scratch + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * node_scratch_stride : smem_dyn;
     __shared__ OctShared S;
 
     const int level = level_lo + blockIdx.x, f = blockIdx.y + g.frame0, tid = threadIdx.x;
@@ -444,6 +448,14 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
     if (tid == 0) nkept_out[f * g.nlevels + level] = min(size, L.kept_cap);
 }
 
+// bytes of one problem's node tables (no key arrays): the slice size of the global-memory fallback
+int octree_table_bytes(const Geo &g)
+{
+    int nc = 0;
+    for (int l = 0; l < g.nlevels; ++l) nc = nc > g.lv[l].node_cap ? nc : g.lv[l].node_cap;
+    return (nc * (2 * (int)sizeof(Node) + 4 * 4 * 2 + 3 * 4 + 16 + 2) + 64 + 16 + 255) & ~255;
+}
+
 int octree_smem_bytes(const Geo &g)
 {
     int nc = 0;
@@ -489,13 +501,28 @@ void launch_octree(const Geo &g, const DevBuffers &b, int nframes, int smem_byte
     if (level_hi > g.nlevels) level_hi = g.nlevels;
     if (level_hi <= level_lo) return;
     dim3 grd(level_hi - level_lo, nframes);                 // levels [level_lo, level_hi); default: all
+    if (b.oct_scratch) {
+        // node tables in global memory (see the kernel): one slice per (frame, level) of the whole batch geometry
+        unsigned char *base = b.oct_scratch + ((size_t)g.frame0 * g.nlevels + level_lo) * b.oct_scratch_stride;
+        if (level_hi - level_lo == g.nlevels)
+            k_octree<256, 1><<<grd, 256, 0, s>>>(g, b.cell_count, b.cell_slots, b.keysA, b.keysB, b.nodeA, b.nodeB, b.scanE, b.ncand, b.kept, b.nkept,
+                                                 0, level_lo, base, b.oct_scratch_stride);
+        else
+            for (int l = level_lo; l < level_hi; ++l)     // a level range: slices of consecutive frames are nlevels apart, so one launch per level
+                for (int f = 0; f < nframes; ++f) {
+                    Geo g1 = g; g1.frame0 = g.frame0 + f;
+                    k_octree<256, 1><<<dim3(1, 1), 256, 0, s>>>(g1, b.cell_count, b.cell_slots, b.keysA, b.keysB, b.nodeA, b.nodeB, b.scanE, b.ncand, b.kept,
+                                                               b.nkept, 0, l, b.oct_scratch + ((size_t)(g.frame0 + f) * g.nlevels + l) * b.oct_scratch_stride, b.oct_scratch_stride);
+                }
+        return;
+    }
     // candidate counts scale with the level area: large levels (4K) get 1024 threads per problem
     int big = 0;
     for (int l = 0; l < g.nlevels; ++l) big = big > g.lv[l].regionW * g.lv[l].regionH ? big : g.lv[l].regionW * g.lv[l].regionH;
     if (big > 1500000) {
         static int variant = -1;                             // ORBX_OCT_BIG: 0 = 1024 threads, 1 / 3 = 1024 threads with 2 / 4 key groups in flight (default 3: 0.864 -> 0.731 -> 0.638 -> 0.608 ms per 32 4K frames), 2 = 512 threads x 4 groups (0.873)
         if (variant < 0) { const char *e = std::getenv("ORBX_OCT_BIG"); variant = e ? std::atoi(e) : 3; }
-#define OCT_ARGS g, b.cell_count, b.cell_slots, b.keysA, b.keysB, b.nodeA, b.nodeB, b.scanE, b.ncand, b.kept, b.nkept, 0, level_lo
+#define OCT_ARGS g, b.cell_count, b.cell_slots, b.keysA, b.keysB, b.nodeA, b.nodeB, b.scanE, b.ncand, b.kept, b.nkept, 0, level_lo, nullptr, 0ull
         if (variant == 0) k_octree<1024, 1><<<grd, 1024, smem_bytes, s>>>(OCT_ARGS);
         else if (variant == 1) k_octree<1024, 2><<<grd, 1024, smem_bytes, s>>>(OCT_ARGS);
         else if (variant == 3) k_octree<1024, 4><<<grd, 1024, smem_bytes, s>>>(OCT_ARGS);
@@ -505,10 +532,10 @@ void launch_octree(const Geo &g, const DevBuffers &b, int nframes, int smem_byte
     else if (nframes <= 4)
         // small batches (low-latency path): twice the threads per problem -- half the keys per warp in every sweep
         k_octree<512, 1><<<grd, 512, smem_bytes, s>>>(g, b.cell_count, b.cell_slots, b.keysA, b.keysB, b.nodeA, b.nodeB,
-                                                   b.scanE, b.ncand, b.kept, b.nkept, octree_smem_keys(g), level_lo);
+                                                   b.scanE, b.ncand, b.kept, b.nkept, octree_smem_keys(g), level_lo, nullptr, 0ull);
     else
         k_octree<256, 1><<<grd, 256, smem_bytes, s>>>(g, b.cell_count, b.cell_slots, b.keysA, b.keysB, b.nodeA, b.nodeB,
-                                                   b.scanE, b.ncand, b.kept, b.nkept, octree_smem_keys(g), level_lo);
+                                                   b.scanE, b.ncand, b.kept, b.nkept, octree_smem_keys(g), level_lo, nullptr, 0ull);
 }
 
 } // namespace orbx

@@ -86,6 +86,7 @@ struct DevBuffers {
     int *nkept;          // [F][nlevels]
     uint8_t *staging;    // device staging for host inputs [max_batch][max_h][max_w]
     orbx_keypoint *out_kps; uint8_t *out_desc; int *out_counts; // device outputs for the host path
+    unsigned char *oct_scratch; unsigned long long oct_scratch_stride;   // octree node tables in global memory when they do not fit one SM (else NULL)
 };
 
 // kernels (defined in the .cu files)
@@ -98,6 +99,7 @@ void launch_blur(const Geo &g, const DevBuffers &b, int nframes, cudaStream_t s)
 void launch_describe(const Geo &g, const DevBuffers &b, int nframes, orbx_keypoint *d_kps, uint8_t *d_desc, int *d_counts, cudaStream_t s);
 void launch_undistort(const orbx_keypoint *in, orbx_keypoint *out, int n, const float *cam, const float *dist, int literal_bug, cudaStream_t s);
 int octree_smem_bytes(const Geo &g);
+int octree_table_bytes(const Geo &g);
 int octree_configure(int smem_bytes);
 
 // search_init.cu: one windowed-search launch (SearchForInitialization and the projection-style search share it)

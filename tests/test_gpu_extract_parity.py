@@ -113,12 +113,30 @@ def test_capacity_errors(orbx):
         ex.extract_host(np.zeros((480, 640), np.uint8))
     with pytest.raises(orbx.OrbxError):
         ex.extract_host(np.zeros((2, 240, 320), np.uint8))
-    # a per-level quota the octree's shared-memory node tables cannot hold is refused with ORBX_E_UNSUPPORTED (-6), loudly
-    with pytest.raises(orbx.OrbxError, match="unsupported"):
-        big = orbx.Extractor(nfeatures=3900, nlevels=1, max_width=640, max_height=480, max_batch=1)
-        big.extract_host(np.zeros((480, 640), np.uint8))
     ok = orbx.Extractor(nfeatures=2300, nlevels=1, max_width=640, max_height=480, max_batch=1)
     assert ok.extract_host(np.zeros((480, 640), np.uint8))[2][0] == 0
+
+
+@pytest.mark.parametrize("low_latency", [True, False])
+def test_level_quota_beyond_one_sm(orbx, oracle, low_latency):
+    """A per-level quota whose octree node tables do not fit one SM's shared memory (> ~2 400 features on one level) runs
+    with the tables in global memory: same keypoints as the oracle, through the graph path and the stream path."""
+    imgs = np.stack([adversarial_frame("noise", 640, 480, seed=3), synth_frame(9)])
+    params = dict(nfeatures=3900, nlevels=1)
+    ex = orbx.Extractor(max_width=640, max_height=480, max_batch=2, **params)
+    ex.set_low_latency(low_latency)
+    oex = oracle.OracleExtractor(**params)
+    kps, desc, counts = ex.extract_host(imgs)
+    assert _compare_frame(oracle, ex, oex, imgs[0], 0, kps, desc, counts) > 3000
+    _compare_frame(oracle, ex, oex, imgs[1], 1, kps, desc, counts)
+    # two levels, the first one beyond the limit
+    params = dict(nfeatures=5000, nlevels=2, scale_factor=1.5)
+    ex = orbx.Extractor(max_width=640, max_height=480, max_batch=2, **params)
+    ex.set_low_latency(low_latency)
+    oex = oracle.OracleExtractor(**params)
+    kps, desc, counts = ex.extract_host(imgs)
+    _compare_frame(oracle, ex, oex, imgs[0], 0, kps, desc, counts)
+    _compare_frame(oracle, ex, oex, imgs[1], 1, kps, desc, counts)
 
 
 def test_4k_frame_nfeatures_8000(orbx, oracle):
