@@ -40,7 +40,8 @@ extern "C" {
 #define ORBX_E_CAPACITY (-4)  /* frame/batch larger than the handle was created for */
 #define ORBX_E_NODEVICE (-5)  /* no usable sm_100 device */
 #define ORBX_E_UNSUPPORTED (-6) /* outside the supported range: a level wider/taller than 4095 + 32 px, a FAST cell > 64 px, or a per-level
-                                  feature quota above ~2 400 (the octree's shared-memory node tables); orbx_last_cuda_error() says which */
+                                  feature quota above 65 531 (16-bit node ids).  Quotas above ~2 400 per level run with the octree's node
+                                  tables in global instead of shared memory (slower, same results) */
 
 #define ORBX_MAX_LEVELS 16
 #define ORBX_EDGE_THRESHOLD 19 /* pyramid border, src/ORBextractor.cpp:24 */
