@@ -120,6 +120,11 @@ int orbx_extract_device(orbx_extractor *ex, const uint8_t *d_imgs, size_t row_pi
  * staging for pageable caller buffers and one download.  Results are identical.  enabled = 0 restores the stream path. */
 int orbx_set_low_latency(orbx_extractor *ex, int enabled);
 
+/* Debug aid: a handle created while the environment has ORBX_GUARD=1 surrounds every device buffer it owns with a 4 KB canary
+ * zone; this call synchronises the device and checks all of them.  ORBX_OK = intact, ORBX_E_CUDA = a kernel wrote outside a
+ * buffer (*bad_buffer = its index in allocation order), ORBX_E_UNSUPPORTED = the handle has no guard zones. */
+int orbx_debug_guard_check(orbx_extractor *ex, int *bad_buffer);
+
 /* Input pixel format of the following extract calls: channels = 1 (gray, default), 3 or 4 interleaved 8-bit
  * channels; rgb_order = 0 for BGR(A), 1 for RGB(A).  Colour input is converted to gray inside the level-0 kernel with
  * OpenCV's 8U fixed point (R*9798 + G*19235 + B*3735 + 16384) >> 15, replacing the cv::cvtColor call in front of the

@@ -21,7 +21,7 @@ CAND_DTYPE = np.dtype([("x", "<i2"), ("y", "<i2"), ("score", "<i4")])
 ABI_SYMBOLS = [
     "orbx_strerror", "orbx_last_cuda_error", "orbx_version", "orbx_build_id", "orbx_device_count",
     "orbx_create", "orbx_destroy", "orbx_nlevels", "orbx_capacity", "orbx_tables",
-    "orbx_extract_host", "orbx_extract_host_begin", "orbx_extract_host_end", "orbx_extract_device", "orbx_set_pyramid_border", "orbx_set_device_split", "orbx_set_low_latency", "orbx_set_input_format", "orbx_undistort_keypoints_device",
+    "orbx_extract_host", "orbx_extract_host_begin", "orbx_extract_host_end", "orbx_extract_device", "orbx_set_pyramid_border", "orbx_set_device_split", "orbx_set_low_latency", "orbx_debug_guard_check", "orbx_set_input_format", "orbx_undistort_keypoints_device",
     "orbx_level_dims", "orbx_download_level", "orbx_level_device_ptr",
     "orbx_download_candidates", "orbx_download_kept", "orbx_max_candidates", "orbx_launch_count",
     "orbx_set_profiling", "orbx_stage_times", "orbm_set_profiling", "orbm_knn2_times",
@@ -94,6 +94,7 @@ def load():
     L.orbx_set_pyramid_border.argtypes = [vp, i32]
     L.orbx_set_device_split.argtypes = [vp, i32]
     L.orbx_set_low_latency.argtypes = [vp, i32]
+    L.orbx_debug_guard_check.argtypes = [vp, C.POINTER(i32)]
     L.orbx_set_input_format.argtypes = [vp, i32, i32]
     L.orbx_undistort_keypoints_device.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp]
     L.orbx_level_dims.argtypes = [vp, i32, C.POINTER(i32), C.POINTER(i32)]
@@ -183,6 +184,11 @@ class Extractor:
 
     def set_device_split(self, nsplit):
         check(load().orbx_set_device_split(self.h, int(nsplit)))
+
+    def guard_check(self):
+        """ORBX_GUARD=1 handles: raises if a kernel wrote into a canary zone around one of the handle's device buffers."""
+        bad = C.c_int(-1)
+        check(load().orbx_debug_guard_check(self.h, C.byref(bad)))
 
     def set_low_latency(self, on):
         check(load().orbx_set_low_latency(self.h, int(on)))

@@ -56,6 +56,8 @@ struct orbx_extractor {
     Geo full;                    // geometry of (max_w, max_h): sized every buffer
     DevBuffers buf;
     std::vector<void *> allocs;
+    std::vector<size_t> alloc_bytes;             // payload sizes, recorded only with guard zones
+    int guard;                                   // ORBX_GUARD=1: canary zones around every device buffer (orbx_debug_guard_check)
     cudaStream_t stream, stream2, s_h2d, s_d2h;   // compute (two, alternating chunks) / upload / download
     static const int kMaxChunks = 8;
     cudaEvent_t ev_h2d[kMaxChunks], ev_done[kMaxChunks];
@@ -333,13 +335,44 @@ static int build_geometry(const orbx_extractor *ex, int w, int h, Geo &g, std::v
     return ORBX_OK;
 }
 
+// Debug aid (ORBX_GUARD=1 at orbx_create; compute-sanitizer is not available on every pool): every device buffer of the handle
+// gets a 4 KB canary zone in front of and behind it, and orbx_debug_guard_check() verifies that no kernel wrote into one.
+static const size_t kGuardBytes = 4096;
+static const int kGuardByte = 0xA5;
 template <typename T> static int dev_alloc(orbx_extractor *ex, T **p, size_t count)
 {
     void *q = nullptr;
-    cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T), gz = ex->guard ? kGuardBytes : 0;
+    cudaError_t e = cudaMalloc(&q, bytes + 2 * gz);
     if (e != cudaSuccess) { cuda_fail(e, "cudaMalloc"); return ORBX_E_NOMEM; }
     ex->allocs.push_back(q);
-    *p = (T *)q;
+    if (gz) {
+        if (cudaMemset(q, kGuardByte, gz) != cudaSuccess || cudaMemset((char *)q + gz + bytes, kGuardByte, gz) != cudaSuccess) return cuda_fail(cudaGetLastError(), "cudaMemset");
+        ex->alloc_bytes.push_back(bytes);
+    }
+    *p = (T *)((char *)q + gz);
+    return ORBX_OK;
+}
+
+extern "C" int orbx_debug_guard_check(orbx_extractor *ex, int *bad_buffer)
+{
+    if (!ex) return ORBX_E_INVALID;
+    if (bad_buffer) *bad_buffer = -1;
+    if (!ex->guard) return ORBX_E_UNSUPPORTED;          // the handle was created without ORBX_GUARD=1
+    CK(cudaSetDevice(ex->device));
+    CK(cudaDeviceSynchronize());
+    std::vector<unsigned char> h(2 * kGuardBytes);
+    for (size_t i = 0; i < ex->allocs.size() && i < ex->alloc_bytes.size(); ++i) {
+        const char *q = (const char *)ex->allocs[i];
+        CK(cudaMemcpy(h.data(), q, kGuardBytes, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(h.data() + kGuardBytes, q + kGuardBytes + ex->alloc_bytes[i], kGuardBytes, cudaMemcpyDeviceToHost));
+        for (unsigned char b : h)
+            if (b != (unsigned char)kGuardByte) {
+                if (bad_buffer) *bad_buffer = (int)i;
+                std::snprintf(g_cuda_err, sizeof(g_cuda_err), "guard zone of device buffer %d (allocation order in orbx_create) was overwritten", (int)i);
+                return ORBX_E_CUDA;
+            }
+    }
     return ORBX_OK;
 }
 
@@ -401,6 +434,8 @@ extern "C" int orbx_create(const orbx_params *p, int max_width, int max_height, 
     orbx_extractor *ex = new (std::nothrow) orbx_extractor();
     if (!ex) return ORBX_E_NOMEM;
     ex->params = *p; ex->device = device; ex->max_w = max_width; ex->max_h = max_height; ex->max_batch = max_batch;
+    ex->guard = 0;
+    if (const char *e = std::getenv("ORBX_GUARD")) ex->guard = std::atoi(e) != 0;
     ex->launches = 0; ex->last_frames = 0; ex->border_on = 0; ex->in_channels = 1; ex->in_rgb = 0;
     ex->staging_color = nullptr; ex->staging_color_bytes = 0; ex->profiling = 0; ex->prof_calls = 0;
     for (auto &set : ex->ev) for (auto &e : set) e = nullptr;
