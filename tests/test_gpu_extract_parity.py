@@ -404,6 +404,16 @@ def test_low_latency_graph_path_equals_stream_path(orbx, oracle):
     # the intermediate buffers are the ones the stage accessors read
     kps, desc, counts = ex.extract_host(imgs[:1])
     _compare_frame(oracle, ex, oex, imgs[0], 0, kps, desc, counts)
+    # one handle, alternating frame sizes: the geometry tables are re-uploaded and the graph re-captured each time
+    small = synth_batch([50, 51], 320, 240)
+    oex_small = [oex(im) for im in small]
+    for rep in range(2):
+        k2, d2, c2 = ex.extract_host(small[rep:rep + 1])
+        ko, do = oex_small[rep]
+        n = int(c2[0])
+        assert n == len(ko) and np.array_equal(k2[0, :n]["x"], ko["x"]) and np.array_equal(k2[0, :n]["y"], ko["y"])
+        assert np.unpackbits(d2[0, :n] ^ do).sum() <= 1e-3 * do.size * 8
+        check(*ex.extract_host(imgs[rep:rep + 1]), [rep])
     # device pointers: the second graph slot
     dev = torch.device("cuda:0")
     d_f = torch.from_numpy(imgs[:2].copy()).to(dev); cap = ex.capacity
