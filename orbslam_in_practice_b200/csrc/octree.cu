@@ -80,7 +80,10 @@ __device__ __forceinline__ uint32_t comp(const uint4 &v, int q) { return q == 0 
 // kU: key groups a warp loads before it processes them.  Problems whose keys live in global memory (4K-sized levels: tens of
 // thousands of candidates, one block per SM because of the node tables) are bound by the latency of the dependent L2 round
 // trips of every sweep (ncu, round 2: st_long 9.4 per issue at 39 % issue-active); kU = 4 puts four groups' loads in flight.
-template <int kOctThreads, int kU>
+// kGlobalTables: the node tables live in a global scratch slice instead of shared memory (level quotas beyond one SM); a
+// template parameter, not a runtime pointer choice, so that the normal instantiations keep shared-memory addressing (as a
+// runtime select every node-table access became a generic load: VGA octree 0.140 -> 0.161 ms).
+template <int kOctThreads, int kU, bool kGlobalTables = false>
 __global__ void __launch_bounds__(kOctThreads, kOctThreads == 256 ? 5 : ((kOctThreads == 512 && kU == 1) ? 2 : 1))   // latency-bound: favour resident blocks over registers
 k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, const uint32_t *__restrict__ cell_slots,
          uint32_t *keysA_all, uint32_t *keysB_all, uint16_t *nodeA_all, uint16_t *nodeB_all, uint4 *scanE_all,
@@ -90,7 +93,7 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
     extern __shared__ __align__(16) unsigned char smem_dyn[];
     // node tables: shared memory, or -- for a level quota whose tables do not fit one SM (more than ~2 400 features on one
     // level) -- this problem's slice of a global scratch buffer (slow, but the configuration is served instead of refused)
-    unsigned char *smem_raw = node_scratch ? node_scratch + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * node_scratch_stride : smem_dyn;
+    unsigned char *smem_raw = kGlobalTables ? node_scratch + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * node_scratch_stride : smem_dyn;
     __shared__ OctShared S;
 
     const int level = level_lo + blockIdx.x, f = blockIdx.y + g.frame0, tid = threadIdx.x;
@@ -403,7 +406,10 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
             for (int u = 0; u < kU; ++u) {
                 const int p = pb + u * kOctThreads;
                 gis[u] = 0; qs[u] = 0; keys[u] = 0; es[u] = 0;
-                if (p < n) { gis[u] = nA[p]; keys[u] = kA[p]; qs[u] = qbuf[p]; es[u] = E32[p]; }   // qbuf / E32 are stale for unsplit nodes and unused there
+                if (p < n) {
+                    gis[u] = nA[p]; keys[u] = kA[p];
+                    if (kU > 1) { qs[u] = qbuf[p]; es[u] = E32[p]; }   // ahead of their use (stale for unsplit nodes and unused there); kU == 1 loads them on demand
+                }
             }
 #pragma unroll
             for (int u = 0; u < kU; ++u) {
@@ -413,11 +419,11 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
                 const uint32_t key = keys[u];
                 if (split[gi]) {
                     const Node nd = nodes[gi];
-                    const int q = qs[u];
+                    const int q = kU > 1 ? qs[u] : (int)qbuf[p];
                     int off = 0;
 #pragma unroll
                     for (int qq = 0; qq < 3; ++qq) if (qq < q) off += childCnt[4 * gi + qq];
-                    const int np = nd.begin + off + (int)(es[u] - comp(nodeFirst[gi], q));
+                    const int np = nd.begin + off + (int)((kU > 1 ? es[u] : E32[p]) - comp(nodeFirst[gi], q));
                     kB[np] = key; nB[np] = (uint16_t)newIdx[4 * gi + q];
                 } else {
                     kB[p] = key; nB[p] = (uint16_t)newIdx[4 * gi];
@@ -505,13 +511,13 @@ void launch_octree(const Geo &g, const DevBuffers &b, int nframes, int smem_byte
         // node tables in global memory (see the kernel): one slice per (frame, level) of the whole batch geometry
         unsigned char *base = b.oct_scratch + ((size_t)g.frame0 * g.nlevels + level_lo) * b.oct_scratch_stride;
         if (level_hi - level_lo == g.nlevels)
-            k_octree<256, 1><<<grd, 256, 0, s>>>(g, b.cell_count, b.cell_slots, b.keysA, b.keysB, b.nodeA, b.nodeB, b.scanE, b.ncand, b.kept, b.nkept,
-                                                 0, level_lo, base, b.oct_scratch_stride);
+            k_octree<256, 1, true><<<grd, 256, 0, s>>>(g, b.cell_count, b.cell_slots, b.keysA, b.keysB, b.nodeA, b.nodeB, b.scanE, b.ncand, b.kept, b.nkept,
+                                                       0, level_lo, base, b.oct_scratch_stride);
         else
             for (int l = level_lo; l < level_hi; ++l)     // a level range: slices of consecutive frames are nlevels apart, so one launch per level
                 for (int f = 0; f < nframes; ++f) {
                     Geo g1 = g; g1.frame0 = g.frame0 + f;
-                    k_octree<256, 1><<<dim3(1, 1), 256, 0, s>>>(g1, b.cell_count, b.cell_slots, b.keysA, b.keysB, b.nodeA, b.nodeB, b.scanE, b.ncand, b.kept,
+                    k_octree<256, 1, true><<<dim3(1, 1), 256, 0, s>>>(g1, b.cell_count, b.cell_slots, b.keysA, b.keysB, b.nodeA, b.nodeB, b.scanE, b.ncand, b.kept,
                                                                b.nkept, 0, l, b.oct_scratch + ((size_t)(g.frame0 + f) * g.nlevels + l) * b.oct_scratch_stride, b.oct_scratch_stride);
                 }
         return;
