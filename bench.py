@@ -716,11 +716,53 @@ def extract_sample(_lib, torch, dev, local, rank, world, name, nframes, K, barri
     algo = w * h + sum(a * b for a, b in lv[1:]) + nf * 60
     peaks, _ = measured_peaks()
     val = world * nframes / (ms * 1e-3)
+    out = {"metric": "orb_extract_frames_per_s", "value": val, "unit": "frames/s", "ms_per_step": ms, "steps": K,
+           "config": {"workload": desc, "sample": "%d frames per GPU, device resident, one handle" % nframes, "nfeatures": nf},
+           "keypoints_per_frame": kp / nframes, "stage_ms": {n: float(m) for n, m in zip(STAGES, stage)},
+           "whole_pipeline_hbm_frac": val / world * algo / 1e9 / peaks["hbm_gbs"]}
+    if name == "kitti":
+        # BASELINE configs[2]: "... plus left-right ORBmatcher Hamming matching": frames (2i, 2i+1) are a stereo pair; left -> right
+        # brute-force best-2 + TH_LOW / ratio 0.7 on the descriptors the extraction above left on the device (ORBmatcher.cpp:37-67)
+        cnt = d_c.cpu().numpy()
+        npairs = nframes // 2
+        mm = _lib.Matcher(cap, cap, local)
+        tri = torch.empty((4, npairs, cap), dtype=torch.int32, device=dev)
+        t_pa = torch.arange(0, 2 * npairs, 2, dtype=torch.int32, device=dev); t_pb = t_pa + 1
+        wsb = _lib.load().orbm_knn2_pairs_workspace_bytes(cap, npairs)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+
+        def match_step():       # ONE batched launch pair for all stereo pairs of the batch (orbm_knn2_pairs_device)
+            mm.knn2_pairs_device(d_d.data_ptr(), d_c.data_ptr(), cap, t_pa.data_ptr(), t_pb.data_ptr(), npairs, tri[0].data_ptr(), tri[1].data_ptr(),
+                                 tri[2].data_ptr(), 50, 0.7, tri[3].data_ptr(), ws.data_ptr(), wsb, st.cuda_stream)
+
+        for _ in range(2):
+            match_step()
+        barrier()
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record(st)
+        for _ in range(K):
+            match_step()
+        m1.record(st)
+        barrier()
+        mms = max_over_ranks(m0.elapsed_time(m1)) / K
+        pairs = float(sum(int(cnt[2 * i]) * int(cnt[2 * i + 1]) for i in range(npairs)))
+        lr = {"metric": "stereo_left_right_match_pairs_per_s", "value": world * npairs / (mms * 1e-3), "unit": "stereo pairs/s",
+              "ms_per_step": mms, "stereo_pairs_per_step": npairs, "gpairs_per_s": world * pairs / (mms * 1e-3) / 1e9,
+              "config": "left -> right best-2 over ~%d x %d descriptors per pair, TH_LOW 50, ratio 0.7, all pairs of the batch in one launch pair (orbm_knn2_pairs_device)" % (nf, nf)}
+        if rank == 0:
+            from oracle import oracle as O                      # checker: pair 0 against the CPU restatement
+            nl, nr = int(cnt[0]), int(cnt[1])
+            dd = d_d[:2].cpu().numpy()
+            want = O.knn2(dd[0, :nl], dd[1, :nr], 0, host_cores())
+            wm = O.ratio_select(*want, 50, 0.7)
+            got = tri[:, 0].cpu().numpy()[:, :nl]
+            if not all(np.array_equal(g_, w_) for g_, w_ in zip(got, list(want) + [wm])):
+                raise SystemExit("left-right matching parity check against the oracle FAILED")
+            lr["parity_checked"] = True
+        out["left_right_matching"] = lr
+        del mm
     del ex
-    return {"metric": "orb_extract_frames_per_s", "value": val, "unit": "frames/s", "ms_per_step": ms, "steps": K,
-            "config": {"workload": desc, "sample": "%d frames per GPU, device resident, one handle" % nframes, "nfeatures": nf},
-            "keypoints_per_frame": kp / nframes, "stage_ms": {n: float(m) for n, m in zip(STAGES, stage)},
-            "whole_pipeline_hbm_frac": val / world * algo / 1e9 / peaks["hbm_gbs"]}
+    return out
 
 
 def run_match(args, _lib, torch, dist, dev, world, rank, local, stream, K, barrier, max_over_ranks):

@@ -222,6 +222,18 @@ int orbm_knn2_sharded_device(orbm_matcher *m, const uint8_t *d_query, int nq, co
                              int th_low, float ratio, int32_t *d_match, void *stream);
 int orbm_exchange_status(orbm_matcher *m);
 
+/* Many independent brute-force scans in one launch pair: descriptor rows of frame d_pair_a[p] (queries) against those of frame
+ * d_pair_b[p] (database), both inside the extractor's output layout d_desc[nframes][capacity][32] with d_counts[nframes] on the
+ * device -- e.g. left -> right matching of a batch of stereo pairs (BASELINE configs[2]; the reference has no stereo matcher,
+ * this is its best-2 scan src/ORBmatcher.cpp:37-62 + acceptance :65-67 applied per pair).  Outputs are [npairs][capacity]:
+ * d1 / idx1 (row inside frame b, -1 if it has none) / d2 and, if d_match != NULL, the accepted row or -1; entries past the
+ * query frame's count are (INT_MAX, -1, INT_MAX, -1).  workspace: orbm_knn2_pairs_workspace_bytes(capacity, npairs). */
+size_t orbm_knn2_pairs_workspace_bytes(int capacity, int npairs);
+int orbm_knn2_pairs_device(orbm_matcher *m, const uint8_t *d_desc, const int32_t *d_counts, int capacity,
+                           const int32_t *d_pair_a, const int32_t *d_pair_b, int npairs,
+                           int32_t *d_d1, int32_t *d_idx1, int32_t *d_d2, int th_low, float ratio, int32_t *d_match,
+                           void *d_workspace, size_t workspace_bytes, void *stream);
+
 /* ORBmatcher::SearchForInitialization (src/ORBmatcher.cpp:9-126) on extractor outputs, including the Frame grid
  * it queries (Frame::AssignFeaturesToGrid / GetFeaturesInArea, src/Frame.cpp:144-168, 219-271): windowed best-2
  * with the sequential one-to-one gate, TH_LOW / ratio acceptance, rotation-histogram filter, prev-matched update.

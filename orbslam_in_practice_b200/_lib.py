@@ -25,7 +25,7 @@ ABI_SYMBOLS = [
     "orbx_level_dims", "orbx_download_level", "orbx_level_device_ptr",
     "orbx_download_candidates", "orbx_download_kept", "orbx_max_candidates", "orbx_launch_count",
     "orbx_set_profiling", "orbx_stage_times", "orbm_set_profiling", "orbm_knn2_times",
-    "orbm_create", "orbm_destroy", "orbm_launch_count", "orbm_hamming_pairs_host",
+    "orbm_knn2_pairs_workspace_bytes", "orbm_knn2_pairs_device", "orbm_create", "orbm_destroy", "orbm_launch_count", "orbm_hamming_pairs_host",
     "orbm_knn2_device", "orbm_knn2_host", "orbm_ratio_select_device", "orbm_merge_shards_device",
     "orbm_popc_peak", "orbm_search_init_workspace_bytes", "orbm_search_init_device", "orbm_search_init_host",
     "orbm_search_window_device", "orbm_search_window_host", "orbm_search_groups_device", "orbm_search_groups_host",
@@ -123,6 +123,9 @@ def load():
     L.orbm_search_window_host.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, vp, C.POINTER(i32), vp]
     L.orbm_search_groups_device.argtypes = [vp, vp, vp, vp, vp, i32, vp, vp, i32, vp, vp, i32, f32, i32, vp, sz, vp]
     L.orbm_search_groups_host.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, i32, vp, C.POINTER(i32), i32, f32, i32]
+    L.orbm_knn2_pairs_workspace_bytes.restype = sz
+    L.orbm_knn2_pairs_workspace_bytes.argtypes = [i32, i32]
+    L.orbm_knn2_pairs_device.argtypes = [vp, vp, vp, i32, vp, vp, i32, vp, vp, vp, i32, f32, vp, vp, sz, vp]
     L.orbm_search_init_workspace_bytes.restype = sz
     L.orbm_search_init_workspace_bytes.argtypes = [i32, i32]
     L.orbm_exchange_create.argtypes = [vp, i32, i32, i32, vp]
@@ -296,6 +299,11 @@ class Matcher:
 
     def knn2_device(self, q_ptr, nq, db_ptr, ndb, index_base, d1_ptr, idx1_ptr, d2_ptr, stream=0):
         check(load().orbm_knn2_device(self.h, q_ptr, nq, db_ptr, ndb, index_base, d1_ptr, idx1_ptr, d2_ptr, stream))
+
+    def knn2_pairs_device(self, desc_ptr, counts_ptr, capacity, pair_a_ptr, pair_b_ptr, npairs, d1_ptr, idx1_ptr, d2_ptr,
+                          th_low, ratio, match_ptr, ws_ptr, ws_bytes, stream=0):
+        check(load().orbm_knn2_pairs_device(self.h, desc_ptr, counts_ptr, capacity, pair_a_ptr, pair_b_ptr, npairs, d1_ptr, idx1_ptr,
+                                            d2_ptr, th_low, ratio, match_ptr, ws_ptr, ws_bytes, stream))
 
     def ratio_select_device(self, d1_ptr, idx1_ptr, d2_ptr, nq, th_low, ratio, match_ptr, stream=0):
         check(load().orbm_ratio_select_device(self.h, d1_ptr, idx1_ptr, d2_ptr, nq, th_low, ratio, match_ptr, stream))

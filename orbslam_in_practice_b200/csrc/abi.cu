@@ -28,6 +28,9 @@ void launch_knn2_empty(int nq, int *d1, int *idx1, int *d2, cudaStream_t s);
 void launch_knn2(const uint8_t *d_query, int nq, const uint8_t *d_db, int ndb, int index_base, int nseg, int seg_rows,
                  uint2 *partial, int *d1, int *idx1, int *d2, cudaStream_t s, cudaEvent_t *ev);
 void launch_hamming_pairs(const uint8_t *a, const uint8_t *b, int n, int *dist, cudaStream_t s);
+size_t knn2_pairs_workspace_bytes(int cap, int npairs);
+void launch_knn2_pairs(const uint8_t *desc, const int *counts, int cap, const int *pair_a, const int *pair_b, int npairs, uint2 *partial,
+                       int *d1, int *idx1, int *d2, int th_low, float ratio, int *match, cudaStream_t s);
 void launch_ratio_select(const int *d1, const int *idx1, const int *d2, int nq, int th, float ratio, int *match, cudaStream_t s);
 void launch_merge_shards(const int *d1, const int *idx1, const int *d2, int nshards, int nq, size_t stride, int *od1, int *oidx1, int *od2, cudaStream_t s);
 int run_popc_bench(int mode, int sm_count, double *ops_per_second);
@@ -1445,6 +1448,30 @@ static orbm_window_params search_init_params(int window, float nnratio, int chec
     p.gate = 0; p.th_dist = 50; p.nnratio = nnratio; p.check_orientation = check_orientation ? 1 : 0; p.update_centers = 1;
     p.width = width; p.height = height; p.literal_gridid_bug = literal_gridid_bug ? 1 : 0;
     return p;
+}
+
+extern "C" size_t orbm_knn2_pairs_workspace_bytes(int capacity, int npairs)
+{
+    if (capacity < 1 || npairs < 1) return 0;
+    return knn2_pairs_workspace_bytes(capacity, npairs);
+}
+
+extern "C" int orbm_knn2_pairs_device(orbm_matcher *m, const uint8_t *d_desc, const int32_t *d_counts, int capacity,
+                                      const int32_t *d_pair_a, const int32_t *d_pair_b, int npairs,
+                                      int32_t *d_d1, int32_t *d_idx1, int32_t *d_d2, int th_low, float ratio, int32_t *d_match,
+                                      void *d_workspace, size_t workspace_bytes, void *stream)
+{
+    if (!m || npairs < 0 || capacity < 1 || capacity >= (1 << 22)) return ORBX_E_INVALID;
+    if (npairs == 0) return ORBX_OK;
+    if (!d_desc || !d_counts || !d_pair_a || !d_pair_b || !d_d1 || !d_idx1 || !d_d2 || !d_workspace) return ORBX_E_INVALID;
+    if (npairs > 65535) return ORBX_E_CAPACITY;                        // grid.z / grid.y
+    if (workspace_bytes < knn2_pairs_workspace_bytes(capacity, npairs)) return ORBX_E_CAPACITY;
+    CK(cudaSetDevice(m->device));
+    cudaStream_t s = stream ? (cudaStream_t)stream : m->stream;
+    launch_knn2_pairs(d_desc, d_counts, capacity, d_pair_a, d_pair_b, npairs, (uint2 *)d_workspace, d_d1, d_idx1, d_d2, th_low, ratio, d_match, s);
+    m->launches += 2;
+    CK(cudaGetLastError());
+    return ORBX_OK;
 }
 
 extern "C" int orbm_search_init_device(orbm_matcher *m, const orbx_keypoint *d_kps, const uint8_t *d_desc, const int32_t *d_counts,

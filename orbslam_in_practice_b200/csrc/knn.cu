@@ -82,18 +82,16 @@ __device__ __forceinline__ uint32_t hamming_key(const uint32_t (&q)[8], const ui
     return mad_u32(__popc(c3), W4, key);
 }
 
+// one block's share of a scan: queries [q0, q0 + kQPB) against database segment `seg` (rows [seg * seg_rows, ...))
 template <int CSA>
-__global__ void __launch_bounds__(kKnnThreads, 4)
-k_knn2(const uint4 *__restrict__ query, int nq, const uint4 *__restrict__ db, int ndb, int seg_rows,
-       uint2 *__restrict__ partial)
+__device__ __forceinline__ void knn2_block(const uint4 *__restrict__ query, int nq, const uint4 *__restrict__ db, int ndb, int seg_rows,
+                                           const int seg, const int q0, uint2 *__restrict__ partial)
 {
     __shared__ __align__(16) uint4 tile[2][kTileRows * 2];
 
     const int tid = threadIdx.x;
-    const int seg = blockIdx.y;
     const int row0 = seg * seg_rows;
     const int rows = min(seg_rows, ndb - row0);
-    const int q0 = blockIdx.x * kQPB;
 
     uint32_t q[kQPT][8];
     uint32_t k1[kQPT], k2[kQPT];
@@ -169,6 +167,64 @@ k_knn2(const uint4 *__restrict__ query, int nq, const uint4 *__restrict__ db, in
         const int qi = q0 + i * kKnnThreads + tid;
         if (qi < nq) partial[(size_t)seg * nq + qi] = make_uint2(k1[i], k2[i]);
     }
+}
+
+template <int CSA>
+__global__ void __launch_bounds__(kKnnThreads, 4)
+k_knn2(const uint4 *__restrict__ query, int nq, const uint4 *__restrict__ db, int ndb, int seg_rows,
+       uint2 *__restrict__ partial)
+{
+    knn2_block<CSA>(query, nq, db, ndb, seg_rows, blockIdx.y, blockIdx.x * kQPB, partial);
+}
+
+// Many small, independent scans in ONE launch (blockIdx.z = pair): descriptor rows of frame pair_a[p] against those of frame
+// pair_b[p], both inside the extractor's output layout desc[F][cap][32] with counts[F] on the device -- the left -> right
+// matching of a batch of stereo pairs (BASELINE configs[2]).  A 2 000 x 2 000 scan alone is 32 blocks: launch-latency bound
+// (64 us per pair through k_knn2 + merge + select); a batch of them fills the GPU.
+template <int CSA>
+__global__ void __launch_bounds__(kKnnThreads, 4)
+k_knn2_pairs(const uint4 *__restrict__ desc, const int *__restrict__ counts, int cap, const int *__restrict__ pair_a, const int *__restrict__ pair_b,
+             int seg_rows, int nseg_max, uint2 *__restrict__ partial)
+{
+    const int p = blockIdx.z;
+    const int a = pair_a[p], b = pair_b[p];
+    const int nq = min(max(counts[a], 0), cap), ndb = min(max(counts[b], 0), cap);
+    const int q0 = blockIdx.x * kQPB, seg = blockIdx.y;
+    if (q0 >= nq || seg * seg_rows >= ndb) return;                      // block-uniform
+    knn2_block<CSA>(desc + 2 * (size_t)a * cap, nq, desc + 2 * (size_t)b * cap, ndb, seg_rows, seg, q0,
+                    partial + (size_t)p * nseg_max * cap + (size_t)seg * (cap - nq));   // knn2_block indexes [seg * nq + qi]: land on [seg * cap + qi]
+}
+
+// fold a pair's segments (ascending row ranges) and apply TH_LOW / the float ratio test (ORBmatcher.cpp:65-67) in the same pass
+__global__ void __launch_bounds__(256)
+k_knn2_pairs_merge(const uint2 *__restrict__ partial, const int *__restrict__ counts, int cap, const int *__restrict__ pair_a,
+                   const int *__restrict__ pair_b, int seg_rows, int nseg_max, int *__restrict__ d1, int *__restrict__ idx1, int *__restrict__ d2,
+                   int th_low, float ratio, int *__restrict__ match)
+{
+    const int p = blockIdx.y, qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= cap) return;
+    const int nq = min(max(counts[pair_a[p]], 0), cap), ndb = min(max(counts[pair_b[p]], 0), cap);
+    const size_t o = (size_t)p * cap + qi;
+    if (qi >= nq) { d1[o] = INT_MAX; idx1[o] = -1; d2[o] = INT_MAX; if (match) match[o] = -1; return; }   // rows past the frame's count: defined, empty
+    const int nseg = (ndb + seg_rows - 1) / seg_rows;
+    uint32_t b1 = kNoKey, b2 = kNoKey; int bseg = 0;
+    const uint2 *ps = partial + (size_t)p * nseg_max * cap + qi;
+    for (int s = 0; s < nseg; ++s) {
+        const uint2 k = ps[(size_t)s * cap];
+        // keys are (distance << 22 | row in segment): compare distances first, earlier segment wins ties (ascending rows)
+        const uint32_t ks[2] = { k.x, k.y };
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            if (ks[j] == kNoKey) continue;
+            const uint32_t dist = ks[j] >> kIdxBits;
+            if (b1 == kNoKey || dist < (b1 >> kIdxBits)) { b2 = b1; b1 = ks[j]; bseg = s; }
+            else if (b2 == kNoKey || dist < (b2 >> kIdxBits)) b2 = ks[j];
+        }
+    }
+    const int best = b1 == kNoKey ? INT_MAX : (int)(b1 >> kIdxBits), best2 = b2 == kNoKey ? INT_MAX : (int)(b2 >> kIdxBits);
+    const int bidx = b1 == kNoKey ? -1 : (int)(b1 & ((1u << kIdxBits) - 1u)) + bseg * seg_rows;
+    d1[o] = best; idx1[o] = bidx; d2[o] = best2;
+    if (match) match[o] = (bidx >= 0 && best <= th_low && (float)best < __fmul_rn((float)best2, ratio)) ? bidx : -1;
 }
 
 // fold the per-segment pairs: segments are ascending index ranges, so (distance, segment, row)
@@ -389,6 +445,29 @@ void launch_knn2(const uint8_t *d_query, int nq, const uint8_t *d_db, int ndb, i
     if (ev) cudaEventRecord(ev[1], s);
     k_knn2_merge<<<(nq + 255) / 256, 256, 0, s>>>(partial, nq, nseg, seg_rows, index_base, d1, idx1, d2);
     if (ev) cudaEventRecord(ev[2], s);
+}
+
+// seg_rows / nseg_max of the batched scan depend on the row capacity only (the counts live on the device)
+void knn2_pairs_geometry(int cap, int *seg_rows, int *nseg_max)
+{
+    *seg_rows = kTileRows;                                   // one 4 KB tile per block: the most blocks a small scan can give
+    *nseg_max = (cap + kTileRows - 1) / kTileRows;
+}
+size_t knn2_pairs_workspace_bytes(int cap, int npairs)
+{
+    int sr, ns;
+    knn2_pairs_geometry(cap, &sr, &ns);
+    return (size_t)npairs * ns * cap * sizeof(uint2);
+}
+void launch_knn2_pairs(const uint8_t *desc, const int *counts, int cap, const int *pair_a, const int *pair_b, int npairs, uint2 *partial,
+                       int *d1, int *idx1, int *d2, int th_low, float ratio, int *match, cudaStream_t s)
+{
+    if (npairs <= 0 || cap <= 0) return;
+    int seg_rows, nseg_max;
+    knn2_pairs_geometry(cap, &seg_rows, &nseg_max);
+    dim3 grd((cap + kQPB - 1) / kQPB, nseg_max, npairs);
+    k_knn2_pairs<kDefaultCsa><<<grd, kKnnThreads, 0, s>>>((const uint4 *)desc, counts, cap, pair_a, pair_b, seg_rows, nseg_max, partial);
+    k_knn2_pairs_merge<<<dim3((cap + 255) / 256, npairs), 256, 0, s>>>(partial, counts, cap, pair_a, pair_b, seg_rows, nseg_max, d1, idx1, d2, th_low, ratio, match);
 }
 
 void launch_hamming_pairs(const uint8_t *a, const uint8_t *b, int n, int *dist, cudaStream_t s)

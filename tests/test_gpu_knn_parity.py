@@ -96,3 +96,40 @@ def test_peer_exchange_single_rank_equals_plain_knn(orbx, oracle):
     got = out.cpu().numpy()
     assert np.array_equal(got[0], o1) and np.array_equal(got[1], oi) and np.array_equal(got[2], o2)
     assert np.array_equal(got[3], oracle.ratio_select(o1, oi, o2, 50, 0.7))
+
+
+def test_batched_pairwise_knn2_matches_oracle(orbx, oracle):
+    """orbm_knn2_pairs_device: many independent scans (frame a's rows against frame b's rows, the extractor's [F][cap][32] layout,
+    counts on the device) in one launch pair -- the left -> right matching of a batch of stereo pairs (BASELINE configs[2]).
+    Every pair must equal the oracle's best-2 scan + acceptance (ORBmatcher.cpp:37-67): ragged counts, an empty frame on either
+    side, duplicates (ties -> lowest row), counts at capacity, pairs that reuse frames."""
+    import torch
+    from orbslam_in_practice_b200.synth import synth_descriptor_db, synth_queries
+    dev = torch.device("cuda:0")
+    for cap, counts in ((300, [300, 257, 0, 1, 129, 128]), (2032, [2005, 2032, 1999, 640, 0, 2031]), (1024, [1024, 1, 1023, 5, 77, 900])):
+        F = len(counts)
+        desc = np.zeros((F, cap, 32), np.uint8)
+        base = synth_descriptor_db(cap, seed=cap, dup_frac=0.05)
+        for f, n in enumerate(counts):
+            desc[f, :n] = base[:n] if f % 2 == 0 else synth_queries(base, max(n, 1), seed=100 + f)[:n]
+            desc[f, n:] = 0xEE                                           # rows past the count must never be read as data
+        pa = np.array([0, 1, 2, 3, 1, 4, 5, 0, 3], np.int32); pb = np.array([1, 0, 1, 2, 3, 5, 4, 0, 4], np.int32)
+        P = len(pa)
+        m = orbx.Matcher(cap, cap, 0)
+        t_desc, t_cnt = torch.from_numpy(desc).to(dev), torch.tensor(counts, dtype=torch.int32, device=dev)
+        t_pa, t_pb = torch.from_numpy(pa).to(dev), torch.from_numpy(pb).to(dev)
+        out = torch.full((4, P, cap), -5, dtype=torch.int32, device=dev)
+        wsb = orbx.load().orbm_knn2_pairs_workspace_bytes(cap, P)
+        ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
+        st = torch.cuda.Stream(device=dev); torch.cuda.synchronize()
+        m.knn2_pairs_device(t_desc.data_ptr(), t_cnt.data_ptr(), cap, t_pa.data_ptr(), t_pb.data_ptr(), P, out[0].data_ptr(), out[1].data_ptr(),
+                            out[2].data_ptr(), 50, 0.7, out[3].data_ptr(), ws.data_ptr(), wsb, st.cuda_stream)
+        st.synchronize()
+        got = out.cpu().numpy()
+        for p in range(P):
+            nq, ndb = counts[pa[p]], counts[pb[p]]
+            d1, i1, d2 = oracle.knn2(desc[pa[p], :nq], desc[pb[p], :ndb], 0, 2) if nq else (np.zeros(0, np.int32),) * 3
+            wm = oracle.ratio_select(d1, i1, d2, 50, 0.7) if nq else np.zeros(0, np.int32)
+            assert np.array_equal(got[0, p, :nq], d1) and np.array_equal(got[1, p, :nq], i1) and np.array_equal(got[2, p, :nq], d2), (cap, p)
+            assert np.array_equal(got[3, p, :nq], wm), (cap, p)
+            assert (got[1, p, nq:] == -1).all() and (got[3, p, nq:] == -1).all() and (got[0, p, nq:] == np.iinfo(np.int32).max).all()
