@@ -41,6 +41,7 @@ __device__ __forceinline__ int max3(int a, int b, int c) { return __vimax3_s32(a
 __device__ __forceinline__ uint32_t pack_pm(int e) { return (uint32_t)e * 0xffff0001u + 0x00ff0000u; }
 __device__ __forceinline__ uint32_t min3x2(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u16x2(a, b, c); }
 __device__ __forceinline__ uint32_t max3x2(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_u16x2(a, b, c); }
+__device__ __forceinline__ uint32_t min2x2(uint32_t a, uint32_t b) { uint32_t r; asm("min.u16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 
 // cornerScore<16>'s core for both polarities at once on packed ring values (see pack_pm):
 //   low half:  max over the 16 arcs of 9 contiguous ring values of their minimum           (bright arcs)
@@ -65,16 +66,18 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // TP: tile pitch as a compile-time constant (56 covers every cell up to 56 - 7 - 6 = 43 px wide incl. the alignment
 // slack, i.e. all VGA / KITTI / 4K geometries), 0 = the runtime pitch sm.tp.
-template <int TP>
+// kRange: the launch covers cells [g.fast_cell_lo, g.fast_cell_hi) (one level, low-latency path) instead of all of them.  A template
+// parameter on purpose: with the range test in the one kernel, ptxas allocated 39 registers instead of 48 (8 bytes of spills) and
+// the batch path lost 3.5 % (0.387 -> 0.401 ms per 256 VGA frames); the full-range instantiation is the round-2 kernel unchanged.
+template <int TP, bool kRange>
 __global__ void __launch_bounds__(kFastThreads)
 k_fast_cells(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr,
-             int *__restrict__ cell_count, uint32_t *__restrict__ cell_slots, const int4 *__restrict__ cell_tab, const FastSmem sm,
-             const int cell_lo, const int cell_hi)
+             int *__restrict__ cell_count, uint32_t *__restrict__ cell_slots, const int4 *__restrict__ cell_tab, const FastSmem sm)
 {
     extern __shared__ __align__(16) unsigned char fast_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int cell = cell_lo + blockIdx.x * kFastWarps + warp, f = blockIdx.y + g.frame0;   // [cell_lo, cell_hi): all cells, or one level's
-    if (cell >= cell_hi) return;
+    const int cell = (kRange ? g.fast_cell_lo : 0) + blockIdx.x * kFastWarps + warp, f = blockIdx.y + g.frame0;
+    if (cell >= (kRange ? g.fast_cell_hi : g.total_cells)) return;
     unsigned char *mine = fast_smem + warp * sm.per_warp;
     uint8_t *tile = mine;                                                     // [tile_rows][tp]
     uint8_t *score = mine + sm.off_score;                                     // [tile_rows - 4][sp]
@@ -120,6 +123,7 @@ k_fast_cells(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr,
 #pragma unroll 1
     for (int attempt = 0; attempt < 2 && !found; ++attempt) {
         const int th = attempt == 0 ? iniTh : minTh;
+        const uint32_t tt = (uint32_t)th * 0x10001u;
         {
             // score array and NMS bitmap are adjacent: one 16-byte store loop clears both
             uint4 *z = reinterpret_cast<uint4 *>(score);
@@ -140,16 +144,23 @@ k_fast_cells(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr,
                 const int rows = min(32, ih - yb);
                 const int nr = (rows + 7) & ~7;            // rows walked (the extra ones are masked off below)
                 const uint8_t *p = tile + (yb + 3) * kTP + 3 + xoff + (inx ? x : 0);
-                int c0 = p[-3 * kTP], c1 = p[-2 * kTP], c2 = p[-kTP], c3 = p[0], c4 = p[kTP], c5 = p[2 * kTP];
+                // the window holds the column's last six pixels PACKED as (e, 255 - e) (see pack_pm), so one 16x2 min/max works on both
+                // polarities: with T = pack(v) + (t, t), max(min(max(N,S),max(E,W)), T) = min(max3(N,S,T), max3(E,W,T)) differs from T
+                // iff min(max(N,S),max(E,W)) > v + t (low half, bright) or 255 - max(min(N,S),min(E,W)) > 255 - v + t (high half, dark).
+                // Every half of Y is >= T's, so the 32-bit difference T - Y is negative iff either half differs: its sign is the verdict.
+                // Per pixel: 3 LDS.U8, 3 packs + T + difference on the FMA pipe (IMAD), 2 VIMNMX3 + VIMNMX + SHF on the ALU pipe.  The
+                // scalar form (6 VIMNMX, 2 IADD3, LOP3, SHF = 10 ALU-pipe instructions of 13, two cycles each) was ALU-pipe bound.
+                uint32_t c0 = pack_pm(p[-3 * kTP]), c1 = pack_pm(p[-2 * kTP]), c2 = pack_pm(p[-kTP]), c3 = pack_pm(p[0]), c4 = pack_pm(p[kTP]),
+                         c5 = pack_pm(p[2 * kTP]);
                 uint32_t m = 0;
 #pragma unroll 1
                 for (int y0 = 0; y0 < nr; y0 += 8, p += 8 * kTP) {
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        const int n = p[(k + 3) * kTP], e = p[k * kTP + 3], w = p[k * kTP - 3];
-                        const int hi = min(max(n, c0), max(e, w));
-                        const int lo = max(min(n, c0), min(e, w));
-                        m = __funnelshift_l((uint32_t)((c3 + th - hi) | (lo + th - c3)), m, 1);
+                        const uint32_t n = pack_pm(p[(k + 3) * kTP]), e = pack_pm(p[k * kTP + 3]), w = pack_pm(p[k * kTP - 3]);
+                        const uint32_t T = c3 + tt;
+                        const uint32_t Y = min2x2(max3x2(n, c0, T), max3x2(e, w, T));
+                        m = __funnelshift_l(T - Y, m, 1);
                         c0 = c1; c1 = c2; c2 = c3; c3 = c4; c4 = c5; c5 = n;
                     }
                 }
@@ -268,14 +279,16 @@ void launch_fast(const Geo &g, const DevBuffers &b, int nframes, cudaStream_t s,
     if (sm.per_warp < walk) sm.per_warp = up16(walk);
     const size_t bytes = (size_t)sm.per_warp * kFastWarps;
     dim3 grd((cell_hi - cell_lo + kFastWarps - 1) / kFastWarps, nframes);
+    Geo gl = g;
+    gl.fast_cell_lo = cell_lo; gl.fast_cell_hi = cell_hi;
     // per-device function attribute; a handful of nanoseconds, so no process-wide caching (one handle per device each)
-    if (sm.tp == 56) {
-        if (bytes > 48 * 1024) cudaFuncSetAttribute(k_fast_cells<56>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        k_fast_cells<56><<<grd, kFastThreads, bytes, s>>>(g, b.pyr, b.cell_count, b.cell_slots, b.cell_tab, sm, cell_lo, cell_hi);
-    } else {
-        if (bytes > 48 * 1024) cudaFuncSetAttribute(k_fast_cells<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-        k_fast_cells<0><<<grd, kFastThreads, bytes, s>>>(g, b.pyr, b.cell_count, b.cell_slots, b.cell_tab, sm, cell_lo, cell_hi);
-    }
+    const bool range = cell_lo != 0 || cell_hi != g.total_cells;
+#define FAST_LAUNCH(TPV, RV) do { \
+        if (bytes > 48 * 1024) cudaFuncSetAttribute(k_fast_cells<TPV, RV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); \
+        k_fast_cells<TPV, RV><<<grd, kFastThreads, bytes, s>>>(gl, b.pyr, b.cell_count, b.cell_slots, b.cell_tab, sm); } while (0)
+    if (sm.tp == 56) { if (range) FAST_LAUNCH(56, true); else FAST_LAUNCH(56, false); }
+    else { if (range) FAST_LAUNCH(0, true); else FAST_LAUNCH(0, false); }
+#undef FAST_LAUNCH
 }
 
 } // namespace orbx

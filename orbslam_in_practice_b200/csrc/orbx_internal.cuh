@@ -65,6 +65,7 @@ struct Geo {
     int capacity;             // output keypoint slots per frame
     int kept_total;           // kept slots per frame (= capacity)
     int oct_node_cap_max;     // largest node_cap over the levels (sizes the octree's shared-memory carve-up)
+    int fast_cell_lo, fast_cell_hi;   // cell range of one k_fast_cells launch (set by launch_fast)
     unsigned long long pyr_frame_total, blur_frame_total; // allocation sizes (bytes, all frames) of the pyramid / blur buffers
     unsigned long long slots_per_frame, keys_per_frame;
     LevelGeom lv[ORBX_MAX_LEVELS];
