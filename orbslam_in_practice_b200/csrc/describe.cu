@@ -76,7 +76,8 @@ k_blur(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, uint8_t *
     }
     // two-deep software prefetch of the next source rows (ncu: 53 % of the stall samples sat on this load).
     // Rows up to h+3 are read; the buffer has 19 rows below the level, so the reads stay inside it.
-    uint32_t wn[kBlurPrefetch];
+    uint32_t wn[7];
+    static_assert(kBlurPrefetch <= 7, "the prefetch ring has seven slots");
 #pragma unroll
     for (int i = 0; i < kBlurPrefetch; ++i) { wn[i] = __ldg(reinterpret_cast<const uint32_t *>(rp)); rp += L.pitch; }
     uint8_t *dp = dst + (size_t)y0 * L.blur_pitch;
@@ -88,10 +89,9 @@ k_blur(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, uint8_t *
             // stored, which keeps the shuffles convergent (the compiler bracketed them with WARPSYNC otherwise)
             {
                 // window slot (j + 6) % 7 receives source row y + 3; rows y-3 .. y+3 are slots j .. j+6 (mod 7)
-                const uint32_t w = wn[0];
-#pragma unroll
-                for (int i = 0; i + 1 < kBlurPrefetch; ++i) wn[i] = wn[i + 1];
-                wn[kBlurPrefetch - 1] = __ldg(reinterpret_cast<const uint32_t *>(rp)); rp += L.pitch;
+                // the rows in flight sit in a ring of seven (= the unroll): every index is static, no register moves
+                const uint32_t w = wn[j];
+                wn[(j + kBlurPrefetch) % 7] = __ldg(reinterpret_cast<const uint32_t *>(rp)); rp += L.pitch;
                 lo[(j + 6) % 7] = w & 0x00ff00ffu; hi[(j + 6) % 7] = (w >> 8) & 0x00ff00ffu;
                 // vertical 7-tap, two 16-bit lanes per register: V_lo = (V[4c], V[4c+2]), V_hi = (V[4c+1], V[4c+3])
                 const uint32_t vlo = K0 * (lo[j % 7] + lo[(j + 6) % 7]) + K1 * (lo[(j + 1) % 7] + lo[(j + 5) % 7]) +
@@ -327,7 +327,10 @@ k_describe(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, const
         const uint8_t *src = pyr + L.base + (size_t)f * L.frame_stride + (size_t)(kPadY + y - kHalfPatch + mrow) * pitch
                              + (kPadX + x - kHalfPatch - al_out) + 4 * mword;
 #pragma unroll
-        for (int it = 0; it < kMomentPasses; ++it, src += 3 * pitch) dst[it] = __ldg(reinterpret_cast<const uint32_t *>(src));
+        // only the 31 rows of the window are read (lanes 27..31 and the last pass's rows 31, 32 carry zero weights): every row a
+        // load instruction touches is one more L1 wavefront, and the kernel sits on the L1 wavefront ceiling
+        for (int it = 0; it < kMomentPasses; ++it, src += 3 * pitch)
+            dst[it] = (lane < 27 && 3 * it + mrow < 2 * kHalfPatch + 1) ? __ldg(reinterpret_cast<const uint32_t *>(src)) : 0u;
     };
     load_window(0, px, al, true);
 #pragma unroll 1

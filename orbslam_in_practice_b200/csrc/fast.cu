@@ -31,8 +31,9 @@ namespace orbx {
 
 constexpr int kFastWarps = 4;
 constexpr int kFastThreads = kFastWarps * 32;
+constexpr int kFastLeftover = 4;             // cell columns past a multiple of 32 that run transposed (lane = row) in phase A
 // per-warp shared-memory layout, sized at launch from the largest cell of the geometry
-struct FastSmem { int tp, sp, tile_rows, npix_max, off_score, off_queue, off_bm, per_warp, zero_vecs; };
+struct FastSmem { int tp, sp, tile_rows, npix_max, off_score, off_queue, per_warp, zero_vecs; };
 
 __device__ __forceinline__ int min3(int a, int b, int c) { return __vimin3_s32(a, b, c); }
 __device__ __forceinline__ int max3(int a, int b, int c) { return __vimax3_s32(a, b, c); }
@@ -70,7 +71,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // parameter on purpose: with the range test in the one kernel, ptxas allocated 39 registers instead of 48 (8 bytes of spills) and
 // the batch path lost 3.5 % (0.387 -> 0.401 ms per 256 VGA frames); the full-range instantiation is the round-2 kernel unchanged.
 template <int TP, bool kRange>
-__global__ void __launch_bounds__(kFastThreads)
+__global__ void __launch_bounds__(kFastThreads, 8)
 k_fast_cells(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr,
              int *__restrict__ cell_count, uint32_t *__restrict__ cell_slots, const int4 *__restrict__ cell_tab, const FastSmem sm)
 {
@@ -109,77 +110,120 @@ k_fast_cells(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr,
             for (int r = rr; r < ch; r += rstep, src += sstep, dst += rstep * kTP) cp_async8(dst, src);
         }
     }
-    // NMS bitmap: one 32- or 64-bit row of bits per pixel row (bit = column), so bit order is row-major and the
-    // emission needs no division
-    const int bsh = iw <= 32 ? 5 : 6;
-    const int nbm = ih << (bsh - 5);
     const int minTh = g.min_th, iniTh = g.ini_th;
-    uint32_t *bm = reinterpret_cast<uint32_t *>(mine + sm.off_bm);
+    uint32_t *slots = cell_slots + (size_t)f * g.slots_per_frame + (size_t)(unsigned)ct.w;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    // phase A for 32 columns x0 .. x0+31 and rows yb .. yb+rows-1: compass pre-test, lane = column, walking down the rows with
+    // the column's last six pixels in registers (N of row y is the centre of row y+3 and S of row y+6): three loads per pixel.
+    // The window holds the pixels PACKED as (e, 255 - e) (see pack_pm), so one 16x2 min/max works on both polarities: with
+    // T = pack(v) + (t, t), max(min(max(N,S),max(E,W)), T) = min(max3(N,S,T), max3(E,W,T)) differs from T iff
+    // min(max(N,S),max(E,W)) > v + t (low half, bright) or 255 - max(min(N,S),min(E,W)) > 255 - v + t (high half, dark).
+    // Every half of Y is >= T's, so the 32-bit difference T - Y is negative iff either half differs: its sign is the verdict,
+    // shifted into the lane's mask with one funnel shift.  Per pixel: 3 LDS.U8, 3 packs + T + difference on the FMA pipe (IMAD),
+    // 2 VIMNMX3 + VIMNMX + SHF on the ALU pipe.  The scalar form (6 VIMNMX, 2 IADD3, LOP3, SHF = 10 ALU-pipe instructions of 13,
+    // two cycles each) was ALU-pipe bound.  Returns the block TRANSPOSED: lane = row yb + lane, bit = column x0 + bit.
+    auto column_block = [&](int x0, int yb, int rows, uint32_t tt) -> uint32_t {
+        const int x = x0 + lane;
+        const bool inx = x < iw;
+        const int nr = (rows + 7) & ~7;                    // rows walked (the extra ones are masked off below)
+        const uint8_t *p = tile + (yb + 3) * kTP + 3 + xoff + (inx ? x : 0);
+        uint32_t c0 = pack_pm(p[-3 * kTP]), c1 = pack_pm(p[-2 * kTP]), c2 = pack_pm(p[-kTP]), c3 = pack_pm(p[0]), c4 = pack_pm(p[kTP]),
+                 c5 = pack_pm(p[2 * kTP]);
+        uint32_t m = 0;
+#pragma unroll 1
+        for (int y0 = 0; y0 < nr; y0 += 8, p += 8 * kTP) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t n = pack_pm(p[(k + 3) * kTP]), e = pack_pm(p[k * kTP + 3]), w = pack_pm(p[k * kTP - 3]);
+                const uint32_t T = c3 + tt;
+                const uint32_t Y = min2x2(max3x2(n, c0, T), max3x2(e, w, T));
+                m = __funnelshift_l(T - Y, m, 1);
+                c0 = c1; c1 = c2; c2 = c3; c3 = c4; c4 = c5; c5 = n;
+            }
+        }
+        // row y of the block sits at bit nr-1-y: reverse to bit y, drop the rows past the cell and the columns past it
+        m = __brev(m) >> (32 - nr);
+        m = inx ? m & (0xffffffffu >> (32 - rows)) : 0u;
+        // 32 x 32 bit transpose across the warp (lane c, bit r) -> (lane r, bit c): five butterfly stages, each swapping the
+        // off-diagonal blocks of 2j x 2j tiles; the byte-granular stages are one PRMT, the others a rotate and a bitwise select
+        {
+            const uint32_t y16 = __shfl_xor_sync(0xffffffffu, m, 16);
+            m = __byte_perm(m, y16, (lane & 16) ? 0x3276u : 0x5410u);
+            const uint32_t y8 = __shfl_xor_sync(0xffffffffu, m, 8);
+            m = __byte_perm(m, y8, (lane & 8) ? 0x3715u : 0x6240u);
+#pragma unroll
+            for (int j = 4; j >= 1; j >>= 1) {
+                const uint32_t km = j == 4 ? 0x0f0f0f0fu : j == 2 ? 0x33333333u : 0x55555555u;
+                const bool up = (lane & j) != 0;
+                const uint32_t y = __shfl_xor_sync(0xffffffffu, m, j);
+                const uint32_t ry = __funnelshift_l(y, y, up ? 32 - j : j);     // partner's block moved onto the positions this lane takes over
+                const uint32_t keep = up ? ~km : km;
+                m = (m & keep) | (ry & ~keep);
+            }
+        }
+        return m;
+    };
 
     // The reference calls cv::FAST(cell, iniThFAST) and, only if that returns nothing, cv::FAST(cell, minThFAST)
     // (:766-773).  Same here: the whole detect-score-NMS pipeline runs at iniThFAST first (fewer compass
     // survivors and corners than at minThFAST) and is repeated at minThFAST only for cells left empty.
-    bool found = false;
+    int base = 0;                                          // keypoints emitted
 #pragma unroll 1
-    for (int attempt = 0; attempt < 2 && !found; ++attempt) {
+    for (int attempt = 0; attempt < 2 && base == 0; ++attempt) {
         const int th = attempt == 0 ? iniTh : minTh;
         const uint32_t tt = (uint32_t)th * 0x10001u;
         {
-            // score array and NMS bitmap are adjacent: one 16-byte store loop clears both
             uint4 *z = reinterpret_cast<uint4 *>(score);
+#pragma unroll 1                                           // three trips; unrolled by eight with a remainder ladder it was 65 instructions
             for (int i = lane; i < sm.zero_vecs; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
         }
         cp_async_wait_all();                               // the tile (first attempt; nothing pending on the second)
         __syncwarp();
 
-        // ---- phase A: compass pre-test, lane = column, walking down the rows with the column's last six pixels in
-        //      registers (N of row y is the centre of row y+3 and S of row y+6): three loads per pixel.  The two
-        //      verdicts are sign bits, (v + t) - min(max(N,S),max(E,W)) < 0 and max(min(N,S),min(E,W)) + t - v < 0;
-        //      their OR is shifted into a per-lane mask with one funnel shift (row y ends up at bit nr-1-y). ----
+        // ---- phase A: compass pre-test; the survivors of 32 rows go into the queue in ROW-MAJOR order (lane = row after the
+        //      transpose, ascending columns inside a row), so the queue order is the order of the output ----
         int nq = 0;                                        // queue fill
-        for (int x0 = 0; x0 < iw; x0 += 32) {
-            const int x = x0 + lane;
-            const bool inx = x < iw;
-            for (int yb = 0; yb < ih; yb += 32) {
-                const int rows = min(32, ih - yb);
-                const int nr = (rows + 7) & ~7;            // rows walked (the extra ones are masked off below)
-                const uint8_t *p = tile + (yb + 3) * kTP + 3 + xoff + (inx ? x : 0);
-                // the window holds the column's last six pixels PACKED as (e, 255 - e) (see pack_pm), so one 16x2 min/max works on both
-                // polarities: with T = pack(v) + (t, t), max(min(max(N,S),max(E,W)), T) = min(max3(N,S,T), max3(E,W,T)) differs from T
-                // iff min(max(N,S),max(E,W)) > v + t (low half, bright) or 255 - max(min(N,S),min(E,W)) > 255 - v + t (high half, dark).
-                // Every half of Y is >= T's, so the 32-bit difference T - Y is negative iff either half differs: its sign is the verdict.
-                // Per pixel: 3 LDS.U8, 3 packs + T + difference on the FMA pipe (IMAD), 2 VIMNMX3 + VIMNMX + SHF on the ALU pipe.  The
-                // scalar form (6 VIMNMX, 2 IADD3, LOP3, SHF = 10 ALU-pipe instructions of 13, two cycles each) was ALU-pipe bound.
-                uint32_t c0 = pack_pm(p[-3 * kTP]), c1 = pack_pm(p[-2 * kTP]), c2 = pack_pm(p[-kTP]), c3 = pack_pm(p[0]), c4 = pack_pm(p[kTP]),
-                         c5 = pack_pm(p[2 * kTP]);
-                uint32_t m = 0;
+        for (int yb = 0; yb < ih; yb += 32) {
+            const int rows = min(32, ih - yb);
+            uint32_t rlo = 0u, rhi = 0u;
+            const bool leftover = iw > 32 && iw - 32 <= kFastLeftover;
+            const int xfull = leftover ? 32 : iw;          // columns that run as lane-per-column blocks
 #pragma unroll 1
-                for (int y0 = 0; y0 < nr; y0 += 8, p += 8 * kTP) {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const uint32_t n = pack_pm(p[(k + 3) * kTP]), e = pack_pm(p[k * kTP + 3]), w = pack_pm(p[k * kTP - 3]);
-                        const uint32_t T = c3 + tt;
-                        const uint32_t Y = min2x2(max3x2(n, c0, T), max3x2(e, w, T));
-                        m = __funnelshift_l(T - Y, m, 1);
-                        c0 = c1; c1 = c2; c2 = c3; c3 = c4; c4 = c5; c5 = n;
-                    }
-                }
-                const uint32_t valid = inx ? (0xffffffffu >> (32 - nr)) & (0xffffffffu << (nr - rows)) : 0u;
-                m &= valid;
-                const int cnt = __popc(m);
-                int inc = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-                // queue entry: x | y << 6   (x, y < 64); bit b of the mask is row yb + nr - 1 - b
-                const int ebase = x | ((yb + nr - 1) << 6);
-                uint16_t *q = queue + nq + (inc - cnt);
-                while (m) {
-                    const int b = 31 - __clz(m);
-                    m ^= 1u << b;
-                    *q++ = (uint16_t)(ebase - (b << 6));
-                }
-                nq += __shfl_sync(0xffffffffu, inc, 31);
+            for (int x0 = 0; x0 < xfull; x0 += 32) {       // one body for both blocks (inlined twice it cost 16 registers)
+                const uint32_t m = column_block(x0, yb, rows, tt);
+                if (x0 == 0) rlo = m; else rhi = m;
             }
+            if (leftover) {
+                // a few columns past a multiple of 32 (VGA levels 2 and 5 have 33-px cells): a lane-per-column pass would walk
+                // every row for one or two active lanes, so these columns run lane = row, five loads per pixel
+                const int y = yb + lane;
+                const bool iny = lane < rows;
+                const uint8_t *p = tile + ((iny ? y : 0) + 3) * kTP + 3 + xoff + 32;
+                for (int x = 32; x < iw; ++x, ++p) {
+                    const int v = p[0], n = p[-3 * kTP], s2 = p[3 * kTP], e = p[3], w = p[-3];
+                    const int hi = min(max(n, s2), max(e, w)), lo = max(min(n, s2), min(e, w));
+                    if (iny && (hi > v + th || lo < v - th)) rhi |= 1u << (x - 32);
+                }
+            }
+            const int cnt = __popc(rlo) + __popc(rhi);
+            int inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            // queue entry: x | y << 6   (x, y < 64)
+            const int ebase = (yb + lane) << 6;
+            uint16_t *q = queue + nq + (inc - cnt);
+            while (rlo) {
+                const int b = __ffs(rlo) - 1;
+                rlo &= rlo - 1;
+                *q++ = (uint16_t)(ebase + b);
+            }
+            while (rhi) {
+                const int b = __ffs(rhi) - 1;
+                rhi &= rhi - 1;
+                *q++ = (uint16_t)(ebase + 32 + b);
+            }
+            nq += __shfl_sync(0xffffffffu, inc, 31);
         }
         __syncwarp();
 
@@ -206,47 +250,28 @@ k_fast_cells(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr,
         }
         __syncwarp();
 
-        // ---- phase C: strict 3x3 NMS inside the cell; walks the same queue (non-corners have score 0) ----
-        bool mine_any = false;
-        for (int i = lane; i < nq; i += 32) {
-            const uint32_t ent = queue[i];
-            const int x = ent & 63, y = ent >> 6;
-            const uint8_t *q = score + (y + 1) * kSP + (x + 1);
-            const int s = q[0];
-            if (s == 0) continue;                         // every stored score is >= th >= 1
-            const int nmax = max3(max3((int)q[-kSP - 1], (int)q[-kSP], (int)q[-kSP + 1]), max3((int)q[-1], (int)q[1], (int)q[kSP - 1]),
-                                  max((int)q[kSP], (int)q[kSP + 1]));
-            if (s > nmax) {
-                const int idx = (y << bsh) + x;
-                atomicOr(&bm[idx >> 5], 1u << (idx & 31));
-                mine_any = true;
+        // ---- phase C: strict 3x3 NMS inside the cell (non-corners and pixels outside the cell read 0) over the same queue, and the
+        //      emission in one: the queue is row-major, so a ballot-ranked store writes the survivors in output order ----
+        for (int i0 = 0; i0 < nq; i0 += 32) {
+            const int i = i0 + lane;
+            bool keep = false;
+            uint32_t cand = 0;
+            if (i < nq) {
+                const uint32_t ent = queue[i];
+                const int x = ent & 63, y = ent >> 6;
+                const uint8_t *q = score + (y + 1) * kSP + (x + 1);
+                const int s = q[0];
+                if (s != 0) {                             // every stored score is >= th >= 1
+                    const int nmax = max3(max3((int)q[-kSP - 1], (int)q[-kSP], (int)q[-kSP + 1]), max3((int)q[-1], (int)q[1], (int)q[kSP - 1]),
+                                          max((int)q[kSP], (int)q[kSP + 1]));
+                    keep = s > nmax;
+                    // keypoint in level coordinates relative to (16,16): cell pixel (x+3, y+3) + (j*wCell, i*hCell)
+                    cand = pack_cand(x + 3 + iniX - kMinBorder, y + 3 + iniY - kMinBorder, s);
+                }
             }
-        }
-        found = __any_sync(0xffffffffu, mine_any);
-        __syncwarp();
-    }
-
-    // ---- phase D: ordered emission (row-major = ascending bit index) ----
-    uint32_t *slots = cell_slots + (size_t)f * g.slots_per_frame + (size_t)(unsigned)ct.w;
-    int base = 0;
-    if (found) {
-        for (int w0 = 0; w0 < nbm; w0 += 32) {
-            const int wi = w0 + lane;
-            uint32_t bits = wi < nbm ? bm[wi] : 0u;
-            const int cnt = __popc(bits);
-            int inc = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-            int pos = base + inc - cnt;
-            while (bits) {
-                const int b = __ffs(bits) - 1;
-                bits &= bits - 1;
-                const int idx = wi * 32 + b;
-                const int y = idx >> bsh, x = idx & ((1 << bsh) - 1);
-                // keypoint in level coordinates relative to (16,16): cell pixel (x+3, y+3) + (j*wCell, i*hCell)
-                slots[pos++] = pack_cand(x + 3 + iniX - kMinBorder, y + 3 + iniY - kMinBorder, score[(y + 1) * kSP + (x + 1)]);
-            }
-            base += __shfl_sync(0xffffffffu, inc, 31);
+            const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+            if (keep) slots[base + __popc(bal & lt_mask)] = cand;
+            base += __popc(bal);
         }
     }
     if (lane == 0) *count_out = base;
@@ -269,8 +294,7 @@ void launch_fast(const Geo &g, const DevBuffers &b, int nframes, cudaStream_t s,
     sm.sp = (mw + 2 + 3) / 4 * 4; sm.tile_rows = mh + 6;
     sm.npix_max = (mw * mh + 1) / 2 * 2;
     sm.off_score = up16(sm.tile_rows * sm.tp);
-    sm.off_bm = sm.off_score + up16((mh + 2) * sm.sp);
-    sm.off_queue = sm.off_bm + up16(mh * 2 * 4);
+    sm.off_queue = sm.off_score + up16((mh + 2) * sm.sp);
     sm.per_warp = sm.off_queue + up16(sm.npix_max * 2);
     sm.zero_vecs = (sm.off_queue - sm.off_score) / 16;
     // phase A walks its rows in groups of eight: the rows past the cell are masked off, but they are read, so the

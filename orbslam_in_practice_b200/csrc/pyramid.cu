@@ -278,11 +278,15 @@ k_resize(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr_src, uin
     const int nrows = min(kResizeRows, D.h + B - Ybase);
     int prev_off1 = -1;
     int hp[4] = { 0, 0, 0, 0 };                           // horizontally interpolated lower source row, already >> 4
+    // shared-window addresses of the two 8-byte windows, formed once: through the generic pointer the compiler rebuilt the window
+    // base (S2UR + UMOV + UIADD3 + ULEA) in front of every interpolated row
+    const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(rs_tile);
+    const uint32_t tb[2] = { tile_s + (uint32_t)pbase[0], tile_s + (uint32_t)pbase[1] };
     auto hrow = [&](int off, int (&h)[4]) {
-        const unsigned char *t = rs_tile + off;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-            const uint32_t w0 = *reinterpret_cast<const uint32_t *>(t + pbase[j]), w1 = *reinterpret_cast<const uint32_t *>(t + pbase[j] + 4);
+            uint32_t w0, w1;
+            asm volatile("ld.shared.u32 %0, [%2];\n\tld.shared.u32 %1, [%2+4];" : "=r"(w0), "=r"(w1) : "r"(tb[j] + (uint32_t)off));
             const uint32_t P = __byte_perm(w0, w1, psel[j]);
             h[2 * j] = (int)(__dp2a_lo(cf[2 * j], P, 0u) >> 4);
             h[2 * j + 1] = (int)(__dp2a_hi(cf[2 * j + 1], P, 0u) >> 4);
@@ -304,16 +308,21 @@ k_resize(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr_src, uin
         } else {
             hrow(ty.y, h1);
         }
-        // ((b0 * (H0 >> 4)) >> 16) + ((b1 * (H1 >> 4)) >> 16) + 2) >> 2 never leaves [0, 255] (see k_resize_gather)
-        uint32_t out = 0;
+        // ((b0 * (H0 >> 4)) >> 16) + ((b1 * (H1 >> 4)) >> 16) + 2) >> 2 never leaves [0, 255] (see k_resize_gather).  Two pixels per
+        // register from here on: one PRMT takes the upper halves of two products (the two >> 16), the sums stay below 1024 per
+        // 16-bit half, (sum + 2) << 6 puts (sum + 2) >> 2 into the second byte of each half, and a last PRMT collects the four bytes:
+        // 8 IMAD + 5 PRMT + 2 IADD + 2 IMAD per four pixels instead of 27 scalar instructions (ncu: 26 % of the kernel).
+        uint32_t s2[2];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const uint32_t v = (uint32_t)(((ty.z * h0[k]) >> 16) + ((ty.w * h1[k]) >> 16) + 2) >> 2;
-            out |= v << (8 * k);
-            hp[k] = h1[k];
+        for (int j = 0; j < 2; ++j) {
+            const uint32_t a = __byte_perm((uint32_t)(ty.z * h0[2 * j]), (uint32_t)(ty.z * h0[2 * j + 1]), 0x7632u);
+            const uint32_t b = __byte_perm((uint32_t)(ty.w * h1[2 * j]), (uint32_t)(ty.w * h1[2 * j + 1]), 0x7632u);
+            s2[j] = (a + b) * 64u + 0x00800080u;
         }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) hp[k] = h1[k];
         prev_off1 = ty.y;
-        *reinterpret_cast<uint32_t *>(drow) = out;
+        *reinterpret_cast<uint32_t *>(drow) = __byte_perm(s2[0], s2[1], 0x7531u);
     }
 }
 
