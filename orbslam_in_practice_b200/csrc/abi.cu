@@ -23,6 +23,7 @@ struct NvtxRange {
 namespace orbx {
 // knn.cu
 int knn_segments(int nq, int ndb, int sm_count, int *seg_rows_out);
+int octree_closed_depth(const Geo &g, int level);
 size_t knn_partial_elems(int max_q, int max_db, int sm_count);
 void launch_knn2_empty(int nq, int *d1, int *idx1, int *d2, cudaStream_t s);
 void launch_knn2(const uint8_t *d_query, int nq, const uint8_t *d_db, int ndb, int index_base, int nseg, int seg_rows,
@@ -332,6 +333,7 @@ static int build_geometry(const orbx_extractor *ex, int w, int h, Geo &g, std::v
     g.total_cells = cell_off;
     g.oct_node_cap_max = 0;
     for (int l = 0; l < g.nlevels; ++l) g.oct_node_cap_max = std::max(g.oct_node_cap_max, g.lv[l].node_cap);
+    for (int l = 0; l < g.nlevels; ++l) g.lv[l].oct_B = octree_closed_depth(g, l);
     g.capacity = kept_off; g.kept_total = kept_off;
     g.slots_per_frame = slot_off; g.keys_per_frame = key_off;
     g.pyr_frame_total = pyr_off; g.blur_frame_total = blur_off;

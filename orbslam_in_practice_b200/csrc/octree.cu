@@ -39,6 +39,7 @@ struct OctShared {
     int warp_i[kOctMaxWarps + 1];
     uint4 warp_v[kOctMaxWarps + 1];
     int n, nsplit, C, U, nToExpand, J, pending;
+    int psize[8], pmulti[8];                              // closed-form phase 1: nodes / nodes with more than one key per depth
 };
 
 __device__ __forceinline__ int warp_incl_scan(int v)
@@ -169,7 +170,146 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
     const int seg = (((n + kOctWarps - 1) / kOctWarps) + 31) & ~31;
     const int s0 = min(n, warp * seg), s1 = min(n, s0 + seg);
     int cur_size = 0;                                      // nodes in the list (lNodes.size()), kept in a register by every thread
-    {
+    // ---- phase 1 (:545-625) in closed form.  A DivideNode split depends on the node's bounds only, never on its keys, so the path
+    //      of every key (root, then one quadrant digit per depth) is known up front, a node of depth k is the set of keys sharing a
+    //      k-digit prefix, and lNodes.size() after the pass that creates depth d is the number of distinct d-prefixes.  Counting the
+    //      keys per depth-B prefix (bins) gives the sizes of every depth <= B, hence the depth e at which phase 1 ends (:621-626).  The
+    //      list at that point is [depth-e nodes] ++ [single-key nodes that stopped at depth e-1] ++ ... ++ [single-key roots], and
+    //      because children are pushed to the FRONT in quadrant order while the parents are walked front to back, the order inside
+    //      the depth-k group is lexicographic in (root, q1 .. qk) with directions that alternate from the last digit backwards
+    //      (descending, ascending, ...; the root follows q1): an XOR mask on the prefix.  So one flag scan over the concatenated
+    //      prefix spaces yields every node's list index, and one counting scatter by depth-e prefix replaces the root partition and
+    //      e partition passes.  tools/proto/octree_closed_form.py checks this restatement against the oracle.  When phase 1 does not
+    //      end within depth B (few, clustered candidates) the sequential form below runs instead.
+    int closed = 0;                                        // 0: sequential phase 1; 1: closed form, the run is finished; 2: closed form, phase 2 follows
+    if (!kGlobalTables && L.oct_B > 0) {
+        const int B = L.oct_B;
+        const float hX = L.hX;
+        const int MB = nIni * (((1 << (2 * B + 2)) - 1) / 3);         // prefixes of all depths 0..B; depth k starts at nIni * (4^k - 1) / 3
+        uint32_t *cnt = reinterpret_cast<uint32_t *>(childCnt);       // [MB] keys per prefix (scratch: the pass tables are not live yet)
+        uint32_t *start = cnt + MB;                                   // [nIni * 4^B] first key slot of a depth-e prefix
+        uint16_t *listpos = reinterpret_cast<uint16_t *>(start + (nIni << (2 * B)));   // [MB] list index of the node of a prefix
+        auto lvoff = [&](int k) { return nIni * (((1 << (2 * k)) - 1) / 3); };
+        for (int i = tid; i < MB; i += kOctThreads) cnt[i] = 0u;
+        if (tid < 8) { S.psize[tid] = 0; S.pmulti[tid] = 0; }
+        __syncthreads();
+        {
+            uint32_t *cB = cnt + lvoff(B);
+            for (int p = tid; p < n; p += kOctThreads) {
+                const uint32_t key = kB[p];
+                const int x = cand_x(key), y = cand_y(key);
+                const int r = min((int)((float)x / hX), nIni - 1);                                       // :519
+                int x0 = (int)(hX * (float)r), x1 = (int)(hX * (float)(r + 1)), y0 = 0, y1 = L.regionH;   // :505-506
+                int code = r;
+                for (int d = 0; d < B; ++d) {                                                            // DivideNode :433-434, :462-476
+                    const int sx = x0 + ((x1 - x0 + 1) >> 1), sy = y0 + ((y1 - y0 + 1) >> 1);
+                    const bool left = x < sx, up = y < sy;
+                    code = (code << 2) | (left ? (up ? 0 : 2) : (up ? 1 : 3));
+                    x0 = left ? x0 : sx; x1 = left ? sx : x1; y0 = up ? y0 : sy; y1 = up ? sy : y1;
+                }
+                nB[p] = (uint16_t)code;
+                atomicAdd(cB + code, 1u);
+            }
+        }
+        __syncthreads();
+        // keys per prefix of every depth, and per depth the number of prefixes with keys / with more than one key
+        for (int k = B; k >= 0; --k) {
+            const int G = nIni << (2 * k);
+            uint32_t *ck = cnt + lvoff(k);
+            for (int j0 = warp * 32; j0 < G; j0 += kOctThreads) {
+                const int j = j0 + lane;
+                uint32_t c = 0;
+                if (j < G) {
+                    if (k == B) c = ck[j];
+                    else { const uint32_t *cc = cnt + lvoff(k + 1) + 4 * j; c = cc[0] + cc[1] + cc[2] + cc[3]; ck[j] = c; }
+                }
+                const uint32_t bz = __ballot_sync(0xffffffffu, c > 0), bm = __ballot_sync(0xffffffffu, c > 1);
+                if (lane == 0) { if (bz) atomicAdd(&S.psize[k], __popc(bz)); if (bm) atomicAdd(&S.pmulti[k], __popc(bm)); }
+            }
+            __syncthreads();
+        }
+        // the pass loop of phase 1 on the sizes alone (:545-626); every thread runs it on the same numbers
+        int e = 0;
+        for (int d = 0; d < B; ++d) {
+            const int sz = S.psize[d + 1];
+            if (sz >= N || sz == S.psize[d]) { e = d + 1; closed = 1; break; }                            // :621
+            if (sz + 3 * S.pmulti[d + 1] > N) { e = d + 1; closed = 2; break; }                           // :626
+        }
+        if (closed) {
+            // first key slot of every depth-e prefix (exclusive scan in natural order)
+            const int Ge = nIni << (2 * e);
+            uint32_t *ce = cnt + lvoff(e);
+            {
+                int carry = 0;
+                for (int base = 0; base < Ge; base += kOctThreads) {
+                    const int j = base + tid;
+                    const int v = j < Ge ? (int)ce[j] : 0;
+                    int tot;
+                    const int ex = block_excl_scan<kOctWarps>(v, S, tot);
+                    if (j < Ge) start[j] = (uint32_t)(carry + ex);
+                    carry += tot;
+                }
+            }
+            __syncthreads();
+            // the list: depth e first, then the single-key nodes of depth e-1, ..., 0; inside a depth the order is the XOR-masked prefix
+            {
+                const int Me = nIni * (((1 << (2 * e + 2)) - 1) / 3);
+                int carry = 0;
+                for (int base = 0; base < Me; base += kOctThreads) {
+                    const int t = base + tid;
+                    int k = e, j = 0, flag = 0;
+                    uint32_t c = 0;
+                    if (t < Me) {
+                        int rem = t;
+                        while (rem >= (nIni << (2 * k))) { rem -= nIni << (2 * k); --k; }            // segment k holds nIni * 4^k prefixes
+                        int r = rem >> (2 * k);
+                        const int path = (rem & ((1 << (2 * k)) - 1)) ^ (0x33333333 & ((1 << (2 * k)) - 1));
+                        if (k & 1) r = nIni - 1 - r;
+                        j = (r << (2 * k)) | path;
+                        c = cnt[lvoff(k) + j];
+                        const bool parent_multi = k == 0 || cnt[lvoff(k - 1) + (j >> 2)] > 1u;
+                        flag = parent_multi && (k == e ? c > 0u : c == 1u);
+                    }
+                    int tot;
+                    const int pos = carry + block_excl_scan<kOctWarps>(flag, S, tot);
+                    carry += tot;
+                    if (flag) {
+                        listpos[lvoff(k) + j] = (uint16_t)pos;
+                        const int r = j >> (2 * k);
+                        int x0 = (int)(hX * (float)r), x1 = (int)(hX * (float)(r + 1)), y0 = 0, y1 = L.regionH;
+                        for (int d = 1; d <= k; ++d) {
+                            const int q = (j >> (2 * (k - d))) & 3;
+                            const int sx = x0 + ((x1 - x0 + 1) >> 1), sy = y0 + ((y1 - y0 + 1) >> 1);
+                            if (q & 1) x0 = sx; else x1 = sx;
+                            if (q & 2) y0 = sy; else y1 = sy;
+                        }
+                        Node nd;
+                        nd.x0 = (short)x0; nd.x1 = (short)x1; nd.y0 = (short)y0; nd.y1 = (short)y1;
+                        nd.begin = (int)start[j << (2 * (e - k))]; nd.count = (int)c;
+                        nodes[pos] = nd;
+                    }
+                }
+            }
+            __syncthreads();
+            // keys to their nodes' ranges (any order inside a range: the final choice breaks score ties by candidate order explicitly)
+            for (int p = tid; p < n; p += kOctThreads) {
+                const uint32_t key = kB[p];
+                const int code = nB[p];
+                const int ge = code >> (2 * (B - e));
+                int node = -1;
+                for (int k = 0; k < e; ++k) {
+                    const int gk = code >> (2 * (B - k));
+                    if (cnt[lvoff(k) + gk] == 1u) { node = listpos[lvoff(k) + gk]; break; }
+                }
+                if (node < 0) node = listpos[lvoff(e) + ge];
+                const int dst = (int)start[ge] + (int)atomicSub(ce + ge, 1u) - 1;
+                kA[dst] = key; nA[dst] = (uint16_t)node;
+            }
+            cur_size = S.psize[e];
+            __syncthreads();
+        }
+    }
+    if (!closed) {
         const float hX = L.hX;
         int placed = 0, nroots = 0;
         for (int r0 = 0; r0 < nIni; r0 += 4) {                            // four roots per sweep
@@ -219,9 +359,9 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
         cur_size = nroots;                                 // block-uniform: every thread derived it from the same totals
     }
 
-    bool phase2 = false;
+    bool phase2 = closed == 2;
 #pragma unroll 1
-    for (;;) {
+    for (; closed != 1;) {
         const int size = cur_size;
         const int prevSize = size;
 
@@ -444,14 +584,41 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
     uint32_t *kept = kept_out + (size_t)f * g.kept_total + L.kept_base;
     for (int gi = tid; gi < size && gi < L.kept_cap; gi += kOctThreads) {
         const Node nd = nodes[gi];
+        // the first maximum in CANDIDATE order wins (:700-712).  The keys of a node are not kept in that order (closed-form phase 1), so
+        // ties are broken explicitly: candidates come cell by cell (row-major cells, ORBextractor.cpp:745-786), row-major inside a cell
         uint32_t best = kA[nd.begin];
         for (int k = 1; k < nd.count; ++k) {
             const uint32_t key = kA[nd.begin + k];
             if (cand_score(key) > cand_score(best)) best = key;
+            else if (cand_score(key) == cand_score(best)) {
+                const int ya = cand_y(key), yb = cand_y(best), xa = cand_x(key), xb = cand_x(best);
+                const int ia = (ya - 3) / L.hCell, ib = (yb - 3) / L.hCell, ja = (xa - 3) / L.wCell, jb = (xb - 3) / L.wCell;
+                const bool before = ia != ib ? ia < ib : ja != jb ? ja < jb : ya != yb ? ya < yb : xa < xb;
+                if (before) best = key;
+            }
         }
         kept[gi] = best;
     }
     if (tid == 0) nkept_out[f * g.nlevels + level] = min(size, L.kept_cap);
+}
+
+// Depth B of the closed-form phase 1 for one level: the smallest depth whose prefix space holds twice the quota (a well
+// spread level reaches its quota one or two depths earlier), shrunk until the scratch -- counts of all depths, start slots
+// and list indices, laid over the pass tables behind the two node tables -- fits.  0 switches the closed form off.
+int octree_closed_depth(const Geo &g, int level)
+{
+    static int enabled = -1;
+    if (enabled < 0) { const char *e = std::getenv("ORBX_OCT_CLOSED"); enabled = e ? std::atoi(e) : 1; }
+    const LevelGeom &L = g.lv[level];
+    if (!enabled || L.nIni < 1 || L.nIni > 16 || L.N < 1 || L.max_cand > 65535) return 0;
+    const long avail = (long)g.oct_node_cap_max * (2 * (long)sizeof(Node) + 4 * 4 * 2 + 16 + 3 * 4 + 2) - (long)L.node_cap * 2 * (long)sizeof(Node) - 64;
+    int B = 1;
+    while (B < 6 && ((long)L.nIni << (2 * B)) < 2L * L.N) ++B;
+    for (; B >= 1; --B) {
+        const long G = (long)L.nIni << (2 * B), M = (long)L.nIni * (((1L << (2 * B + 2)) - 1) / 3);
+        if (G <= 65536 && 4 * M + 4 * G + 2 * M <= avail) break;
+    }
+    return B < 2 ? 0 : B;
 }
 
 // bytes of one problem's node tables (no key arrays): the slice size of the global-memory fallback
