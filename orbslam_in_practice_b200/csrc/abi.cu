@@ -333,7 +333,11 @@ static int build_geometry(const orbx_extractor *ex, int w, int h, Geo &g, std::v
     g.total_cells = cell_off;
     g.oct_node_cap_max = 0;
     for (int l = 0; l < g.nlevels; ++l) g.oct_node_cap_max = std::max(g.oct_node_cap_max, g.lv[l].node_cap);
-    for (int l = 0; l < g.nlevels; ++l) g.lv[l].oct_B = octree_closed_depth(g, l);
+    for (int l = 0; l < g.nlevels; ++l) {
+        LevelGeom &L = g.lv[l];
+        L.oct_B = octree_closed_depth(g, l);
+        L.inv_wCell = ((1 << 18) + L.wCell - 1) / L.wCell; L.inv_hCell = ((1 << 18) + L.hCell - 1) / L.hCell;
+    }
     g.capacity = kept_off; g.kept_total = kept_off;
     g.slots_per_frame = slot_off; g.keys_per_frame = key_off;
     g.pyr_frame_total = pyr_off; g.blur_frame_total = blur_off;

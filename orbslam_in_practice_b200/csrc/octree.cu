@@ -182,6 +182,13 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
     //      e partition passes.  tools/proto/octree_closed_form.py checks this restatement against the oracle.  When phase 1 does not
     //      end within depth B (few, clustered candidates) the sequential form below runs instead.
     int closed = 0;                                        // 0: sequential phase 1; 1: closed form, the run is finished; 2: closed form, phase 2 follows
+    // The first pass of phase 2 runs from the bins as well when the prefixes one depth below e were counted (e + 1 <= B): the child
+    // sizes come from the counts instead of two sweeps over the keys, and ONE scatter by depth-(e+1) prefix places every key in its
+    // final node.  The tables that pass needs (child counts = fill cursors, start slots, list indices) are copied into the per-key
+    // rank array of the sequential passes, which is dead until one of them runs.
+    bool bins_pass = false;
+    uint32_t *cfill = nullptr; uint16_t *cstart = nullptr, *clist = nullptr;
+    int bins_e = 0;
     if (!kGlobalTables && L.oct_B > 0) {
         const int B = L.oct_B;
         const float hX = L.hX;
@@ -235,7 +242,83 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
             if (sz >= N || sz == S.psize[d]) { e = d + 1; closed = 1; break; }                            // :621
             if (sz + 3 * S.pmulti[d + 1] > N) { e = d + 1; closed = 2; break; }                           // :626
         }
-        if (closed) {
+        if (closed == 2 && e + 1 <= B) {
+            const int G1 = nIni << (2 * e + 2), Me = nIni * (((1 << (2 * e + 2)) - 1) / 3);
+            const long cap_bytes = 4L * (n <= smem_keys ? smem_keys : L.max_cand);
+            bins_pass = n <= 65535 && 6L * G1 + 2L * Me + 8 <= cap_bytes;      // 16-bit start slots
+        }
+        if (bins_pass) {
+            const int e1 = e + 1, G1 = nIni << (2 * e1), Me = nIni * (((1 << (2 * e + 2)) - 1) / 3);
+            bins_e = e;
+            cfill = E32; cstart = reinterpret_cast<uint16_t *>(cfill + G1); clist = cstart + G1;
+            const uint32_t *c1 = cnt + lvoff(e1);
+            {
+                int carry = 0;
+                for (int base = 0; base < G1; base += kOctThreads) {
+                    const int j = base + tid;
+                    const int v = j < G1 ? (int)c1[j] : 0;
+                    int tot;
+                    const int ex = block_excl_scan<kOctWarps>(v, S, tot);
+                    if (j < G1) { cfill[j] = (uint32_t)v; cstart[j] = (uint16_t)(carry + ex); }
+                    carry += tot;
+                }
+            }
+            __syncthreads();
+            {
+                int carry = 0;
+                for (int base = 0; base < Me; base += kOctThreads) {
+                    const int t = base + tid;
+                    int k = e, j = 0, flag = 0;
+                    uint32_t c = 0;
+                    if (t < Me) {
+                        int rem = t;
+                        while (rem >= (nIni << (2 * k))) { rem -= nIni << (2 * k); --k; }
+                        int r = rem >> (2 * k);
+                        const int path = (rem & ((1 << (2 * k)) - 1)) ^ (0x33333333 & ((1 << (2 * k)) - 1));
+                        if (k & 1) r = nIni - 1 - r;
+                        j = (r << (2 * k)) | path;
+                        c = cnt[lvoff(k) + j];
+                        const bool parent_multi = k == 0 || cnt[lvoff(k - 1) + (j >> 2)] > 1u;
+                        flag = parent_multi && (k == e ? c > 0u : c == 1u);
+                    }
+                    int tot;
+                    const int pos = carry + block_excl_scan<kOctWarps>(flag, S, tot);
+                    carry += tot;
+                    if (t < Me) clist[lvoff(k) + j] = flag ? (uint16_t)pos : (uint16_t)0xffffu;
+                    if (flag) {
+                        const int r = j >> (2 * k);
+                        int x0 = (int)(hX * (float)r), x1 = (int)(hX * (float)(r + 1)), y0 = 0, y1 = L.regionH;
+                        for (int d = 1; d <= k; ++d) {
+                            const int q = (j >> (2 * (k - d))) & 3;
+                            const int sx = x0 + ((x1 - x0 + 1) >> 1), sy = y0 + ((y1 - y0 + 1) >> 1);
+                            if (q & 1) x0 = sx; else x1 = sx;
+                            if (q & 2) y0 = sy; else y1 = sy;
+                        }
+                        const int pfx = j << (2 * (e1 - k));                 // first depth-(e+1) prefix below this node
+                        Node nd;
+                        nd.x0 = (short)x0; nd.x1 = (short)x1; nd.y0 = (short)y0; nd.y1 = (short)y1;
+                        nd.begin = (int)cstart[pfx]; nd.count = (int)c;
+                        nodes[pos] = nd;
+                        nodesN[pos].begin = pfx;                             // parked until the child sizes are read (next step)
+                    }
+                }
+            }
+            cur_size = S.psize[e];
+            if (tid == 0) { S.J = 0x7fffffff; S.pending = 0; S.nToExpand = 0; }
+            __syncthreads();
+            // child sizes of the nodes (step B of a pass) from the counts; the scratch of the analysis is dead from here on
+            for (int gi = tid; gi < cur_size; gi += kOctThreads) {
+                int ne = 0;
+                if (nodes[gi].count > 1) {
+                    const int pfx = nodesN[gi].begin;
+                    const int c0 = (int)cfill[pfx], c1v = (int)cfill[pfx + 1], c2 = (int)cfill[pfx + 2], c3 = (int)cfill[pfx + 3];
+                    childCnt[4 * gi] = c0; childCnt[4 * gi + 1] = c1v; childCnt[4 * gi + 2] = c2; childCnt[4 * gi + 3] = c3;
+                    ne = (c0 > 0) + (c1v > 0) + (c2 > 0) + (c3 > 0);
+                }
+                nonEmpty[gi] = (unsigned char)ne;
+            }
+            __syncthreads();
+        } else if (closed) {
             // first key slot of every depth-e prefix (exclusive scan in natural order)
             const int Ge = nIni << (2 * e);
             uint32_t *ce = cnt + lvoff(e);
@@ -366,7 +449,7 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
         const int prevSize = size;
 
         // ---- A: stable rank of every key inside its future child (warp-streaming scan, see above) ----
-        {
+        if (!bins_pass) {
             uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0;
             for (int p0 = s0; p0 < s1; p0 += 32 * kU) {
                 int gis[kU]; uint32_t keys[kU];
@@ -424,6 +507,7 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
             __syncthreads();
         }
         // ---- B: child sizes ----
+        if (!bins_pass)
         for (int gi = tid; gi < size; gi += kOctThreads) {
             const Node nd = nodes[gi];
             int ne = 0;
@@ -540,6 +624,23 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
             __syncthreads();
         }
         // ---- F: move keys ----
+        if (bins_pass) {
+            // from the gathered keys (kB, prefix codes in nB) straight to the final ranges: a key's node is the single-key node of the
+            // shallowest depth at which its prefix is alone, else its depth-e node; split nodes hand it on to the child of its next digit
+            const int B = L.oct_B, e = bins_e;
+            auto lvoff = [&](int k) { return nIni * (((1 << (2 * k)) - 1) / 3); };
+            for (int p = tid; p < n; p += kOctThreads) {
+                const uint32_t key = kB[p];
+                const int code = nB[p];
+                int gi = 0xffff;
+                for (int k = 0; k < e && gi == 0xffff; ++k) gi = clist[lvoff(k) + (code >> (2 * (B - k)))];
+                if (gi == 0xffff) gi = clist[lvoff(e) + (code >> (2 * (B - e)))];
+                const int pfx1 = code >> (2 * (B - e - 1));
+                const int fin = split[gi] ? newIdx[4 * gi + (pfx1 & 3)] : newIdx[4 * gi];
+                const int dst = (int)cstart[pfx1] + (int)atomicSub(cfill + pfx1, 1u) - 1;
+                kA[dst] = key; nA[dst] = (uint16_t)fin;
+            }
+        } else
         for (int pb = tid; pb < n; pb += kOctThreads * kU) {
             int gis[kU], qs[kU]; uint32_t keys[kU], es[kU];
 #pragma unroll
@@ -571,7 +672,8 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
             }
         }
         __syncthreads();
-        { uint32_t *t = kA; kA = kB; kB = t; uint16_t *u = nA; nA = nB; nB = u; Node *v = nodes; nodes = nodesN; nodesN = v; }
+        if (bins_pass) { Node *v = nodes; nodes = nodesN; nodesN = v; bins_pass = false; }   // the keys went kB -> kA
+        else { uint32_t *t = kA; kA = kB; kB = t; uint16_t *u = nA; nA = nB; nB = u; Node *v = nodes; nodes = nodesN; nodesN = v; }
         const int newSize = C + U;
         const int nToExpand = S.nToExpand;                 // reset only behind the next pass's first barrier
         cur_size = newSize;
@@ -592,7 +694,9 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
             if (cand_score(key) > cand_score(best)) best = key;
             else if (cand_score(key) == cand_score(best)) {
                 const int ya = cand_y(key), yb = cand_y(best), xa = cand_x(key), xb = cand_x(best);
-                const int ia = (ya - 3) / L.hCell, ib = (yb - 3) / L.hCell, ja = (xa - 3) / L.wCell, jb = (xb - 3) / L.wCell;
+                // (v - 3) / cell size by a host-made reciprocal (exact for v < 4096 and cells <= 64 px, see octree_closed_depth's neighbour)
+                const int ia = ((ya - 3) * L.inv_hCell) >> 18, ib = ((yb - 3) * L.inv_hCell) >> 18;
+                const int ja = ((xa - 3) * L.inv_wCell) >> 18, jb = ((xb - 3) * L.inv_wCell) >> 18;
                 const bool before = ia != ib ? ia < ib : ja != jb ? ja < jb : ya != yb ? ya < yb : xa < xb;
                 if (before) best = key;
             }
@@ -610,7 +714,7 @@ int octree_closed_depth(const Geo &g, int level)
     static int enabled = -1;
     if (enabled < 0) { const char *e = std::getenv("ORBX_OCT_CLOSED"); enabled = e ? std::atoi(e) : 1; }
     const LevelGeom &L = g.lv[level];
-    if (!enabled || L.nIni < 1 || L.nIni > 16 || L.N < 1 || L.max_cand > 65535) return 0;
+    if (!enabled || L.nIni < 1 || L.nIni > 16 || L.N < 1) return 0;
     const long avail = (long)g.oct_node_cap_max * (2 * (long)sizeof(Node) + 4 * 4 * 2 + 16 + 3 * 4 + 2) - (long)L.node_cap * 2 * (long)sizeof(Node) - 64;
     int B = 1;
     while (B < 6 && ((long)L.nIni << (2 * B)) < 2L * L.N) ++B;

@@ -43,6 +43,7 @@ struct LevelGeom {
     unsigned long long key_base;      // u32 offset of this level's key scratch inside a frame's region
     int kept_cap, kept_base;  // survivors bound and offset inside a frame's kept array
     int node_cap;             // octree node table capacity
+    int inv_wCell, inv_hCell; // ceil(2^18 / cell size): (v * inv) >> 18 == v / size for 0 <= v < 4096 and sizes <= 64
     int oct_B;                // depth of the closed-form phase 1 of the octree kernel (bins = nIni * 4^B), 0 = off
     float scale;              // mvScaleFactor[level]
     int patch_size;           // (int)(31 * scale), ORBextractor.cpp:794
