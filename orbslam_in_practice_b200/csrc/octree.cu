@@ -76,6 +76,22 @@ __device__ __forceinline__ int quadrant(uint32_t key, const Node &nd)
     return left ? (up ? 0 : 2) : (up ? 1 : 3);
 }
 
+// A key as a 64-bit value whose maximum over a node is the key the reference keeps (:697-715): the highest score, and among equal
+// scores the FIRST in candidate order -- candidates come cell by cell (row-major cells, ORBextractor.cpp:745-786) and row-major
+// inside a cell, so the order is (cell row, cell column, y, x); (v - 3) / cell size is a multiply by a host-made reciprocal.
+__device__ __forceinline__ unsigned long long best_key(uint32_t key, const LevelGeom &L)
+{
+    const int x = cand_x(key), y = cand_y(key);
+    const unsigned long long i = (unsigned)(((y - 3) * L.inv_hCell) >> 18), j = (unsigned)(((x - 3) * L.inv_wCell) >> 18);
+    const unsigned long long ord = (i << 32) | (j << 24) | ((unsigned long long)y << 12) | (unsigned long long)x;
+    return ((unsigned long long)cand_score(key) << 40) | (0xffffffffffull - ord);
+}
+__device__ __forceinline__ uint32_t best_key_decode(unsigned long long v)
+{
+    const unsigned long long ord = 0xffffffffffull - (v & 0xffffffffffull);
+    return pack_cand((int)(ord & 0xfff), (int)((ord >> 12) & 0xfff), (int)(v >> 40));
+}
+
 __device__ __forceinline__ uint32_t comp(const uint4 &v, int q) { return q == 0 ? v.x : q == 1 ? v.y : q == 2 ? v.z : v.w; }
 
 // kU: key groups a warp loads before it processes them.  Problems whose keys live in global memory (4K-sized levels: tens of
@@ -189,6 +205,9 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
     bool bins_pass = false;
     uint32_t *cfill = nullptr; uint16_t *cstart = nullptr, *clist = nullptr;
     int bins_e = 0;
+    // when the scatter of the closed form is the last step of the run, it also takes each node's best key (atomicMax of best_key):
+    // the final walk over every node's keys -- one thread per node, a dependent load per key -- is skipped
+    unsigned long long *best64 = nullptr;
     if (!kGlobalTables && L.oct_B > 0) {
         const int B = L.oct_B;
         const float hX = L.hX;
@@ -356,8 +375,9 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
                     int tot;
                     const int pos = carry + block_excl_scan<kOctWarps>(flag, S, tot);
                     carry += tot;
+                    if (t < Me) listpos[lvoff(k) + j] = flag ? (uint16_t)pos : (uint16_t)0xffffu;
                     if (flag) {
-                        listpos[lvoff(k) + j] = (uint16_t)pos;
+                        if (closed == 1) reinterpret_cast<unsigned long long *>(E32)[pos] = 0ull;
                         const int r = j >> (2 * k);
                         int x0 = (int)(hX * (float)r), x1 = (int)(hX * (float)(r + 1)), y0 = 0, y1 = L.regionH;
                         for (int d = 1; d <= k; ++d) {
@@ -379,15 +399,15 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
                 const uint32_t key = kB[p];
                 const int code = nB[p];
                 const int ge = code >> (2 * (B - e));
-                int node = -1;
-                for (int k = 0; k < e; ++k) {
-                    const int gk = code >> (2 * (B - k));
-                    if (cnt[lvoff(k) + gk] == 1u) { node = listpos[lvoff(k) + gk]; break; }
-                }
-                if (node < 0) node = listpos[lvoff(e) + ge];
+                // its depth-e node, or -- when an ancestor prefix already held this key alone -- that single-key node (exactly one
+                // prefix of the key's path is a node)
+                int node = listpos[lvoff(e) + ge];
+                for (int k = e - 1; node == 0xffff && k >= 0; --k) node = listpos[lvoff(k) + (code >> (2 * (B - k)))];
                 const int dst = (int)start[ge] + (int)atomicSub(ce + ge, 1u) - 1;
                 kA[dst] = key; nA[dst] = (uint16_t)node;
+                if (closed == 1) atomicMax(reinterpret_cast<unsigned long long *>(E32) + node, best_key(key, L));
             }
+            if (closed == 1) best64 = reinterpret_cast<unsigned long long *>(E32);
             cur_size = S.psize[e];
             __syncthreads();
         }
@@ -609,6 +629,7 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
                             ch.y0 = (q & 2) ? (short)sy : nd.y0; ch.y1 = (q & 2) ? nd.y1 : (short)sy;
                             ch.begin = nd.begin + off; ch.count = cnt;
                             nodesN[pos] = ch;
+                            if (bins_pass) reinterpret_cast<unsigned long long *>(nodeFirst)[pos] = 0ull;
                             off += cnt;
                             expand += cnt > 1;
                         }
@@ -618,6 +639,7 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
                     const int pos = C + ubase[gi];
                     nodesN[pos] = nd;
                     newIdx[4 * gi] = pos;
+                    if (bins_pass) reinterpret_cast<unsigned long long *>(nodeFirst)[pos] = 0ull;
                 }
             }
             if (expand) atomicAdd(&S.nToExpand, expand);
@@ -629,17 +651,20 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
             // shallowest depth at which its prefix is alone, else its depth-e node; split nodes hand it on to the child of its next digit
             const int B = L.oct_B, e = bins_e;
             auto lvoff = [&](int k) { return nIni * (((1 << (2 * k)) - 1) / 3); };
+            const bool last = C + U >= N || C + U == prevSize;      // the loop's exit test below: this scatter ends the run
+            unsigned long long *b64 = reinterpret_cast<unsigned long long *>(nodeFirst);   // zeroed per new node in step E
             for (int p = tid; p < n; p += kOctThreads) {
                 const uint32_t key = kB[p];
                 const int code = nB[p];
-                int gi = 0xffff;
-                for (int k = 0; k < e && gi == 0xffff; ++k) gi = clist[lvoff(k) + (code >> (2 * (B - k)))];
-                if (gi == 0xffff) gi = clist[lvoff(e) + (code >> (2 * (B - e)))];
+                int gi = clist[lvoff(e) + (code >> (2 * (B - e)))];
+                for (int k = e - 1; gi == 0xffff && k >= 0; --k) gi = clist[lvoff(k) + (code >> (2 * (B - k)))];
                 const int pfx1 = code >> (2 * (B - e - 1));
                 const int fin = split[gi] ? newIdx[4 * gi + (pfx1 & 3)] : newIdx[4 * gi];
                 const int dst = (int)cstart[pfx1] + (int)atomicSub(cfill + pfx1, 1u) - 1;
                 kA[dst] = key; nA[dst] = (uint16_t)fin;
+                if (last) atomicMax(b64 + fin, best_key(key, L));
             }
+            if (last) best64 = b64;
         } else
         for (int pb = tid; pb < n; pb += kOctThreads * kU) {
             int gis[kU], qs[kU]; uint32_t keys[kU], es[kU];
@@ -684,6 +709,9 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
     // ---- :697-715 keep the best key of every node (first maximum wins), list order ----
     const int size = cur_size;
     uint32_t *kept = kept_out + (size_t)f * g.kept_total + L.kept_base;
+    if (best64) {
+        for (int gi = tid; gi < size && gi < L.kept_cap; gi += kOctThreads) kept[gi] = best_key_decode(best64[gi]);
+    } else
     for (int gi = tid; gi < size && gi < L.kept_cap; gi += kOctThreads) {
         const Node nd = nodes[gi];
         // the first maximum in CANDIDATE order wins (:700-712).  The keys of a node are not kept in that order (closed-form phase 1), so
