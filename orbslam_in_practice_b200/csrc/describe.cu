@@ -167,9 +167,11 @@ constexpr int kPatchAlloc = 2 * kStagePasses * kPatchWords; // words per patch b
 // Patch staging variants (ORBX_DESC_STAGE): 0 = 4-byte cp.async.ca, rows of 11 words from a 4-byte aligned column;
 // 1 = 16-byte cp.async.cg (L1 bypass), 2 = one cp.async.bulk (TMA engine, mbarrier completion) per row -- both with rows of
 // 64 bytes from a 16-byte aligned column (x - 18 rounded down to 16: the 37 columns end at byte 51 at most).
-__host__ __device__ constexpr int patch_pitch(int stage) { return stage == 0 ? kPatchWords * 4 : 64; }           // bytes per staged patch row
-__host__ __device__ constexpr int patch_buf_words(int stage) { return stage == 0 ? kPatchAlloc : kPatchRows * 16; }  // words per patch buffer
-__host__ __device__ constexpr int patch_align_mask(int stage) { return stage == 0 ? ~3 : ~15; }
+// 3 = 8-byte cp.async.ca, rows of 48 bytes from an 8-byte aligned column, five rows (30 lanes) per pass: 8 LDGSTS.64 per patch
+// instead of 19 LDGSTS.32, and a 12-word pitch on which eight consecutive rows of 16 bytes fall into 32 different banks.
+__host__ __device__ constexpr int patch_pitch(int stage) { return stage == 0 ? kPatchWords * 4 : stage == 3 ? 48 : 64; }           // bytes per staged patch row
+__host__ __device__ constexpr int patch_buf_words(int stage) { return stage == 0 ? kPatchAlloc : stage == 3 ? kPatchRows * 12 : kPatchRows * 16; }  // words per patch buffer
+__host__ __device__ constexpr int patch_align_mask(int stage) { return stage == 0 ? ~3 : stage == 3 ? ~7 : ~15; }
 // IC_Angle as dot products: the 31 x 31 window is read as 9 aligned words per row, three rows per warp pass
 // (lane = row-in-pass * 9 + word), and a host-built table holds for every (alignment, pass, lane) the four
 // column weights u and the four row weights v as signed bytes, zero outside the circular patch (umax) and
@@ -192,6 +194,10 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 __device__ __forceinline__ void cp_async16_cg(void *smem, const void *gmem)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8_ca(void *smem, const void *gmem)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
@@ -225,6 +231,18 @@ __device__ __forceinline__ void stage_patch(uint32_t *patch, const uint8_t *blur
 #pragma unroll
         for (int it = 0; it < (kPatchRows + 7) / 8; ++it, src += 8 * bp, dst += 8 * 64)
             if (it * 8 + (lane >> 2) < kPatchRows) cp_async16_cg(dst, src);
+        cp_async_commit();
+        return;
+    }
+    if (kStage == 3) {
+        const int r = lane / 6, wx = lane - r * 6;
+        if (lane < 30) {
+            const uint8_t *src = blur + L.blur_base + (size_t)f * L.blur_frame_stride + (size_t)(y - kPatchR + r) * bp + xa + 8 * wx;
+            uint8_t *dst = reinterpret_cast<uint8_t *>(patch) + r * 48 + wx * 8;
+#pragma unroll
+            for (int it = 0; it < 8; ++it, src += 5 * bp)
+                if (it < 7 || r < 2) cp_async8_ca(dst + it * 5 * 48, src);      // rows 35, 36 in the last pass
+        }
         cp_async_commit();
         return;
     }
@@ -471,6 +489,7 @@ void launch_describe(const Geo &g, const DevBuffers &b, int nframes, orbx_keypoi
         cudaFuncSetAttribute(k_describe<5, kDescSlots, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         cudaFuncSetAttribute(k_describe<5, kDescSlots, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         cudaFuncSetAttribute(k_describe<5, kDescSlots, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaFuncSetAttribute(k_describe<5, kDescSlots, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         cudaFuncSetAttribute(k_describe<5, 2, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 72);
         cudaFuncSetAttribute(k_describe<5, kDescSlots, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDescWarps * 2 * patch_buf_words(1) * 4);
         cudaFuncSetAttribute(k_describe<5, kDescSlots, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDescWarps * 2 * patch_buf_words(2) * 4);
@@ -481,6 +500,7 @@ void launch_describe(const Geo &g, const DevBuffers &b, int nframes, orbx_keypoi
     if (small) k_describe<5, 2, 0><<<grd, kDescWarps * 32, dyn0, s>>>(DESC_ARGS);
     else if (stage == 1) k_describe<5, kDescSlots, 1><<<grd, kDescWarps * 32, dyn1, s>>>(DESC_ARGS);
     else if (stage == 2) k_describe<5, kDescSlots, 2><<<grd, kDescWarps * 32, dyn1, s>>>(DESC_ARGS);
+    else if (stage == 3) k_describe<5, kDescSlots, 3><<<grd, kDescWarps * 32, kDescWarps * 2 * patch_buf_words(3) * 4, s>>>(DESC_ARGS);
     else k_describe<5, kDescSlots, 0><<<grd, kDescWarps * 32, dyn0, s>>>(DESC_ARGS);
 #undef DESC_ARGS
 }
