@@ -193,7 +193,7 @@ static int host_reflect101(int i, int n)
 // Padded tables and per-block source ranges of the staged resize kernel (pyramid.cu).  tabx / taby of level L must
 // already be in `tab`.  Everything a block needs to know about its source tile is precomputed here, for both border
 // widths (variant 0: kMinBlurBorder, variant 1: kBorder).
-static void staged_resize_tables(const LevelGeom &S, LevelGeom &L, std::vector<int2> &tab)
+static void staged_resize_tables(const LevelGeom &S, LevelGeom &L, std::vector<int2> &tab, int max_batch)
 {
     while (tab.size() & 3) tab.push_back(make_int2(0, 0));
     L.tabxp = (int)tab.size();
@@ -213,6 +213,17 @@ static void staged_resize_tables(const LevelGeom &S, LevelGeom &L, std::vector<i
     L.rs_bw = chunks > 64 ? 128 : 64;                 // small levels: narrower blocks so that few lanes idle past the end of a row
     L.rs_nbx = (chunks + L.rs_bw - 1) / L.rs_bw;
     L.rs_staged = S.h < 32768 ? 1 : 0;
+    // Destination rows per block.  16 amortises the staged source rows best and wins for every level of a large batch (measured on
+    // 256 VGA frames: 0.174 ms with 16 rows everywhere, 0.183 with 8 rows on levels 5-7, 0.190 / 0.235 with 8 / 4 everywhere).  The
+    // handles of the low-latency path (batches of <= 8 frames, a handful of blocks per launch) are bound by the serial depth of a
+    // thread instead: 4 rows per block cut the resize chain of one VGA frame from 46 to 32 us.
+    {
+        static int forced = -1;
+        if (forced < 0) { const char *e = std::getenv("ORBX_RS_ROWS"); forced = e ? std::atoi(e) : 0; }
+        L.rs_rows = max_batch <= 8 ? 4 : 16;
+        if (forced == 4 || forced == 8 || forced == 16) L.rs_rows = forced;
+    }
+    const int kRows = L.rs_rows;
     const int Bv[2] = { kMinBlurBorder, kBorder };
     int tile_w = 16;
     L.rs_xr = (int)tab.size();
@@ -237,11 +248,11 @@ static void staged_resize_tables(const LevelGeom &S, LevelGeom &L, std::vector<i
     int tile_h = 1;
     L.rs_yr = (int)tab.size();
     for (int v = 0; v < 2; ++v) {
-        const int B = Bv[v], nby = (L.h + 2 * B + kResizeRows - 1) / kResizeRows;
+        const int B = Bv[v], nby = (L.h + 2 * B + kRows - 1) / kRows;
         if (v == 0) L.rs_nby0 = nby;
         for (int by = 0; by < nby; ++by) {
             int lo = INT_MAX, hi = -1;
-            for (int Y = by * kResizeRows - B; Y < std::min((by + 1) * kResizeRows - B, L.h + B); ++Y) {
+            for (int Y = by * kRows - B; Y < std::min((by + 1) * kRows - B, L.h + B); ++Y) {
                 const int e = tab[(size_t)L.tabyp + (size_t)(Y + kBorder)].x;
                 lo = std::min(lo, e & 0xffff); hi = std::max(hi, e >> 16);
             }
@@ -327,7 +338,7 @@ static int build_geometry(const orbx_extractor *ex, int w, int h, Geo &g, std::v
             while (tables->size() & 3) tables->push_back(make_int2(0, 0));   // 32-byte aligned runs for int4 loads
             L.tabx = (int)tables->size(); linear_table(g.lv[l - 1].w, L.w, true, *tables);
             L.taby = (int)tables->size(); linear_table(g.lv[l - 1].h, L.h, false, *tables);
-            staged_resize_tables(g.lv[l - 1], L, *tables);
+            staged_resize_tables(g.lv[l - 1], L, *tables, ex->max_batch);
         }
     }
     g.total_cells = cell_off;
@@ -482,7 +493,7 @@ extern "C" int orbx_create(const orbx_params *p, int max_width, int max_height, 
     DevBuffers &b = ex->buf;
     size_t ntab = 0;
     for (int l = 1; l < g.nlevels; ++l) ntab += (size_t)g.lv[l].w + 2 * (size_t)g.lv[l].h + (size_t)g.lv[l].pitch + 2 * kBorder + 16 +
-                                               2 * ((size_t)g.lv[l].pitch / 256 + 2) + 2 * ((size_t)(g.lv[l].h + 2 * kBorder) / kResizeRows + 2);   // plain + padded tables + block ranges
+                                               2 * ((size_t)g.lv[l].pitch / 256 + 2) + 2 * ((size_t)(g.lv[l].h + 2 * kBorder) / 4 + 2);   // plain + padded tables + block ranges
 #define TRY(x) do { rc = (x); if (rc) { orbx_destroy(ex); return rc; } } while (0)
     TRY(dev_alloc(ex, &b.pyr, g.pyr_frame_total));
     TRY(dev_alloc(ex, &b.blur, g.blur_frame_total + 256));   // the descriptor stage reads 64-byte row segments: up to 26 bytes past a row's end

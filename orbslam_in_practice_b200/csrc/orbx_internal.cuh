@@ -15,7 +15,7 @@ constexpr int kBorder = ORBX_EDGE_THRESHOLD;
 constexpr int kMinBlurBorder = 4;     // border always written: the blur kernel reads 3 px (+1 for word alignment) outside the level
 constexpr int kHalfPatch = 15;       // HALF_PATCH_SIZE, ORBextractor.cpp:23
 constexpr int kMinBorder = 16;       // EDGE_THRESHOLD - 3, ORBextractor.cpp:729
-constexpr int kResizeRows = 16;      // destination rows per block of the staged resize kernel (host tables depend on it)
+constexpr int kResizeRows = 16;      // most destination rows per block of the staged resize kernel (LevelGeom::rs_rows is the level's choice)
 
 // packed FAST candidate: x (12 bit) | y (12 bit) << 12 | score (8 bit) << 24, coordinates
 // relative to (16,16) of the level (the values of vToDistributeKeys).
@@ -53,6 +53,7 @@ struct LevelGeom {
     int tabxp;                // [pitch] entry(i) = tabx[reflect101(clamp(i - kPadX, -19, w + 18))]
     int tabyp;                // [h + 38] entry(Y + 19) = {sy0 | sy1 << 16 (clamped source rows), cy0 | cy1 << 16}
     int rs_bw;                // threads per block (4 pixels each)
+    int rs_rows;              // destination rows per block (4, 8 or 16 <= kResizeRows), chosen per level by the host
     int rs_tile_w, rs_tile_h; // shared-memory source tile: bytes per row (multiple of 16) and rows, maxima over all blocks
     int rs_xr, rs_yr;         // per-block source ranges {lo, hi}: [2 border variants][blocks in x], [variant 0 blocks in y][variant 1 ...]
     int rs_nbx, rs_nby0;      // blocks in x; blocks in y of variant 0 (border 4)

@@ -232,14 +232,15 @@ k_resize(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr_src, uin
     const int chunk = blockIdx.x * blockDim.x + threadIdx.x;
     const int X0 = chunk * 4 - kPadX;
     const bool active = chunk * 4 < D.pitch && X0 + 3 >= -B && X0 < D.w + B;
-    const int Ybase = (int)blockIdx.y * kResizeRows - B;
+    const int kRows = D.rs_rows;
+    const int Ybase = (int)blockIdx.y * kRows - B;
     const int TP = D.rs_tile_w;
     // source ranges of this block, precomputed on the host: columns [xr.x, xr.y] (+1 for the second tap), rows [yr.x, yr.y]
     const int2 xr = __ldg(tables + D.rs_xr + var * D.rs_nbx + blockIdx.x);
     const int2 yr = __ldg(tables + D.rs_yr + var * D.rs_nby0 + blockIdx.y);
     if (xr.y < 0) return;                                  // no pixel of this block lies inside the bordered level (uniform)
     const int tx0 = xr.x & ~15, smin = yr.x;
-    if (threadIdx.x < kResizeRows) {
+    if (threadIdx.x < kRows) {
         const int2 t = __ldg(tables + D.tabyp + kBorder + min(Ybase + (int)threadIdx.x, D.h + B - 1));
         s_ty[threadIdx.x] = make_int4(((t.x & 0xffff) - smin) * TP, ((t.x >> 16) - smin) * TP, (short)(t.y & 0xffff), t.y >> 16);
     }
@@ -275,7 +276,7 @@ k_resize(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr_src, uin
     if (!active) return;
 
     uint8_t *drow = pyr_dst + D.base + (size_t)f * D.frame_stride + (size_t)chunk * 4 + (size_t)(Ybase + kPadY) * D.pitch;
-    const int nrows = min(kResizeRows, D.h + B - Ybase);
+    const int nrows = min(kRows, D.h + B - Ybase);
     int prev_off1 = -1;
     int hp[4] = { 0, 0, 0, 0 };                           // horizontally interpolated lower source row, already >> 4
     // shared-window addresses of the two 8-byte windows, formed once: through the generic pointer the compiler rebuilt the window
@@ -358,7 +359,7 @@ void launch_resize(const Geo &g, const DevBuffers &b, int level, int nframes, cu
     const LevelGeom &L = g.lv[level];
     const int chunks = L.pitch / 4;
     const int bw = L.rs_bw;
-    const int rows = L.rs_staged ? kResizeRows : kGatherRows;
+    const int rows = L.rs_staged ? L.rs_rows : kGatherRows;
     dim3 grd((chunks + bw - 1) / bw, (L.h + 2 * B + rows - 1) / rows, nframes);
     if (L.rs_staged)
         k_resize<<<grd, bw, (size_t)L.rs_tile_w * L.rs_tile_h, s>>>(g, b.pyr, b.pyr, b.tables, level);
