@@ -195,7 +195,7 @@ k_octree(const __grid_constant__ Geo g, const int *__restrict__ cell_count, cons
     //      the depth-k group is lexicographic in (root, q1 .. qk) with directions that alternate from the last digit backwards
     //      (descending, ascending, ...; the root follows q1): an XOR mask on the prefix.  So one flag scan over the concatenated
     //      prefix spaces yields every node's list index, and one counting scatter by depth-e prefix replaces the root partition and
-    //      e partition passes.  tools/proto/octree_closed_form.py checks this restatement against the oracle.  When phase 1 does not
+    //      e partition passes.  The restatement is checked on the CPU against the sequential form (tools/proto/octree_closed_form.py).  When phase 1 does not
     //      end within depth B (few, clustered candidates) the sequential form below runs instead.
     int closed = 0;                                        // 0: sequential phase 1; 1: closed form, the run is finished; 2: closed form, phase 2 follows
     // The first pass of phase 2 runs from the bins as well when the prefixes one depth below e were counted (e + 1 <= B): the child
