@@ -169,9 +169,9 @@ constexpr int kPatchAlloc = 2 * kStagePasses * kPatchWords; // words per patch b
 // 64 bytes from a 16-byte aligned column (x - 18 rounded down to 16: the 37 columns end at byte 51 at most).
 // 3 = 8-byte cp.async.ca, rows of 48 bytes from an 8-byte aligned column, five rows (30 lanes) per pass: 8 LDGSTS.64 per patch
 // instead of 19 LDGSTS.32, and a 12-word pitch on which eight consecutive rows of 16 bytes fall into 32 different banks.
-__host__ __device__ constexpr int patch_pitch(int stage) { return stage == 0 ? kPatchWords * 4 : stage == 3 ? 48 : 64; }           // bytes per staged patch row
-__host__ __device__ constexpr int patch_buf_words(int stage) { return stage == 0 ? kPatchAlloc : stage == 3 ? kPatchRows * 12 : kPatchRows * 16; }  // words per patch buffer
-__host__ __device__ constexpr int patch_align_mask(int stage) { return stage == 0 ? ~3 : stage == 3 ? ~7 : ~15; }
+__host__ __device__ constexpr int patch_pitch(int stage) { return stage == 0 || stage == 4 ? kPatchWords * 4 : stage == 3 ? 48 : 64; }           // bytes per staged patch row
+__host__ __device__ constexpr int patch_buf_words(int stage) { return stage == 0 || stage == 4 ? kPatchAlloc : stage == 3 ? kPatchRows * 12 : kPatchRows * 16; }  // words per patch buffer
+__host__ __device__ constexpr int patch_align_mask(int stage) { return stage == 0 || stage == 4 ? ~3 : stage == 3 ? ~7 : ~15; }
 // IC_Angle as dot products: the 31 x 31 window is read as 9 aligned words per row, three rows per warp pass
 // (lane = row-in-pass * 9 + word), and a host-built table holds for every (alignment, pass, lane) the four
 // column weights u and the four row weights v as signed bytes, zero outside the circular patch (umax) and
@@ -305,6 +305,12 @@ k_describe(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, const
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // variant 4: the lane's eight pattern entries live in registers (16 of the 64 a 4-block launch bound allows; shared memory
+    // holds 4 blocks per SM anyway): eight LDS.64 = 16 of ~200 L1 wavefronts per keypoint less
+    constexpr bool kRegPat = kStage == 4;
+    uint2 rpat[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) rpat[k] = kRegPat ? pat[k][lane] : make_uint2(0u, 0u);
     // per-level keypoint counts -> inclusive prefix in lanes 0..nlevels-1 (level-major concatenation, :1036-1063)
     const int myc = lane < g.nlevels ? nkept[f * g.nlevels + lane] : 0;
     int incl = myc;
@@ -407,7 +413,8 @@ k_describe(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, const
         int val = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-            const uint2 pp = pat[k][lane];                   // pattern offsets are integers in [-13, 13]: exact in half
+            uint2 pp = kRegPat ? rpat[k] : pat[k][lane];     // pattern offsets are integers in [-13, 13]: exact in half
+            if (kRegPat) asm volatile("" : "+r"(pp.x), "+r"(pp.y));   // keeps the half -> float conversions inside the loop (hoisted they cost 32 registers)
             const float2 q0 = __half22float2(*reinterpret_cast<const __half2 *>(&pp.x)), q1 = __half22float2(*reinterpret_cast<const __half2 *>(&pp.y));
             const float x0 = q0.x, y0 = q0.y, x1 = q1.x, y1 = q1.y;
             const int r0 = __float2int_rn(__fadd_rn(__fmul_rn(x0, b), __fmul_rn(y0, a)));
@@ -481,10 +488,11 @@ void launch_describe(const Geo &g, const DevBuffers &b, int nframes, orbx_keypoi
     const int per_block = kDescWarps * (small ? 2 : kDescSlots);
     dim3 grd((g.capacity + per_block - 1) / per_block, nframes);
     // measured on a B200 (256 VGA frames): the kernel is bound by the L1 data pipe, and a small L1 (the default carve-out
-    // maximises shared memory: 28 KB of L1 left) costs 30 %; 164 KB of shared memory = 4 resident blocks and 92 KB of L1.
-    // 48 registers (the 5-block launch bound) leave room for the other stream's kernels on the same SM.
+    // maximises shared memory: 28 KB of L1 left) costs 30 %.  Round 2, after the shuffle ladders were gone: 141 KB of shared
+    // memory = 3 resident blocks and ~85 KB of L1 beat 164 KB = 4 blocks (0.2134 against 0.2195 ms; 114 KB = 2 blocks 0.2176),
+    // and with three blocks the 64 registers of variant 4 (pattern entries in registers) cost nothing: 0.2108 ms.
     static bool configured[64] = {};
-    static int stage = 0, carve = 72;
+    static int stage = 4, carve = 62;
     if (!configured[dev]) {
         if (const char *e = std::getenv("ORBX_DESC_STAGE")) stage = std::atoi(e);
         if (const char *e = std::getenv("ORBX_DESC_CARVEOUT")) carve = std::atoi(e);
@@ -493,6 +501,7 @@ void launch_describe(const Geo &g, const DevBuffers &b, int nframes, orbx_keypoi
         cudaFuncSetAttribute(k_describe<5, kDescSlots, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         cudaFuncSetAttribute(k_describe<5, kDescSlots, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         cudaFuncSetAttribute(k_describe<5, 2, 0>, cudaFuncAttributePreferredSharedMemoryCarveout, 72);
+        cudaFuncSetAttribute(k_describe<4, kDescSlots, 4>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         cudaFuncSetAttribute(k_describe<5, kDescSlots, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDescWarps * 2 * patch_buf_words(1) * 4);
         cudaFuncSetAttribute(k_describe<5, kDescSlots, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kDescWarps * 2 * patch_buf_words(2) * 4);
         configured[dev] = true;
@@ -503,6 +512,7 @@ void launch_describe(const Geo &g, const DevBuffers &b, int nframes, orbx_keypoi
     else if (stage == 1) k_describe<5, kDescSlots, 1><<<grd, kDescWarps * 32, dyn1, s>>>(DESC_ARGS);
     else if (stage == 2) k_describe<5, kDescSlots, 2><<<grd, kDescWarps * 32, dyn1, s>>>(DESC_ARGS);
     else if (stage == 3) k_describe<5, kDescSlots, 3><<<grd, kDescWarps * 32, kDescWarps * 2 * patch_buf_words(3) * 4, s>>>(DESC_ARGS);
+    else if (stage == 4) k_describe<4, kDescSlots, 4><<<grd, kDescWarps * 32, dyn0, s>>>(DESC_ARGS);
     else k_describe<5, kDescSlots, 0><<<grd, kDescWarps * 32, dyn0, s>>>(DESC_ARGS);
 #undef DESC_ARGS
 }
