@@ -387,17 +387,28 @@ k_describe(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, const
         my_a = (float)cd; my_b = (float)sd;
     }
 
+    // the keypoint records of the warp's slots, lane s writing slot s: seven stores per warp instead of seven per keypoint
+    if (lane < nslot) {
+        const LevelGeom &Lk = g.lv[my_level];
+        orbx_keypoint kp;
+        kp.x = (float)(cand_x(my_key) + kMinBorder); kp.y = (float)(cand_y(my_key) + kMinBorder);               // :801-802
+        if (my_level != 0) { kp.x = __fmul_rn(kp.x, Lk.scale); kp.y = __fmul_rn(kp.y, Lk.scale); }   // :1055-1061
+        kp.size = (float)Lk.patch_size;
+        kp.angle = my_angle;
+        kp.response = (float)cand_score(my_key);
+        kp.octave = my_level;
+        kp.class_id = -1;
+        out_kps[(size_t)f * g.capacity + slot0 + lane] = kp;
+    }
+
     // ---- phase 3: rotated BRIEF, lane i produces descriptor byte i from its 16 pattern points ----
     uint32_t nkey = __shfl_sync(0xffffffffu, my_key, 0);     // key / level of the next keypoint, handed from one iteration to the next:
     int nlevel = __shfl_sync(0xffffffffu, my_level, 0);       // every shuffle is a slot on the same pipe as the shared-memory wavefronts
 #pragma unroll 1
     for (int si = 0; si < nslot; ++si) {
         const int slot = slot0 + si;
-        const uint32_t key = nkey;
-        const int level = nlevel;
         const float a = __shfl_sync(0xffffffffu, my_a, si), b = __shfl_sync(0xffffffffu, my_b, si);
-        const int x = cand_x(key) + kMinBorder, y = cand_y(key) + kMinBorder;
-        const LevelGeom &L = g.lv[level];
+        const int x = cand_x(nkey) + kMinBorder;             // this keypoint's (staged one iteration ago)
         if (si + 1 < nslot) {                                // next keypoint's patch into the other buffer
             nkey = __shfl_sync(0xffffffffu, my_key, si + 1);
             nlevel = __shfl_sync(0xffffffffu, my_level, si + 1);
@@ -426,17 +437,6 @@ k_describe(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, const
         }
         out_desc[((size_t)f * g.capacity + slot) * 32 + lane] = (uint8_t)val;
 
-        if (lane == si) {
-            orbx_keypoint kp;
-            kp.x = (float)x; kp.y = (float)y;
-            if (level != 0) { kp.x = __fmul_rn(kp.x, L.scale); kp.y = __fmul_rn(kp.y, L.scale); }   // :1055-1061
-            kp.size = (float)L.patch_size;
-            kp.angle = my_angle;
-            kp.response = (float)cand_score(key);
-            kp.octave = level;
-            kp.class_id = -1;
-            out_kps[(size_t)f * g.capacity + slot] = kp;
-        }
         __syncwarp();                                        // this buffer is the staging target of the next iteration
     }
 }
