@@ -220,13 +220,12 @@ __device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem, uint32_t 
 
 // blurred 37 x 37 patch (word aligned, 11 words per row) -> shared memory: lanes 0..21 copy two rows per pass
 template <int kStage>
-__device__ __forceinline__ void stage_patch(uint32_t *patch, const uint8_t *blur, const LevelGeom &L, int f, int x, int y, int lane, uint64_t *bar)
+__device__ __forceinline__ void stage_patch(uint32_t *patch, const uint8_t *base, int bp, int lane, uint64_t *bar)
 {
-    const int bp = L.blur_pitch;
-    const int xa = (x - kPatchR) & patch_align_mask(kStage);   // first staged column (keypoints sit >= 19 px inside)
+    // base: row y - 18 of the blurred level at the variant's aligned first column (x - 18 rounded down); bp: bytes per blurred row
     if (kStage == 1) {
         // 16 bytes per lane, four lanes per 64-byte row, eight rows per pass: 5 LDGSTS.128 per patch, L1 bypassed
-        const uint8_t *src = blur + L.blur_base + (size_t)f * L.blur_frame_stride + (size_t)(y - kPatchR + (lane >> 2)) * bp + xa + 16 * (lane & 3);
+        const uint8_t *src = base + (size_t)(lane >> 2) * bp + 16 * (lane & 3);
         uint8_t *dst = reinterpret_cast<uint8_t *>(patch) + lane * 16;
 #pragma unroll
         for (int it = 0; it < (kPatchRows + 7) / 8; ++it, src += 8 * bp, dst += 8 * 64)
@@ -237,7 +236,7 @@ __device__ __forceinline__ void stage_patch(uint32_t *patch, const uint8_t *blur
     if (kStage == 3) {
         const int r = lane / 6, wx = lane - r * 6;
         if (lane < 30) {
-            const uint8_t *src = blur + L.blur_base + (size_t)f * L.blur_frame_stride + (size_t)(y - kPatchR + r) * bp + xa + 8 * wx;
+            const uint8_t *src = base + (size_t)r * bp + 8 * wx;
             uint8_t *dst = reinterpret_cast<uint8_t *>(patch) + r * 48 + wx * 8;
 #pragma unroll
             for (int it = 0; it < 8; ++it, src += 5 * bp)
@@ -250,7 +249,7 @@ __device__ __forceinline__ void stage_patch(uint32_t *patch, const uint8_t *blur
         // the TMA engine copies the rows: one 64-byte bulk copy per row, issued by one lane, completion on the buffer's mbarrier
         if (lane == 0) {
             mbar_expect_tx(bar, kPatchRows * 64);
-            const uint8_t *src = blur + L.blur_base + (size_t)f * L.blur_frame_stride + (size_t)(y - kPatchR) * bp + xa;
+            const uint8_t *src = base;
             uint8_t *dst = reinterpret_cast<uint8_t *>(patch);
 #pragma unroll 1
             for (int r = 0; r < kPatchRows; ++r, src += bp, dst += 64) bulk_g2s(dst, src, 64, bar);
@@ -259,7 +258,7 @@ __device__ __forceinline__ void stage_patch(uint32_t *patch, const uint8_t *blur
     }
     if (lane < 2 * kPatchWords) {
         const int r = lane >= kPatchWords ? 1 : 0, wx = lane - r * kPatchWords;
-        const uint8_t *src = blur + L.blur_base + (size_t)f * L.blur_frame_stride + (size_t)(y - kPatchR + r) * bp + xa + 4 * wx;
+        const uint8_t *src = base + (size_t)r * bp + 4 * wx;
         uint32_t *dst = patch + lane;
 #pragma unroll
         for (int it = 0; it < kStagePasses; ++it, src += 2 * bp)
@@ -334,6 +333,25 @@ k_describe(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, const
         my_key = __ldg(kept + (size_t)f * g.kept_total + g.lv[my_level].kept_base + (slot - first));
     }
 
+    // Per-slot records, written once by lane s for keypoint s and read back by the whole warp with ONE broadcast load each: the
+    // window / patch addresses used to be rebuilt by every lane for every keypoint from two shuffles (key, level) and three
+    // constant-bank loads of the level's geometry -- all of them slots on the pipe the kernel is bound by (ncu: L1 wavefronts).
+    __shared__ uint4 rec_win[kDescWarps][kDescSlots], rec_patch[kDescWarps][kDescSlots];   // {address lo, hi, pitch, alignment / x - xa}
+    __shared__ float2 rec_ab[kDescWarps][kDescSlots];
+    if (lane < nslot) {
+        const LevelGeom &Lk = g.lv[my_level];
+        const int x = cand_x(my_key) + kMinBorder, y = cand_y(my_key) + kMinBorder;   // :801-802
+        const int al = (x - kHalfPatch + kPadX) & 3;       // bytes between the aligned first word and column x-15
+        const unsigned long long w = (unsigned long long)(pyr + Lk.base + (size_t)f * Lk.frame_stride + (size_t)(kPadY + y - kHalfPatch) * Lk.pitch
+                                                          + (kPadX + x - kHalfPatch - al));
+        rec_win[warp][lane] = make_uint4((uint32_t)w, (uint32_t)(w >> 32), (uint32_t)Lk.pitch, (uint32_t)al);
+        const int xa = (x - kPatchR) & patch_align_mask(kStage);   // first staged column (keypoints sit >= 19 px inside)
+        const unsigned long long pb = (unsigned long long)(blur + Lk.blur_base + (size_t)f * Lk.blur_frame_stride + (size_t)(y - kPatchR) * Lk.blur_pitch + xa);
+        rec_patch[warp][lane] = make_uint4((uint32_t)pb, (uint32_t)(pb >> 32), (uint32_t)Lk.blur_pitch, (uint32_t)(x - xa));
+    }
+    __syncwarp();
+    auto rec_ptr = [](const uint4 &r) { return reinterpret_cast<const uint8_t *>((unsigned long long)r.x | ((unsigned long long)r.y << 32)); };
+
     // ---- phase 1: IC_Angle moments on the un-blurred level (:27-54) for the warp's keypoints; lane s keeps keypoint s.
     //      The eleven pixel words of keypoint s+1 are loaded before the dot products of keypoint s. ----
     const int mrow = lane / 9, mword = lane - mrow * 9;    // lanes 27..31 read a fourth row with zero weights
@@ -341,18 +359,14 @@ k_describe(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, const
     uint32_t px[kMomentPasses], nx[kMomentPasses];
     int al = 0, nal = 0;
     auto load_window = [&](int si, uint32_t (&dst)[kMomentPasses], int &al_out, bool stage) {
-        const uint32_t key = __shfl_sync(0xffffffffu, my_key, si);
-        const int level = __shfl_sync(0xffffffffu, my_level, si);
-        const LevelGeom &L = g.lv[level];
-        const int x = cand_x(key) + kMinBorder, y = cand_y(key) + kMinBorder;   // :801-802
-        if (stage) stage_patch<kStage>(patch_all[warp][0], blur, L, f, x, y, lane, &patch_bar[warp][0]);
-        const int pitch = L.pitch;
-        al_out = (x - kHalfPatch + kPadX) & 3;             // bytes between the aligned first word and column x-15
-        const uint8_t *src = pyr + L.base + (size_t)f * L.frame_stride + (size_t)(kPadY + y - kHalfPatch + mrow) * pitch
-                             + (kPadX + x - kHalfPatch - al_out) + 4 * mword;
-#pragma unroll
+        if (stage) { const uint4 rp = rec_patch[warp][0]; stage_patch<kStage>(patch_all[warp][0], rec_ptr(rp), (int)rp.z, lane, &patch_bar[warp][0]); }
+        const uint4 rw = rec_win[warp][si];
+        const int pitch = (int)rw.z;
+        al_out = (int)rw.w;
+        const uint8_t *src = rec_ptr(rw) + (size_t)mrow * pitch + 4 * mword;
         // only the 31 rows of the window are read (lanes 27..31 and the last pass's rows 31, 32 carry zero weights): every row a
         // load instruction touches is one more L1 wavefront, and the kernel sits on the L1 wavefront ceiling
+#pragma unroll
         for (int it = 0; it < kMomentPasses; ++it, src += 3 * pitch)
             dst[it] = (lane < 27 && 3 * it + mrow < 2 * kHalfPatch + 1) ? __ldg(reinterpret_cast<const uint32_t *>(src)) : 0u;
     };
@@ -389,6 +403,7 @@ k_describe(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, const
 
     // the keypoint records of the warp's slots, lane s writing slot s: seven stores per warp instead of seven per keypoint
     if (lane < nslot) {
+        rec_ab[warp][lane] = make_float2(my_a, my_b);
         const LevelGeom &Lk = g.lv[my_level];
         orbx_keypoint kp;
         kp.x = (float)(cand_x(my_key) + kMinBorder); kp.y = (float)(cand_y(my_key) + kMinBorder);               // :801-802
@@ -402,25 +417,24 @@ k_describe(const __grid_constant__ Geo g, const uint8_t *__restrict__ pyr, const
     }
 
     // ---- phase 3: rotated BRIEF, lane i produces descriptor byte i from its 16 pattern points ----
-    uint32_t nkey = __shfl_sync(0xffffffffu, my_key, 0);     // key / level of the next keypoint, handed from one iteration to the next:
-    int nlevel = __shfl_sync(0xffffffffu, my_level, 0);       // every shuffle is a slot on the same pipe as the shared-memory wavefronts
+    __syncwarp();
+    uint4 nrec = rec_patch[warp][0];
 #pragma unroll 1
     for (int si = 0; si < nslot; ++si) {
         const int slot = slot0 + si;
-        const float a = __shfl_sync(0xffffffffu, my_a, si), b = __shfl_sync(0xffffffffu, my_b, si);
-        const int x = cand_x(nkey) + kMinBorder;             // this keypoint's (staged one iteration ago)
+        const float2 ab = rec_ab[warp][si];
+        const float a = ab.x, b = ab.y;
+        const int dx = (int)nrec.w;                          // x - xa of this keypoint (its patch was staged one iteration ago)
         if (si + 1 < nslot) {                                // next keypoint's patch into the other buffer
-            nkey = __shfl_sync(0xffffffffu, my_key, si + 1);
-            nlevel = __shfl_sync(0xffffffffu, my_level, si + 1);
-            stage_patch<kStage>(patch_all[warp][(si + 1) & 1], blur, g.lv[nlevel], f, cand_x(nkey) + kMinBorder, cand_y(nkey) + kMinBorder, lane, &patch_bar[warp][(si + 1) & 1]);
+            nrec = rec_patch[warp][si + 1];
+            stage_patch<kStage>(patch_all[warp][(si + 1) & 1], rec_ptr(nrec), (int)nrec.z, lane, &patch_bar[warp][(si + 1) & 1]);
             if (kStage != 2) cp_async_wait<1>();
         } else {
             if (kStage != 2) cp_async_wait<0>();
         }
         if (kStage == 2) mbar_wait(&patch_bar[warp][si & 1], (si >> 1) & 1);   // buffer b is filled for keypoints b, b+2, ...: parity of its use count
         __syncwarp();
-        const int xa = (x - kPatchR) & patch_align_mask(kStage);
-        const uint8_t *pc = reinterpret_cast<const uint8_t *>(patch_all[warp][si & 1]) + kPatchR * kPatchPitch + (x - xa);   // patch centre
+        const uint8_t *pc = reinterpret_cast<const uint8_t *>(patch_all[warp][si & 1]) + kPatchR * kPatchPitch + dx;   // patch centre
         int val = 0;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
