@@ -214,7 +214,7 @@ static void staged_resize_tables(const LevelGeom &S, LevelGeom &L, std::vector<i
     L.rs_nbx = (chunks + L.rs_bw - 1) / L.rs_bw;
     L.rs_staged = S.h < 32768 ? 1 : 0;
     // Destination rows per block.  16 amortises the staged source rows best and wins for every level of a large batch (measured on
-    // 256 VGA frames: 0.174 ms with 16 rows everywhere, 0.183 with 8 rows on levels 5-7, 0.190 / 0.235 with 8 / 4 everywhere).  The
+    // 256 VGA frames: 0.174 ms with 16 rows everywhere, 0.180 with 32, 0.183 with 8 rows on levels 5-7, 0.190 / 0.235 with 8 / 4 everywhere).  The
     // handles of the low-latency path (batches of <= 8 frames, a handful of blocks per launch) are bound by the serial depth of a
     // thread instead: 4 rows per block cut the resize chain of one VGA frame from 46 to 32 us.
     {
@@ -913,7 +913,9 @@ extern "C" int orbx_extract_host_begin(orbx_extractor *ex, const uint8_t *imgs, 
     }
     // Chunked three-stream pipeline: the H2D copy of chunk c+1 and the D2H copy of chunk c-1 overlap
     // the kernels of chunk c (PCIe is full duplex; frames are independent).
-    int nchunks = nframes >= 64 ? 4 : (nframes >= 8 ? 2 : 1);
+    // (256 VGA frames, blocking call, final kernels of round 2: 3 / 4 / 5 / 6 / 8 chunks = 127 / 134 / 138 / 140 / 143 k frames/s: the tail behind the last
+    // upload is one chunk's kernels and download)
+    int nchunks = nframes >= 256 ? 8 : nframes >= 64 ? 4 : (nframes >= 8 ? 2 : 1);
     if (const char *e = std::getenv("ORBX_HOST_CHUNKS")) { const int v = std::atoi(e); if (v >= 1 && v <= orbx_extractor::kMaxChunks && v <= nframes) nchunks = v; }
     const size_t rbytes = (size_t)width * C;           // bytes per tight row
     const size_t fbytes = rbytes * height;

@@ -166,5 +166,24 @@ def test_config2_host_pipeline_256_frames_vs_oracle(orbx, oracle):
     ex.extract_host_end()
     kp = np.zeros((B, cap), orbx.KEYPOINT_DTYPE)
     kp.view(np.uint8).reshape(B, cap, 28)[:] = hk.numpy().view(np.uint8).reshape(B, cap, 28)
-    frames = list(range(0, B, 8)) + [63, 64, 65, 191, 192, 255]              # incl. the seams of the four host chunks
+    frames = list(range(0, B, 8)) + [31, 33, 63, 65, 95, 97, 191, 193, 223, 225, 255]     # incl. both sides of the seams of the eight host chunks
     _check_frames(oracle, imgs, frames, kp, hd.numpy(), hc.numpy())
+
+
+@pytest.mark.parametrize("nframes,chunks", [(37, 8), (37, 5), (70, 3), (9, 8)])
+def test_host_chunk_seams_with_ragged_batches(orbx, oracle, nframes, chunks, monkeypatch):
+    """orbx_extract_host with frame counts that do not divide into the chunk count (ORBX_HOST_CHUNKS is read per call): every
+    frame next to a chunk seam against the oracle, counts of all frames against a one-chunk run."""
+    W, H = 320, 240
+    imgs = np.ascontiguousarray(synth_batch(range(3000, 3000 + nframes), W, H))
+    ex = orbx.Extractor(max_width=W, max_height=H, max_batch=nframes)
+    monkeypatch.setenv("ORBX_HOST_CHUNKS", "1")
+    k1, d1, c1 = ex.extract_host(imgs)
+    monkeypatch.setenv("ORBX_HOST_CHUNKS", str(chunks))
+    kp, desc, counts = ex.extract_host(imgs)
+    assert np.array_equal(c1, counts)
+    for f in range(nframes):
+        n = int(counts[f])
+        assert np.array_equal(k1[f, :n], kp[f, :n]) and np.array_equal(d1[f, :n], desc[f, :n]), "frame %d differs between 1 and %d chunks" % (f, chunks)
+    seams = sorted({min(nframes - 1, max(0, nframes * c // chunks + d)) for c in range(chunks + 1) for d in (-1, 0)})
+    _check_frames(oracle, imgs, seams, kp, desc, counts)
