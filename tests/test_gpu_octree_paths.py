@@ -73,3 +73,28 @@ def test_score_ties_inside_nodes(orbx, oracle):
 def test_tiny_quota_and_single_level(orbx, oracle):
     _check(orbx, oracle, synth_frame(14), 10, nlevels=1)
     _check(orbx, oracle, synth_frame(15), 37, nlevels=3)
+
+
+def test_sequential_form_in_a_fresh_process():
+    """ORBX_OCT_CLOSED=0 (read once per process) switches the closed form off: the sequential partition passes, which inputs
+    whose phase 1 outruns the counted prefixes fall back to, must give the same survivors on ordinary frames too."""
+    import os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "from oracle import oracle\n"
+        "from orbslam_in_practice_b200 import _lib as orbx\n"
+        "from orbslam_in_practice_b200.synth import synth_frame\n"
+        "for seed, nf in ((21, 1000), (22, 300)):\n"
+        "    img = synth_frame(seed)\n"
+        "    ex = orbx.Extractor(nfeatures=nf, max_width=640, max_height=480, max_batch=1)\n"
+        "    oex = oracle.OracleExtractor(nf, 1.2, 8, 20, 7)\n"
+        "    kps, desc, counts = ex.extract_host(img); ko, do = oex(img)\n"
+        "    assert int(counts[0]) == len(ko)\n"
+        "    for l in range(8):\n"
+        "        assert np.array_equal(ex.kept(0, l), oex.kept(l)), (seed, l)\n"
+        "print('sequential ok')\n" % root)
+    env = dict(os.environ, ORBX_OCT_CLOSED="0")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "sequential ok" in out.stdout, out.stdout + out.stderr
