@@ -84,11 +84,39 @@ k_level0(const __grid_constant__ Geo g, uint8_t *__restrict__ pyr, const uint8_t
             for (int j = 0; j < kCopyRows; ++j)
                 if (j < nrows) v[j] = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)reflect_fast(Y0 + j, L.h) * in_pitch + X0));
         }
+        // The first and the last chunk of a row also write the four reflected pixels beside it (one PRMT of the chunk's own
+        // bytes: pixel -k is pixel k, pixel w-1+k is pixel w-1-k).  ncu, round 2: the byte-gather path below ran for ONE lane in
+        // every warp of the launch -- the chunk that holds only border pixels -- and was more than half of this kernel's
+        // instructions (25 per row against 2 for an interior chunk).
+        const bool lb = B == kMinBlurBorder && X0 == 0, rb = B == kMinBlurBorder && X0 + 16 == L.w;
 #pragma unroll
         for (int j = 0; j < kCopyRows; ++j)
-            if (j < nrows) *reinterpret_cast<uint4 *>(dst + (size_t)j * L.pitch) = v[j];
+            if (j < nrows) {
+                uint8_t *d = dst + (size_t)j * L.pitch;
+                *reinterpret_cast<uint4 *>(d) = v[j];
+                if (lb) *reinterpret_cast<uint32_t *>(d - 4) = __byte_perm(v[j].x, v[j].y, 0x1234);
+                if (rb) *reinterpret_cast<uint32_t *>(d + 16) = __byte_perm(v[j].z, v[j].w, 0x3456);
+            }
         return;
     }
+    if (X0 >= 0 && X0 + 19 < L.w) {
+        // rows that are not 16-byte aligned (a 1241-px KITTI frame): five aligned words and four funnel shifts per row instead of
+        // sixteen byte loads (the 20-byte window stays inside the row, so nothing is read past the caller's buffer)
+        const bool lb = B == kMinBlurBorder && X0 == 0;
+        for (int j = 0; j < nrows; ++j) {
+            const uint8_t *a = src + (size_t)(rows_inside ? Y0 + j : reflect_fast(Y0 + j, L.h)) * in_pitch + X0;
+            const uint32_t sh = (uint32_t)((uintptr_t)a & 3) * 8u;
+            const uint32_t *a4 = reinterpret_cast<const uint32_t *>(a - ((uintptr_t)a & 3));
+            const uint32_t w0 = __ldg(a4), w1 = __ldg(a4 + 1), w2 = __ldg(a4 + 2), w3 = __ldg(a4 + 3), w4 = __ldg(a4 + 4);
+            const uint4 v = make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+            uint8_t *d = dst + (size_t)j * L.pitch;
+            *reinterpret_cast<uint4 *>(d) = v;
+            if (lb) *reinterpret_cast<uint32_t *>(d - 4) = __byte_perm(v.x, v.y, 0x1234);
+        }
+        return;
+    }
+    // chunks that hold nothing but the 4-px border are served by their neighbours above
+    if (B == kMinBlurBorder && L.w >= 20 && (X0 == -16 || (src_aligned && X0 == L.w && (L.w & 15) == 0))) return;
     // edge chunks (and unaligned sources): byte gathers at the reflected columns -- only for the 4-byte words that hold
     // at least one pixel of the bordered level (with the default 4-px border that is one word of an edge chunk, not four;
     // the other bytes of the chunk are padding nobody reads)
