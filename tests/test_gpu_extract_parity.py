@@ -425,3 +425,34 @@ def test_low_latency_graph_path_equals_stream_path(orbx, oracle):
     st.synchronize()
     kd = d_k.cpu().numpy().view(np.uint8).reshape(2, cap, 28).copy().view(oracle.KEYPOINT_DTYPE).reshape(2, cap)
     check(kd, d_d.cpu().numpy(), d_c.cpu().numpy(), [0, 1])
+
+
+@pytest.mark.parametrize("offset,pitch_pad,w,h", [(1, 0, 640, 480), (2, 3, 333, 250), (3, 5, 1241, 376), (5, 0, 96, 80), (0, 1, 640, 480)])
+def test_device_input_at_any_alignment(orbx, oracle, offset, pitch_pad, w, h):
+    """k_level0 reads source rows that are not 16-byte aligned as aligned words + funnel shifts: a device image at a byte offset
+    and with a row pitch that is no multiple of 4 must give the same pyramid (incl. the reflected border) and keypoints."""
+    import torch
+    img = synth_frame(77 + offset, w, h)
+    pitch = w + pitch_pad
+    buf = np.zeros(offset + pitch * h + 64, np.uint8)
+    buf[offset:offset + pitch * h].reshape(h, pitch)[:, :w] = img
+    buf[offset:offset + pitch * h].reshape(h, pitch)[:, w:] = 255           # the padding must never be read as pixels
+    d = torch.from_numpy(buf).cuda()
+    ex = orbx.Extractor(max_width=w, max_height=h, max_batch=1)
+    cap = ex.capacity
+    d_k = torch.zeros((1, cap, 7), dtype=torch.float32, device="cuda"); d_d = torch.zeros((1, cap, 32), dtype=torch.uint8, device="cuda")
+    d_c = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ex.extract_device(d.data_ptr() + offset, pitch, pitch * h, w, h, 1, d_k.data_ptr(), d_d.data_ptr(), d_c.data_ptr(), 0)
+    torch.cuda.synchronize()
+    oex = oracle.OracleExtractor()
+    ko, do = oex(img)
+    assert int(d_c.item()) == len(ko)
+    assert np.array_equal(ex.level(0, 0, border=19), oracle.reflect101_border(oex.level(0), 19))
+    for l in range(1, ex.nlevels):
+        assert np.array_equal(ex.level(0, l), oex.level(l)), "pyramid level %d differs" % l
+    kp = np.zeros(cap, orbx.KEYPOINT_DTYPE)
+    kp.view(np.uint8).reshape(cap, 28)[:] = d_k.cpu().numpy().view(np.uint8).reshape(cap, 28)
+    n = len(ko)
+    for fld in ("x", "y", "response", "octave"):
+        assert np.array_equal(kp[:n][fld], ko[fld])
+    assert np.array_equal(d_d.cpu().numpy()[0, :n], do)
