@@ -19,3 +19,4 @@ for f in range(32):
     r += [ex.retries(l) for l in range(8)]; c += [len(ex.candidates(l)) for l in range(8)]
 print('synth.py seeds 0..31: mean keypoints %.1f, min-threshold retry cells per level (mean)'%(k/32), (r/32).round(1).tolist(), 'candidates per level (mean)', (c/32).round(0).tolist())
 " > gpurun_out/r02_synth_coverage.txt 2>&1; cat gpurun_out/r02_synth_coverage.txt
+python tools/latency_probe.py > gpurun_out/r02_latency_final.log 2>&1; tail -4 gpurun_out/r02_latency_final.log
