@@ -53,6 +53,47 @@ k_level0(const __grid_constant__ Geo g, uint8_t *__restrict__ pyr, const uint8_t
     if (g.in_channels != 1) {
         // cvtColor(..2GRAY) fused into the level-0 pass (src/Tracking.cpp:57-70); OpenCV 8U fixed point, 15 bits
         const int C = g.in_channels, ro = g.in_rgb ? 0 : 2, bo = g.in_rgb ? 2 : 0;
+        if (src_aligned && X0 >= 0 && X0 + 15 < L.w && (C == 3 || C == 4)) {
+            // interior chunks of 16-byte aligned rows: the chunk's 48 / 64 source bytes as three / four 16-byte loads, a pixel's
+            // three products as two DP2A (16-bit weights x the pixel's bytes).  The byte-wise form below (three byte loads and
+            // two reflections per pixel) took 0.17 ms (RGB) / 0.45 ms (RGBA) per 256 VGA frames against 0.029 ms for gray input.
+            const uint32_t w01 = g.in_rgb ? (9798u | (19235u << 16)) : (3735u | (19235u << 16));   // weights of bytes 0, 1
+            const uint32_t w2 = g.in_rgb ? 3735u : 9798u;                                          // weight of byte 2 (byte 3: 0)
+            const bool lb = B == kMinBlurBorder && X0 == 0, rb = B == kMinBlurBorder && X0 + 16 == L.w;
+            for (int j = 0; j < nrows; ++j) {
+                const uint4 *row = reinterpret_cast<const uint4 *>(src + (size_t)reflect_fast(Y0 + j, L.h) * in_pitch + (size_t)X0 * C);
+                uint32_t px[16];
+                if (C == 4) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) { const uint4 t = __ldg(row + q); px[4 * q] = t.x; px[4 * q + 1] = t.y; px[4 * q + 2] = t.z; px[4 * q + 3] = t.w; }
+                } else {
+                    uint32_t wd[13];
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) { const uint4 t = __ldg(row + q); wd[4 * q] = t.x; wd[4 * q + 1] = t.y; wd[4 * q + 2] = t.z; wd[4 * q + 3] = t.w; }
+                    wd[12] = 0u;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) px[k] = __funnelshift_r(wd[(3 * k) >> 2], wd[((3 * k) >> 2) + 1], ((3 * k) & 3) * 8);
+                }
+                uint32_t w[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint32_t v = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t gray = __dp2a_hi(w2, px[4 * q + k], __dp2a_lo(w01, px[4 * q + k], 16384u)) >> 15;
+                        v |= gray << (8 * k);
+                    }
+                    w[q] = v;
+                }
+                uint8_t *d = dst + (size_t)j * L.pitch;
+                *reinterpret_cast<uint4 *>(d) = make_uint4(w[0], w[1], w[2], w[3]);
+                if (lb) *reinterpret_cast<uint32_t *>(d - 4) = __byte_perm(w[0], w[1], 0x1234);
+                if (rb) *reinterpret_cast<uint32_t *>(d + 16) = __byte_perm(w[2], w[3], 0x3456);
+            }
+            return;
+        }
+        // chunks that hold nothing but the 4-px border are served by their neighbours above
+        if (src_aligned && (C == 3 || C == 4) && B == kMinBlurBorder && L.w >= 16 && (X0 == -16 || (X0 == L.w && (L.w & 15) == 0))) return;
         for (int j = 0; j < nrows; ++j) {
             const uint8_t *row = src + (size_t)reflect_fast(Y0 + j, L.h) * in_pitch;
             uint32_t w[4];
